@@ -1,0 +1,202 @@
+"""ctypes binding of librtmodt_b200.so (the C ABI declared in include/rtmodt_b200.h).
+
+There is no CPU fallback: if the library is missing or no sm_100 device is present, every
+compute entry point raises.  PyTorch is used only for device memory and CUDA streams.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "librtmodt_b200.so")
+
+RTM_F32, RTM_F16, RTM_BF16 = 0, 1, 2
+STATUS_TRACK_OVERFLOW, STATUS_DET_OVERFLOW, STATUS_CAND_OVERFLOW = 1, 2, 4
+STATUS_EVENT_OVERFLOW, STATUS_ZONE_LIMIT = 8, 16
+DET_NONE, DET_STAGE1, DET_STAGE2, DET_BIRTH = 0, 1, 2, 3
+MAX_ZONES_PER_STREAM = 64
+
+_STATUS_TEXT = {
+    STATUS_TRACK_OVERFLOW: "live tracks exceed the track table capacity (raise max_tracks)",
+    STATUS_DET_OVERFLOW: "more detections than detection slots (raise max_dets)",
+    STATUS_CAND_OVERFLOW: "NMS candidates exceed the workspace capacity",
+    STATUS_EVENT_OVERFLOW: "zone events of one step exceed the event buffer (raise max_events)",
+    STATUS_ZONE_LIMIT: f"a stream has more than {MAX_ZONES_PER_STREAM} zones",
+}
+
+i32p = C.POINTER(C.c_int32)
+f32p = C.POINTER(C.c_float)
+f64p = C.POINTER(C.c_double)
+u8p = C.POINTER(C.c_uint8)
+
+
+class RtmError(RuntimeError):
+    """An rtm_* entry point returned an error code."""
+
+
+class NmsParams(C.Structure):
+    _fields_ = [("iou_thres", C.c_double), ("conf_thres", C.c_float), ("max_det", C.c_int32),
+                ("agnostic", C.c_int32), ("num_classes", C.c_int32), ("class_mask", C.c_uint32 * 8)]
+
+
+class TrackTable(C.Structure):
+    _fields_ = [("num_streams", C.c_int32), ("capacity", C.c_int32), ("count", C.c_void_p),
+                ("next_id", C.c_void_p), ("track_id", C.c_void_p), ("xyxy", C.c_void_p),
+                ("confidence", C.c_void_p), ("class_id", C.c_void_p), ("age", C.c_void_p),
+                ("time_since_update", C.c_void_p)]
+
+
+class ZoneSet(C.Structure):
+    _fields_ = [("num_streams", C.c_int32), ("num_columns", C.c_int32), ("zone_offsets", C.c_void_p),
+                ("poly_offsets", C.c_void_p), ("poly_xy", C.c_void_p), ("dwell_sec", C.c_void_p),
+                ("cooldown_sec", C.c_void_p), ("column", C.c_void_p)]
+
+
+class ZoneState(C.Structure):
+    _fields_ = [("first_seen", C.c_void_p), ("last_alert", C.c_void_p)]
+
+
+class ZoneEventRec(C.Structure):
+    _fields_ = [("stream", C.c_int32), ("frame_id", C.c_int32), ("track_id", C.c_int32),
+                ("zone", C.c_int32), ("class_id", C.c_int32), ("cx", C.c_int32), ("cy", C.c_int32),
+                ("row", C.c_int32), ("dwell", C.c_double), ("now", C.c_double), ("xyxy", C.c_float * 4)]
+
+
+#: numpy view of rtm_zone_event (64 bytes)
+EVENT_DTYPE = [("stream", "<i4"), ("frame_id", "<i4"), ("track_id", "<i4"), ("zone", "<i4"),
+               ("class_id", "<i4"), ("cx", "<i4"), ("cy", "<i4"), ("row", "<i4"), ("dwell", "<f8"),
+               ("now", "<f8"), ("xyxy", "<f4", (4,))]
+
+
+class StepIO(C.Structure):
+    _fields_ = [
+        ("head_p3", C.c_void_p), ("head_p4", C.c_void_p), ("head_p5", C.c_void_p),
+        ("head_dtype", C.c_int32), ("img_h", C.c_int32), ("img_w", C.c_int32),
+        ("scale", C.c_void_p), ("det_xyxy", C.c_void_p), ("det_conf", C.c_void_p),
+        ("det_cls", C.c_void_p), ("det_anchor", C.c_void_p), ("det_keep", C.c_void_p),
+        ("det_count", C.c_void_p), ("det_stride", C.c_int32), ("workspace", C.c_void_p),
+        ("workspace_bytes", C.c_size_t),
+        ("table_in", C.POINTER(TrackTable)), ("table_out", C.POINTER(TrackTable)),
+        ("track_thresh", C.c_float), ("match_thresh", C.c_float), ("track_buffer", C.c_int32),
+        ("det_track_id", C.c_void_p), ("det_kind", C.c_void_p), ("src_row", C.c_void_p),
+        ("zones", C.POINTER(ZoneSet)), ("state_in", C.POINTER(ZoneState)),
+        ("state_out", C.POINTER(ZoneState)), ("now", C.c_double), ("now_per_stream", C.c_void_p),
+        ("frame_id", C.c_int32), ("events", C.c_void_p), ("event_stride", C.c_int32),
+        ("event_count", C.c_void_p), ("status", C.c_void_p),
+    ]
+
+
+class StepHostIO(C.Structure):
+    _fields_ = [("host_head_p3", C.c_void_p), ("host_head_p4", C.c_void_p), ("host_head_p5", C.c_void_p),
+                ("host_events", C.c_void_p), ("host_event_count", C.c_void_p),
+                ("host_det_xyxy", C.c_void_p), ("host_det_conf", C.c_void_p),
+                ("host_det_cls", C.c_void_p), ("host_det_track_id", C.c_void_p),
+                ("host_det_count", C.c_void_p), ("host_status", C.c_void_p),
+                ("wait_event", C.c_void_p), ("done_event", C.c_void_p)]
+
+
+#: every symbol include/rtmodt_b200.h declares: name -> (restype, argtypes)
+SIGNATURES = {
+    "rtm_version": (C.c_int, []),
+    "rtm_last_error": (C.c_char_p, []),
+    "rtm_device_info": (C.c_int, [i32p, i32p, i32p]),
+    "rtm_letterbox": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64,
+                                C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "rtm_nms_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "rtm_decode_nms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                 C.c_int32, C.POINTER(NmsParams), C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                 C.c_void_p, C.c_size_t, C.c_void_p]),
+    "rtm_nms_pred": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(NmsParams), C.c_void_p,
+                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                               C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "rtm_decode_head": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                  C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "rtm_track_step": (C.c_int, [C.POINTER(TrackTable), C.POINTER(TrackTable), C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_int32,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rtm_zone_step": (C.c_int, [C.POINTER(ZoneSet), C.POINTER(TrackTable), C.c_void_p,
+                                C.POINTER(ZoneState), C.POINTER(ZoneState), C.c_double, C.c_void_p,
+                                C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rtm_post_backbone_step": (C.c_int, [C.POINTER(StepIO), C.POINTER(NmsParams), C.c_void_p]),
+    "rtm_post_backbone_step_host": (C.c_int, [C.POINTER(StepIO), C.POINTER(StepHostIO),
+                                              C.POINTER(NmsParams), C.c_void_p]),
+}
+
+_lib = None
+
+
+def load_library(path: str = LIB_PATH):
+    """dlopen the library and type every declared symbol (no CUDA call is made)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(path):
+        raise RtmError(f"{path} is missing: build it with `python __graft_entry__.py` (nvcc, sm_100a). "
+                       "There is no CPU fallback.")
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here = header / library mismatch
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def lib():
+    """The loaded library, after checking that a CUDA device is usable."""
+    import torch
+    if not torch.cuda.is_available():
+        raise RtmError("rtmodt_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return load_library()
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise RtmError(f"rtm call failed ({rc}): {load_library().rtm_last_error().decode()}")
+
+
+def raise_on_status(status_host, what: str = "") -> None:
+    """Turn non-zero per-stream status words (host numpy / list) into an exception."""
+    import numpy as np
+    st = np.asarray(status_host)
+    if not st.any():
+        return
+    bits = int(np.bitwise_or.reduce(st.reshape(-1)))
+    msgs = [t for b, t in _STATUS_TEXT.items() if bits & b]
+    streams = np.flatnonzero(st.reshape(-1))[:8].tolist()
+    raise RtmError(f"{what}: {'; '.join(msgs)} (streams {streams})")
+
+
+def ptr(t) -> int:
+    """Device (or pinned host) address of a torch tensor, None -> NULL."""
+    return None if t is None else t.data_ptr()
+
+
+def cuda_stream() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def dtype_code(torch_dtype) -> int:
+    import torch
+    try:
+        return {torch.float32: RTM_F32, torch.float16: RTM_F16, torch.bfloat16: RTM_BF16}[torch_dtype]
+    except KeyError:
+        raise TypeError(f"unsupported tensor dtype {torch_dtype}") from None
+
+
+def make_nms_params(conf=0.35, iou=0.45, max_det=100, agnostic=False, classes=None, num_classes=80):
+    p = NmsParams()
+    p.iou_thres, p.conf_thres, p.max_det = float(iou), float(conf), int(max_det)
+    p.agnostic, p.num_classes = int(bool(agnostic)), int(num_classes)
+    mask = [0] * 8
+    wanted = range(num_classes) if classes is None else classes
+    for c in wanted:
+        c = int(c)
+        if 0 <= c < 256:
+            mask[c >> 5] |= 1 << (c & 31)
+    for k in range(8):
+        p.class_mask[k] = mask[k]
+    return p

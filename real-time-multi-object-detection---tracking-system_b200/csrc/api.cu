@@ -1,0 +1,112 @@
+// Library-level entry points: version, error string, device info, and the fused
+// post-backbone step (device-resident and host-fed variants).
+#include <stdarg.h>
+#include <string.h>
+
+#include "rtm_common.cuh"
+
+namespace rtm {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+int sm_count() {
+  static int cached = 0;
+  if (!cached) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return cached;
+}
+
+}  // namespace rtm
+
+extern "C" int rtm_version(void) { return RTM_VERSION; }
+
+extern "C" const char* rtm_last_error(void) { return rtm::g_error; }
+
+extern "C" int rtm_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor) {
+  int dev = 0, sms = 0, major = 0, minor = 0;
+  RTM_CUDA(cudaGetDevice(&dev));
+  RTM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  RTM_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  RTM_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  if (sm_count) *sm_count = sms;
+  if (cc_major) *cc_major = major;
+  if (cc_minor) *cc_minor = minor;
+  if (major != 10) {
+    rtm::set_error("librtmodt_b200 is built for sm_100a only; device %d is sm_%d%d", dev, major, minor);
+    return RTM_ERR_UNSUPPORTED;
+  }
+  return RTM_OK;
+}
+
+extern "C" int rtm_post_backbone_step(const rtm_step_io* io, const rtm_nms_params* params,
+                                      rtm_cuda_stream stream) {
+  RTM_REQUIRE(io && params, "rtm_post_backbone_step: null argument");
+  RTM_REQUIRE(io->table_in && io->table_out, "rtm_post_backbone_step: null track table");
+  const int B = io->table_in->num_streams;
+  int rc = rtm_decode_nms(io->head_p3, io->head_p4, io->head_p5, io->head_dtype, B, io->img_h, io->img_w,
+                          params, io->scale, io->det_xyxy, io->det_conf, io->det_cls, io->det_anchor,
+                          io->det_keep, io->det_count, io->det_stride, io->status, io->workspace,
+                          io->workspace_bytes, stream);
+  if (rc) return rc;
+  rc = rtm_track_step(io->table_in, io->table_out, io->det_xyxy, io->det_conf, io->det_cls, io->det_count,
+                      io->det_stride, io->track_thresh, io->match_thresh, io->track_buffer, io->det_track_id,
+                      io->det_kind, io->src_row, io->status, stream);
+  if (rc) return rc;
+  if (!io->zones) return RTM_OK;
+  return rtm_zone_step(io->zones, io->table_out, io->src_row, io->state_in, io->state_out, io->now,
+                       io->now_per_stream, io->frame_id, io->events, io->event_stride, io->event_count,
+                       io->status, stream);
+}
+
+namespace {
+
+size_t elem_size(int dtype) { return dtype == RTM_F32 ? 4 : 2; }
+
+}  // namespace
+
+extern "C" int rtm_post_backbone_step_host(const rtm_step_io* io, const rtm_step_host_io* h,
+                                           const rtm_nms_params* params, rtm_cuda_stream stream) {
+  RTM_REQUIRE(io && h && params, "rtm_post_backbone_step_host: null argument");
+  RTM_REQUIRE(h->host_head_p3 && h->host_head_p4 && h->host_head_p5, "rtm_post_backbone_step_host: null host head");
+  RTM_REQUIRE(io->table_in, "rtm_post_backbone_step_host: null track table");
+  RTM_REQUIRE(io->img_h > 0 && io->img_w > 0 && io->img_h % 32 == 0 && io->img_w % 32 == 0,
+              "rtm_post_backbone_step_host: bad image size");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t B = io->table_in->num_streams;
+  const size_t ch = 64 + params->num_classes, es = elem_size(io->head_dtype);
+  const void* src[3] = {h->host_head_p3, h->host_head_p4, h->host_head_p5};
+  void* dst[3] = {const_cast<void*>(io->head_p3), const_cast<void*>(io->head_p4), const_cast<void*>(io->head_p5)};
+  const int strides[3] = {8, 16, 32};
+  for (int l = 0; l < 3; ++l) {
+    const size_t hw = static_cast<size_t>(io->img_h / strides[l]) * (io->img_w / strides[l]);
+    RTM_CUDA(cudaMemcpyAsync(dst[l], src[l], B * ch * hw * es, cudaMemcpyHostToDevice, s));
+  }
+  if (h->wait_event) RTM_CUDA(cudaStreamWaitEvent(s, static_cast<cudaEvent_t>(h->wait_event), 0));
+  int rc = rtm_post_backbone_step(io, params, stream);
+  if (rc) return rc;
+  const size_t D = static_cast<size_t>(io->det_stride);
+  if (io->zones && h->host_events && h->host_event_count) {
+    RTM_CUDA(cudaMemcpyAsync(h->host_event_count, io->event_count, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    RTM_CUDA(cudaMemcpyAsync(h->host_events, io->events, B * io->event_stride * sizeof(rtm_zone_event),
+                             cudaMemcpyDeviceToHost, s));
+  }
+  if (h->host_det_count) RTM_CUDA(cudaMemcpyAsync(h->host_det_count, io->det_count, B * 4, cudaMemcpyDeviceToHost, s));
+  if (h->host_det_xyxy) RTM_CUDA(cudaMemcpyAsync(h->host_det_xyxy, io->det_xyxy, B * D * 16, cudaMemcpyDeviceToHost, s));
+  if (h->host_det_conf) RTM_CUDA(cudaMemcpyAsync(h->host_det_conf, io->det_conf, B * D * 4, cudaMemcpyDeviceToHost, s));
+  if (h->host_det_cls) RTM_CUDA(cudaMemcpyAsync(h->host_det_cls, io->det_cls, B * D * 4, cudaMemcpyDeviceToHost, s));
+  if (h->host_det_track_id && io->det_track_id)
+    RTM_CUDA(cudaMemcpyAsync(h->host_det_track_id, io->det_track_id, B * D * 4, cudaMemcpyDeviceToHost, s));
+  if (h->host_status && io->status)
+    RTM_CUDA(cudaMemcpyAsync(h->host_status, io->status, B * 4, cudaMemcpyDeviceToHost, s));
+  if (h->done_event) RTM_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(h->done_event), s));
+  return RTM_OK;
+}

@@ -1,0 +1,197 @@
+// P1: letterbox + normalise (rtm_letterbox).
+//
+// Reproduces, per frame, what ultralytics' LetterBox(auto=False, scaleup=True, center=True)
+// followed by BasePredictor.preprocess do on the way into detector.py:100-111:
+//   cv2.resize(img, new_unpad, INTER_LINEAR)          8-bit path of OpenCV: 11-bit fixed-point
+//                                                     horizontal taps, then
+//                                                     ((b0*(S0>>4))>>16 + (b1*(S1>>4))>>16 + 2) >> 2
+//   cv2.copyMakeBorder(..., BORDER_CONSTANT, 114)     top/left = round(pad - 0.1)
+//   BGR -> RGB, HWC -> CHW, cast, / 255               division in float32, rounded once to the
+//                                                     output type (what torch does for half / bf16)
+// The 1080p -> 640x360 case lands exactly on source pixels (every third row and pixel, zero
+// second tap) and 720p -> 640x360 on the 2x2 box mean; both fall out of the general
+// fixed-point formula, so there is one code path.  Taps with zero weight are not loaded.
+//
+// Mapping: one thread produces 8 horizontally consecutive output pixels of all three
+// channel planes (three 16-byte stores for bf16/f16), so stores are fully coalesced; the
+// source rows are read through the read-only path.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <math.h>
+
+#include "rtm_common.cuh"
+
+namespace {
+
+constexpr int kPix = 8;  // output pixels per thread
+constexpr int kCoefBits = 11;
+
+struct LetterboxArgs {
+  const uint8_t* frames;
+  int src_h, src_w;
+  long long row_stride, frame_stride;
+  void* out;
+  int out_h, out_w;
+  int new_h, new_w, top, left;
+  double scale_x, scale_y;  // src / new, as cv::resize derives them (1 / inv_scale)
+  bool resize;              // false when the source already has the unpadded size
+};
+
+// OpenCV resize coordinate + fixed-point taps for one destination index.  Horizontally the
+// fraction is reset at the borders; vertically the weights are kept and the rows clipped
+// (cv::resize computes xofs/alpha and yofs/beta that way) - it matters only when up-scaling.
+template <bool HORIZONTAL>
+__device__ __forceinline__ void linear_tap(int d, double scale, int ssize, int* s0, int* s1, int* c0, int* c1) {
+  float f = static_cast<float>(__dsub_rn(__dmul_rn(d + 0.5, scale), 0.5));  // no FMA contraction
+  int s = static_cast<int>(floorf(f));
+  f -= static_cast<float>(s);
+  if (HORIZONTAL) {
+    if (s < 0) {
+      s = 0;
+      f = 0.f;
+    }
+    if (s >= ssize - 1) {
+      s = ssize - 1;
+      f = 0.f;
+    }
+    *s0 = s;
+    *s1 = min(s + 1, ssize - 1);
+  } else {
+    *s0 = min(max(s, 0), ssize - 1);
+    *s1 = min(max(s + 1, 0), ssize - 1);
+  }
+  *c0 = __float2int_rn((1.f - f) * static_cast<float>(1 << kCoefBits));
+  *c1 = __float2int_rn(f * static_cast<float>(1 << kCoefBits));
+}
+
+template <typename T>
+__device__ __forceinline__ T from_u8(int v);
+template <>
+__device__ __forceinline__ float from_u8<float>(int v) {
+  return __fdiv_rn(static_cast<float>(v), 255.f);
+}
+template <>
+__device__ __forceinline__ __half from_u8<__half>(int v) {
+  return __float2half_rn(__fdiv_rn(static_cast<float>(v), 255.f));
+}
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_u8<__nv_bfloat16>(int v) {
+  return __float2bfloat16_rn(__fdiv_rn(static_cast<float>(v), 255.f));
+}
+
+template <typename T>
+struct alignas(sizeof(T) * kPix) OutPack {
+  T v[kPix];
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) letterbox_kernel(const LetterboxArgs a) {
+  const int groups_per_row = a.out_w / kPix;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= groups_per_row * a.out_h) return;
+  const int b = blockIdx.y;
+  const int oy = g / groups_per_row;
+  const int ox0 = (g - oy * groups_per_row) * kPix;
+  const uint8_t* frame = a.frames + static_cast<long long>(b) * a.frame_stride;
+
+  int px[3][kPix];  // [channel in RGB order][pixel]
+  const int ry = oy - a.top;
+  if (ry < 0 || ry >= a.new_h) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int e = 0; e < kPix; ++e) px[c][e] = 114;
+  } else {
+    int y0 = ry, y1 = ry, b0 = 1 << kCoefBits, b1 = 0;
+    if (a.resize) linear_tap<false>(ry, a.scale_y, a.src_h, &y0, &y1, &b0, &b1);
+    const uint8_t* r0 = frame + static_cast<long long>(y0) * a.row_stride;
+    const uint8_t* r1 = frame + static_cast<long long>(y1) * a.row_stride;
+#pragma unroll
+    for (int e = 0; e < kPix; ++e) {
+      const int rx = ox0 + e - a.left;
+      if (rx < 0 || rx >= a.new_w) {
+        px[0][e] = px[1][e] = px[2][e] = 114;
+        continue;
+      }
+      int x0 = rx, x1 = rx, a0 = 1 << kCoefBits, a1 = 0;
+      if (a.resize) linear_tap<true>(rx, a.scale_x, a.src_w, &x0, &x1, &a0, &a1);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {  // c: B, G, R in the source
+        int v;
+        if (!a.resize) {
+          v = __ldg(r0 + x0 * 3 + c);
+        } else {
+          int s0 = a0 * __ldg(r0 + x0 * 3 + c);
+          if (a1) s0 += a1 * __ldg(r0 + x1 * 3 + c);
+          int s1 = 0;
+          if (b1) {
+            s1 = a0 * __ldg(r1 + x0 * 3 + c);
+            if (a1) s1 += a1 * __ldg(r1 + x1 * 3 + c);
+          }
+          v = (((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2) >> 2;
+          v = min(max(v, 0), 255);
+        }
+        px[2 - c][e] = v;  // BGR -> RGB
+      }
+    }
+  }
+  T* out = static_cast<T*>(a.out) + (static_cast<long long>(b) * 3 * a.out_h + oy) * a.out_w + ox0;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    OutPack<T> p;
+#pragma unroll
+    for (int e = 0; e < kPix; ++e) p.v[e] = from_u8<T>(px[c][e]);
+    *reinterpret_cast<OutPack<T>*>(out + static_cast<long long>(c) * a.out_h * a.out_w) = p;
+  }
+}
+
+}  // namespace
+
+extern "C" int rtm_letterbox(const uint8_t* frames, int32_t num_streams, int32_t src_h, int32_t src_w,
+                             int64_t row_stride, int64_t frame_stride, void* out, int32_t out_dtype,
+                             int32_t out_h, int32_t out_w, rtm_cuda_stream stream) {
+  RTM_REQUIRE(frames && out, "rtm_letterbox: null pointer");
+  RTM_REQUIRE(num_streams > 0 && src_h > 0 && src_w > 0 && out_h > 0 && out_w > 0, "rtm_letterbox: bad shape");
+  RTM_REQUIRE(out_w % kPix == 0, "rtm_letterbox: out_w %d must be a multiple of %d", out_w, kPix);
+  RTM_REQUIRE(row_stride >= 3ll * src_w && frame_stride >= row_stride * src_h, "rtm_letterbox: strides too small");
+  RTM_REQUIRE((reinterpret_cast<uintptr_t>(out) & 31) == 0, "rtm_letterbox: out must be 32-byte aligned");
+  LetterboxArgs a;
+  a.frames = frames;
+  a.src_h = src_h;
+  a.src_w = src_w;
+  a.row_stride = row_stride;
+  a.frame_stride = frame_stride;
+  a.out = out;
+  a.out_h = out_h;
+  a.out_w = out_w;
+  // LetterBox.__call__: r = min(H/h0, W/w0); new_unpad = round(w0*r), round(h0*r);
+  // dw, dh = (W - new_w)/2, (H - new_h)/2; top = round(dh - 0.1), left = round(dw - 0.1)
+  const double r = fmin(static_cast<double>(out_h) / src_h, static_cast<double>(out_w) / src_w);
+  a.new_w = static_cast<int>(nearbyint(src_w * r));  // Python round(): half to even
+  a.new_h = static_cast<int>(nearbyint(src_h * r));
+  RTM_REQUIRE(a.new_w >= 1 && a.new_h >= 1 && a.new_w <= out_w && a.new_h <= out_h, "rtm_letterbox: degenerate resize");
+  a.left = static_cast<int>(nearbyint((out_w - a.new_w) / 2.0 - 0.1));
+  a.top = static_cast<int>(nearbyint((out_h - a.new_h) / 2.0 - 0.1));
+  a.resize = !(a.new_w == src_w && a.new_h == src_h);
+  // cv::resize: inv_scale = dsize / ssize; scale = 1. / inv_scale
+  a.scale_x = 1.0 / (static_cast<double>(a.new_w) / src_w);
+  a.scale_y = 1.0 / (static_cast<double>(a.new_h) / src_h);
+  const int groups = (out_w / kPix) * out_h;
+  dim3 grid((groups + 255) / 256, num_streams);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (out_dtype) {
+    case RTM_F32:
+      letterbox_kernel<float><<<grid, 256, 0, s>>>(a);
+      break;
+    case RTM_F16:
+      letterbox_kernel<__half><<<grid, 256, 0, s>>>(a);
+      break;
+    case RTM_BF16:
+      letterbox_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(a);
+      break;
+    default:
+      RTM_REQUIRE(false, "rtm_letterbox: unknown out_dtype %d", out_dtype);
+  }
+  RTM_LAUNCH_CHECK("letterbox_kernel");
+  return RTM_OK;
+}

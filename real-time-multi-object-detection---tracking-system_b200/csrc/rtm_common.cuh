@@ -1,0 +1,82 @@
+// Shared helpers for the sm_100a kernels of librtmodt_b200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "rtmodt_b200.h"
+
+namespace rtm {
+
+// ---- error plumbing (host) ------------------------------------------------------------
+void set_error(const char* fmt, ...);
+
+#define RTM_REQUIRE(cond, ...)          \
+  do {                                  \
+    if (!(cond)) {                      \
+      ::rtm::set_error(__VA_ARGS__);    \
+      return RTM_ERR_INVALID;           \
+    }                                   \
+  } while (0)
+
+#define RTM_CUDA(call)                                                            \
+  do {                                                                            \
+    cudaError_t err__ = (call);                                                   \
+    if (err__ != cudaSuccess) {                                                   \
+      ::rtm::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), \
+                       __FILE__, __LINE__);                                       \
+      return RTM_ERR_CUDA;                                                        \
+    }                                                                             \
+  } while (0)
+
+#define RTM_LAUNCH_CHECK(name)                                                         \
+  do {                                                                                 \
+    cudaError_t err__ = cudaGetLastError();                                            \
+    if (err__ != cudaSuccess) {                                                        \
+      ::rtm::set_error("launch of %s failed: %s", name, cudaGetErrorString(err__));    \
+      return RTM_ERR_CUDA;                                                             \
+    }                                                                                  \
+  } while (0)
+
+int sm_count();  // cached multiProcessorCount of the current device
+
+// ---- device helpers -------------------------------------------------------------------
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+// Order-preserving compaction support: exclusive prefix of `flag` over the threads of the
+// block (thread order), plus the block total.  `scratch` holds 33 ints.
+// All threads of the block must call it; contains three __syncthreads().
+__device__ __forceinline__ int block_exclusive_count(bool flag, int* scratch, int* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+  const unsigned bal = __ballot_sync(kFull, flag);
+  const int within = __popc(bal & ((1u << lane) - 1u));
+  if (lane == 0) scratch[warp] = __popc(bal);
+  __syncthreads();
+  if (warp == 0) {
+    // nwarp <= 32: one warp scans the per-warp counts
+    int v = lane < nwarp ? scratch[lane] : 0;
+    int incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int o = __shfl_up_sync(kFull, incl, d);
+      if (lane >= d) incl += o;
+    }
+    if (lane < nwarp) scratch[lane] = incl - v;
+    if (lane == 31) scratch[32] = incl;
+  }
+  __syncthreads();
+  const int base = scratch[warp];
+  *total = scratch[32];
+  __syncthreads();  // scratch may be reused by the next call
+  return base + within;
+}
+
+// total order on floats as unsigned ints (ascending)
+__device__ __forceinline__ uint32_t float_orderable(float f) {
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+}  // namespace rtm

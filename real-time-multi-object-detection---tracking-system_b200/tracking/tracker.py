@@ -1,0 +1,149 @@
+"""Drop-in for ``src/tracking/tracker.py``: same classes, arguments, errors and quirks,
+with the association arithmetic on the GPU (``rtm_track_step``).
+
+Quirks kept on purpose, because parity is with the reference's behaviour, not with canonical
+ByteTrack:
+
+* ``MultiObjectTracker.update`` returns ``[]`` on every frame: the reference ages every track
+  *after* resetting the matched ones and then filters on ``time_since_update == 0``
+  (tracker.py:138-147).  The tracks matched or born in the last frame are available from
+  :meth:`MultiObjectTracker.active_tracks` (``time_since_update == 1``).
+* no Kalman filter, IoU >= ``match_thresh`` in both stages, class-agnostic matching,
+  empty frames never prune (tracker.py:70-73).
+* the state the reference keeps in ``tracker._core._tracks`` / ``_next_id`` is readable here
+  under the same names (copied from the device on access).
+
+One instance tracks one stream (B = 1 slab of :class:`~..streams.DeviceTrackTable`); the
+batched product path is :class:`~..streams.StreamBatch`.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from collections import defaultdict
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from .. import _lib
+from ..streams import DeviceTrackTable, stream_tracks
+
+
+@dataclass
+class Track:
+    """Represents a single tracked object (tracker.py:27-37)."""
+    track_id: int
+    xyxy: np.ndarray
+    confidence: float
+    class_id: int
+    class_name: str = ""
+    age: int = 0
+    time_since_update: int = 0
+    trail: list = field(default_factory=list)
+
+
+class _ByteTrackCore:
+    """Device-resident counterpart of the reference's ``_ByteTrackCore`` (tracker.py:43-194)."""
+
+    def __init__(self, track_thresh: float = 0.5, track_buffer: int = 30, match_thresh: float = 0.8,
+                 max_tracks: int = 1024, max_dets: int = 256, device="cuda:0") -> None:
+        import torch
+        self.track_thresh, self.track_buffer, self.match_thresh = track_thresh, track_buffer, match_thresh
+        self._lib = _lib.lib()
+        self.device = torch.device(device)
+        self.max_dets = int(max_dets)
+        with torch.cuda.device(self.device):
+            self._tables = [DeviceTrackTable(1, max_tracks, self.device) for _ in range(2)]
+            self._cur = 0
+            self._det_xyxy = torch.zeros(1, self.max_dets, 4, dtype=torch.float32, device=self.device)
+            self._det_conf = torch.zeros(1, self.max_dets, dtype=torch.float32, device=self.device)
+            self._det_cls = torch.zeros(1, self.max_dets, dtype=torch.int32, device=self.device)
+            self._det_count = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self._det_tid = torch.zeros(1, self.max_dets, dtype=torch.int32, device=self.device)
+            self._det_kind = torch.zeros(1, self.max_dets, dtype=torch.int32, device=self.device)
+            self._src_row = torch.zeros(1, max_tracks, dtype=torch.int32, device=self.device)
+            self._status = torch.zeros(1, dtype=torch.int32, device=self.device)
+
+    # -- the reference's attribute names ------------------------------------
+    @property
+    def _tracks(self) -> list:
+        return stream_tracks(self._tables[self._cur].to_host(), 0)
+
+    @property
+    def _next_id(self) -> int:
+        return int(self._tables[self._cur].next_id.cpu()[0])
+
+    def update(self, xyxy: np.ndarray, confidence: np.ndarray, class_id: np.ndarray) -> list:
+        """One tracking step (tracker.py:58-141).  Returns the reference's (empty) list."""
+        import torch
+        n = len(confidence)
+        if n > self.max_dets:
+            raise _lib.RtmError(f"{n} detections > max_dets={self.max_dets}")
+        with torch.cuda.device(self.device):
+            if n:
+                self._det_xyxy[0, :n] = torch.as_tensor(np.ascontiguousarray(xyxy, np.float32).reshape(n, 4)).to(self.device)
+                self._det_conf[0, :n] = torch.as_tensor(np.ascontiguousarray(confidence, np.float32)).to(self.device)
+                self._det_cls[0, :n] = torch.as_tensor(np.ascontiguousarray(class_id, np.int32)).to(self.device)
+            self._det_count.fill_(n)
+            tin, tout = self._tables[self._cur], self._tables[self._cur ^ 1]
+            _lib.check(self._lib.rtm_track_step(
+                C.byref(tin.struct), C.byref(tout.struct), self._det_xyxy.data_ptr(),
+                self._det_conf.data_ptr(), self._det_cls.data_ptr(), self._det_count.data_ptr(),
+                self.max_dets, float(self.track_thresh), float(self.match_thresh), int(self.track_buffer),
+                self._det_tid.data_ptr(), self._det_kind.data_ptr(), self._src_row.data_ptr(),
+                self._status.data_ptr(), _lib.cuda_stream()))
+            self._cur ^= 1
+            self._last_n = n
+        _lib.raise_on_status(self._status.cpu().numpy(), "MultiObjectTracker")
+        # the reference filters on time_since_update == 0 AFTER ageing every track, so nothing
+        # ever qualifies (tracker.py:141, 144-147)
+        return []
+
+    def assignments(self):
+        """(track_id, kind) per detection of the last update (RTM_DET_* kinds)."""
+        n = self._last_n
+        return self._det_tid.cpu().numpy()[0, :n], self._det_kind.cpu().numpy()[0, :n]
+
+
+class MultiObjectTracker:
+    """High-level tracker wrapping ByteTrack (tracker.py:200-259)."""
+
+    def __init__(self, algorithm: str = "bytetrack", **kwargs) -> None:
+        self.algorithm = algorithm.lower()
+        if self.algorithm == "bytetrack":
+            bt_params = kwargs.get("bytetrack", kwargs)           # nested or flat, tracker.py:206
+            extra = {k: kwargs[k] for k in ("max_tracks", "max_dets", "device") if k in kwargs}
+            self._core = _ByteTrackCore(track_thresh=bt_params.get("track_thresh", 0.5),
+                                        track_buffer=bt_params.get("track_buffer", 30),
+                                        match_thresh=bt_params.get("match_thresh", 0.8), **extra)
+        elif self.algorithm == "deepsort":
+            raise NotImplementedError("DeepSORT adapter not yet wired. Use bytetrack.")
+        else:
+            raise ValueError(f"Unknown tracker: {self.algorithm}")
+        self._trail_map = defaultdict(list)
+        self._trail_maxlen = 30
+
+    def update(self, detections) -> list:
+        """``detections`` needs ``.xyxy``, ``.confidence``, ``.class_id`` (tracker.py:234-238)."""
+        raw = self._core.update(detections.xyxy, detections.confidence, detections.class_id)
+        return self._wrap(raw)
+
+    def active_tracks(self) -> list:
+        """Tracks matched or born in the last frame (``time_since_update == 1``), as ``Track``
+        objects with trails - what a caller of the reference presumably wanted from update()."""
+        return self._wrap([t for t in self._core._tracks if t["time_since_update"] == 1])
+
+    def _wrap(self, raw) -> list:
+        tracks = []
+        for r in raw:                                             # tracker.py:241-258
+            tid = r["track_id"]
+            cx = int((r["xyxy"][0] + r["xyxy"][2]) / 2)
+            cy = int((r["xyxy"][1] + r["xyxy"][3]) / 2)
+            trail = self._trail_map[tid]
+            trail.append((cx, cy))
+            if len(trail) > self._trail_maxlen:
+                trail.pop(0)
+            tracks.append(Track(track_id=tid, xyxy=r["xyxy"], confidence=r["confidence"],
+                                class_id=r["class_id"], age=r["age"],
+                                time_since_update=r["time_since_update"], trail=list(trail)))
+        return tracks

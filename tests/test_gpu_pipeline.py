@@ -1,0 +1,94 @@
+"""The fused post-backbone step (rtm_post_backbone_step) against the oracle chain."""
+
+import numpy as np
+import pytest
+
+from oracle import detect_ref, tracker_ref, zone_ref
+
+pytestmark = pytest.mark.gpu
+
+WANTED = [0, 1, 2, 3, 5, 7]
+
+
+def moving_heads(pkg, B, F, seed, n_obj=12):
+    """F frames of planted head tensors whose objects move slowly (letterbox coordinates)."""
+    rng = np.random.default_rng(seed)
+    frames = []
+    wh = np.stack([rng.uniform(60, 150, (B, n_obj)), rng.uniform(80, 200, (B, n_obj))], -1)
+    c = np.stack([rng.uniform(100, 540, (B, n_obj)), rng.uniform(200, 440, (B, n_obj))], -1)
+    v = rng.uniform(-1.5, 1.5, (B, n_obj, 2))
+    cls = rng.choice(np.asarray(WANTED), (B, n_obj))
+    for f in range(F):
+        c = c + v
+        levels = [[], [], []]
+        for b in range(B):
+            boxes = np.concatenate([c[b] - wh[b] / 2, c[b] + wh[b] / 2], 1)
+            for l, t in enumerate(pkg.synth.plant_head(rng, boxes, cls[b], distractor_frac=0.0)):
+                levels[l].append(t)
+        frames.append([np.stack(l) for l in levels])
+    return frames
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_fused_step_matches_oracle_chain(pkg, dtype):
+    import torch
+    B, F = 4, 25
+    tdt = {"f32": torch.float32, "bf16": torch.bfloat16}[dtype]
+    zones = [pkg.synth.make_zones(seed=b, num_zones=4, width=1920, height=1080, dwell_time_sec=0.2, cooldown_sec=0.4)
+             for b in range(B)]
+    sb = pkg.StreamBatch(B, zones, src_hw=(1080, 1920), classes=WANTED, max_tracks=256)
+    trk = [tracker_ref.TrackerOracle() for _ in range(B)]
+    zon = [zone_ref.ZoneOracle(z) for z in zones]
+    n_events = 0
+    for f, heads in enumerate(moving_heads(pkg, B, F, seed=4)):
+        ht = [torch.from_numpy(h).to(tdt) for h in heads]
+        now = 50.0 + f / 30.0
+        sb.step([h.to(sb.device).contiguous() for h in ht], now=now, frame_id=f)
+        got_det = sb.read_detections()
+        got_trk, got_next = sb.read_tracks()
+        got_ev = sb.read_events()
+        ref_det = detect_ref.detect_post([h.float() for h in ht], (1080, 1920), classes=WANTED)
+        for b in range(B):
+            r = ref_det[b]
+            assert len(r["conf"]) == len(got_det[b]["confidence"]) > 0
+            np.testing.assert_array_equal(got_det[b]["anchor"], r["anchor"])
+            np.testing.assert_array_equal(got_det[b]["class_id"], r["cls"])
+            np.testing.assert_allclose(got_det[b]["xyxy"], r["xyxy"], rtol=1e-4, atol=1e-2)
+            # the tracker / zone oracles consume the DEVICE detections, so that the stages after the
+            # (tolerance-checked) float decode are compared bit for bit
+            tid, kind = trk[b].step(got_det[b]["xyxy"], got_det[b]["confidence"], got_det[b]["class_id"])
+            np.testing.assert_array_equal(got_det[b]["track_id"], tid)
+            np.testing.assert_array_equal(got_det[b]["kind"], kind)
+            o = trk[b]
+            assert int(got_next[b]) == o.next_id
+            assert [t["track_id"] for t in got_trk[b]] == o.track_id.tolist()
+            np.testing.assert_array_equal(np.array([t["xyxy"] for t in got_trk[b]], np.float32).reshape(-1, 4), o.xyxy)
+            assert [t["time_since_update"] for t in got_trk[b]] == o.tsu.tolist()
+            assert [t["age"] for t in got_trk[b]] == o.age.tolist()
+            act = o.active_rows()
+            exp_ev = zon[b].process(zip(o.track_id[act], o.xyxy[act], o.cls[act]), f, now)
+            assert [(e.track_id, e.zone_name, e.centroid, e.dwell_time_sec, e.bbox_xyxy, e.frame_id) for e in got_ev[b]] == \
+                   [(e.track_id, e.zone_name, e.centroid, e.dwell_time_sec, e.bbox_xyxy, e.frame_id) for e in exp_ev]
+            n_events += len(exp_ev)
+    assert n_events > 0
+
+
+def test_host_fed_step_equals_device_step(pkg):
+    """rtm_post_backbone_step_host (pinned host heads in, events out) == the device-resident step."""
+    import torch
+    B, F = 3, 6
+    zones = [pkg.synth.make_zones(seed=b, num_zones=3, width=1920, height=1080, dwell_time_sec=0.0, cooldown_sec=0.1)
+             for b in range(B)]
+    a = pkg.StreamBatch(B, zones, classes=WANTED, max_tracks=128)
+    h = pkg.StreamBatch(B, zones, classes=WANTED, max_tracks=128)
+    feeder = pkg.HostFeeder(h, torch.bfloat16)
+    for f, heads in enumerate(moving_heads(pkg, B, F, seed=9)):
+        ht = [torch.from_numpy(x).to(torch.bfloat16) for x in heads]
+        a.step([x.to(a.device).contiguous() for x in ht], now=10.0 + f, frame_id=f)
+        res = feeder.step(ht, now=10.0 + f, frame_id=f)
+        ev_a = a.read_events()
+        ev_h = res.events()
+        assert [[(e.track_id, e.zone_name, e.centroid, e.bbox_xyxy) for e in s] for s in ev_a] == \
+               [[(e.track_id, e.zone_name, e.centroid, e.bbox_xyxy) for e in s] for s in ev_h]
+        np.testing.assert_array_equal(res.det_count, a.det_count.cpu().numpy())
+    assert sum(len(s) for s in ev_a) >= 0

@@ -1,0 +1,123 @@
+"""rtm_track_step against the reference's golden state and against the oracle (bit-exact)."""
+
+import numpy as np
+import pytest
+
+from conftest import golden_clip, golden_state, load_golden
+from oracle import tracker_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def assert_state_equal(tracks, next_id, ref_state, ref_next):
+    assert next_id == ref_next
+    assert [t["track_id"] for t in tracks] == ref_state["track_id"].tolist()
+    np.testing.assert_array_equal(np.array([t["xyxy"] for t in tracks], np.float32).reshape(-1, 4), ref_state["xyxy"])
+    np.testing.assert_array_equal(np.array([t["confidence"] for t in tracks], np.float64), np.asarray(ref_state["conf"], np.float64))
+    assert [t["class_id"] for t in tracks] == ref_state["cls"].tolist()
+    assert [t["age"] for t in tracks] == ref_state["age"].tolist()
+    assert [t["time_since_update"] for t in tracks] == ref_state["tsu"].tolist()
+
+
+@pytest.mark.parametrize("name", ["cfg1_clip.npz", "crowd_clip.npz", "gaps_clip.npz", "churn_clip.npz"])
+def test_facade_replays_reference_golden(pkg, name):
+    g = load_golden(name)
+    kw = dict(track_thresh=0.5, track_buffer=int(g.get("track_buffer", 30)), match_thresh=float(g.get("match_thresh", 0.8)))
+    trk = pkg.MultiObjectTracker("bytetrack", bytetrack=dict(kw, mot20=False), max_tracks=512, max_dets=128)
+    import types
+    for f, (xyxy, conf, cls) in enumerate(golden_clip(g)):
+        out = trk.update(types.SimpleNamespace(xyxy=xyxy, confidence=conf, class_id=cls))
+        assert out == []
+        assert_state_equal(trk._core._tracks, trk._core._next_id, golden_state(g, f), int(g["next_id"][f]))
+
+
+def run_batch_against_oracle(pkg, B, F, slots, clip_kw, max_tracks, seed=100, track_kw=None, check_every=1):
+    import torch
+    track_kw = track_kw or {}
+    xyxy, conf, cls, count = pkg.synth.scripted_batch(B, F, slots, seed=seed, **clip_kw)
+    sb = pkg.StreamBatch(B, None, max_det=slots, max_tracks=max_tracks, **track_kw)
+    oracles = [tracker_ref.TrackerOracle(**track_kw) for _ in range(B)]
+    dev = sb.device
+    for f in range(F):
+        sb.track_only(torch.from_numpy(xyxy[f]).to(dev), torch.from_numpy(conf[f]).to(dev),
+                      torch.from_numpy(cls[f]).to(dev), torch.from_numpy(count[f]).to(dev), now=f / 30.0)
+        exp = [o.step(xyxy[f, b, :count[f, b]], conf[f, b, :count[f, b]], cls[f, b, :count[f, b]])
+               for b, o in enumerate(oracles)]
+        if f % check_every and f != F - 1:
+            continue
+        tracks, next_id = sb.read_tracks()
+        dets = sb.read_detections() if False else None
+        tid = sb.det_track_id.cpu().numpy()
+        kind = sb.det_kind.cpu().numpy()
+        for b, o in enumerate(oracles):
+            ref = dict(track_id=o.track_id, xyxy=o.xyxy, conf=o.conf, cls=o.cls, age=o.age, tsu=o.tsu)
+            assert_state_equal(tracks[b], int(next_id[b]), ref, o.next_id)
+            n = count[f, b]
+            np.testing.assert_array_equal(tid[b, :n], exp[b][0])
+            np.testing.assert_array_equal(kind[b, :n], exp[b][1])
+    return sb
+
+
+def test_batched_streams_match_oracle_every_frame(pkg):
+    run_batch_against_oracle(pkg, B=16, F=60, slots=64, clip_kw=dict(num_objects=30, w_range=(20, 80), h_range=(30, 120),
+                                                                     vmax=4.0, dropout=0.08), max_tracks=1024)
+
+
+def test_batched_equals_single_stream_runs(pkg):
+    """B streams in one launch == B independent one-stream runs (tier 4)."""
+    import torch
+    B, F, slots = 6, 40, 32
+    kw = dict(num_objects=15, w_range=(20, 60), h_range=(30, 90), vmax=4.0)
+    xyxy, conf, cls, count = pkg.synth.scripted_batch(B, F, slots, seed=7, **kw)
+    sb = pkg.StreamBatch(B, None, max_det=slots, max_tracks=512)
+    singles = [pkg.StreamBatch(1, None, max_det=slots, max_tracks=512) for _ in range(B)]
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(sb.device)
+    for f in range(F):
+        sb.track_only(t(xyxy[f]), t(conf[f]), t(cls[f]), t(count[f]), now=0.0)
+        for b, s in enumerate(singles):
+            s.track_only(t(xyxy[f, b:b + 1]), t(conf[f, b:b + 1]), t(cls[f, b:b + 1]), t(count[f, b:b + 1]), now=0.0)
+    tracks, next_id = sb.read_tracks()
+    for b, s in enumerate(singles):
+        tr, ni = s.read_tracks()
+        assert ni[0] == next_id[b]
+        assert [(x["track_id"], x["age"], x["time_since_update"], x["xyxy"].tolist()) for x in tr[0]] == \
+               [(x["track_id"], x["age"], x["time_since_update"], x["xyxy"].tolist()) for x in tracks[b]]
+
+
+def test_dense_crowd_matches_oracle(pkg):
+    """Config 5 of BASELINE.json at reduced stream count: 1000 objects per stream."""
+    run_batch_against_oracle(pkg, B=3, F=8, slots=1024, clip_kw=pkg.synth.dense_crowd_kwargs(1000),
+                             max_tracks=4096, seed=11, check_every=4)
+
+
+def test_thresholds_ties_and_degenerate_frames(pkg):
+    """IoU exactly at the threshold, duplicate detections (column conflicts), zero-area boxes,
+    all-low and empty frames."""
+    import types
+    frames = []
+    box = np.array([[0, 0, 10, 10]], np.float32)
+    frames.append((box, [0.9], [0]))
+    frames.append((np.array([[0, 0, 10, 8]], np.float32), [0.9], [1]))        # IoU = 0.8 vs thresh 0.8
+    frames.append((np.array([[0, 0, 10, 8], [0, 0, 10, 8], [50, 50, 50, 50]], np.float32), [0.9, 0.95, 0.7], [1, 2, 3]))
+    frames.append((np.zeros((0, 4), np.float32), [], []))
+    frames.append((np.array([[0, 0, 10, 8], [0, 0, 10, 8.5]], np.float32), [0.4, 0.45], [4, 5]))   # all low
+    frames.append((np.array([[0, 0, 10, 8.5], [50, 50, 50, 50]], np.float32), [0.6, 0.3], [6, 7]))
+    trk = pkg.MultiObjectTracker(max_tracks=64, max_dets=16)
+    orc = tracker_ref.TrackerOracle()
+    for xyxy, conf, cls in frames * 3:
+        conf, cls = np.asarray(conf, np.float32), np.asarray(cls, np.int32)
+        trk.update(types.SimpleNamespace(xyxy=xyxy, confidence=conf, class_id=cls))
+        exp_tid, exp_kind = orc.step(xyxy, conf, cls)
+        ref = dict(track_id=orc.track_id, xyxy=orc.xyxy, conf=orc.conf, cls=orc.cls, age=orc.age, tsu=orc.tsu)
+        assert_state_equal(trk._core._tracks, trk._core._next_id, ref, orc.next_id)
+        tid, kind = trk._core.assignments()
+        np.testing.assert_array_equal(tid, exp_tid)
+        np.testing.assert_array_equal(kind, exp_kind)
+
+
+def test_track_table_overflow_is_reported_not_truncated(pkg):
+    import types
+    trk = pkg.MultiObjectTracker(max_tracks=8, max_dets=16)
+    xy = np.arange(12, dtype=np.float32)[:, None] * 100 + np.array([0, 0, 10, 10], np.float32)
+    with pytest.raises(pkg.RtmError, match="capacity"):
+        trk.update(types.SimpleNamespace(xyxy=xy, confidence=np.full(12, 0.9, np.float32), class_id=np.zeros(12, np.int32)))

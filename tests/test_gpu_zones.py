@@ -1,0 +1,127 @@
+"""rtm_zone_step against the reference's golden events, the oracle and cv2 (bit-exact)."""
+
+import ctypes as C
+import types
+
+import numpy as np
+import pytest
+
+from conftest import golden_clip, load_golden
+from oracle import tracker_ref, zone_ref
+from test_oracle_golden import tracker_params, zones_for
+
+pytestmark = pytest.mark.gpu
+
+
+def event_rows(events, zone_index):
+    return [(e.frame_id, e.track_id, zone_index[(e.zone_name, e.event_type)], e.class_id, *e.centroid,
+             e.dwell_time_sec, *e.bbox_xyxy) for e in events]
+
+
+@pytest.mark.parametrize("name", ["cfg1_clip.npz", "crowd_clip.npz", "gaps_clip.npz", "churn_clip.npz"])
+def test_fused_tracker_and_zones_replay_reference_events(pkg, name):
+    """Scripted detections -> rtm_track_step -> rtm_zone_step == reference tracker + zone engine."""
+    import torch
+    g = load_golden(name)
+    zones = zones_for(name)
+    zone_index = {(z["name"], z.get("trigger", "intrusion")): i for i, z in reversed(list(enumerate(zones)))}
+    p = tracker_params(g)
+    slots = 128
+    sb = pkg.StreamBatch(1, [zones], max_det=slots, max_tracks=512, src_hw=(720, 1280), **p)
+    rows = []
+    for f, (xyxy, conf, cls) in enumerate(golden_clip(g)):
+        n = len(conf)
+        bx = np.zeros((1, slots, 4), np.float32); bx[0, :n] = xyxy
+        cf = np.zeros((1, slots), np.float32); cf[0, :n] = conf
+        cl = np.zeros((1, slots), np.int32); cl[0, :n] = cls
+        t = lambda a: torch.from_numpy(a).to(sb.device)
+        sb.track_only(t(bx), t(cf), t(cl), t(np.array([n], np.int32)), now=float(g["t0"]) + f / float(g["fps"]), frame_id=f)
+        rows += event_rows(sb.read_events()[0], zone_index)
+    np.testing.assert_array_equal(np.array(rows, np.float64).reshape(-1, 11), g["events"])
+
+
+def test_point_in_polygon_kernel_matches_cv2_golden(pkg):
+    """One stream per golden polygon, one track per query point; dwell = cooldown = 0 makes every
+    inside test visible as an event."""
+    import torch
+    g = load_golden("pip_cases.npz")
+    off = g["poly_offsets"]
+    P, Q = len(off) - 1, g["points"].shape[1]
+    zones = [[dict(name="z", polygon=g["poly_xy"][off[p]:off[p + 1]].tolist(), dwell_time_sec=0.0, cooldown_sec=0.0)]
+             for p in range(P)]
+    dev = torch.device("cuda:0")
+    zt = pkg.ZoneTables(zones, Q, dev, max_events=Q)
+    tt = pkg.DeviceTrackTable(P, Q, dev)
+    pts = g["points"].astype(np.float32)
+    box = np.concatenate([pts, pts], 2)                     # centroid == the point
+    tt.xyxy.copy_(torch.from_numpy(box))
+    tt.track_id.copy_(torch.arange(1, Q + 1, dtype=torch.int32).repeat(P, 1))
+    tt.time_since_update.fill_(1)
+    tt.count.fill_(Q)
+    status = torch.zeros(P, dtype=torch.int32, device=dev)
+    lib = pkg._lib.lib()
+    st = zt.state_in()[2]
+    pkg._lib.check(lib.rtm_zone_step(C.byref(zt.zone_set), C.byref(tt.struct), None, C.byref(st), C.byref(st), 5.0, None, 0,
+                                     zt.events.data_ptr(), zt.event_stride, zt.event_count.data_ptr(), status.data_ptr(),
+                                     pkg._lib.cuda_stream()))
+    assert not status.cpu().numpy().any()
+    cnt = zt.event_count.cpu().numpy()
+    recs = zt.events.cpu().numpy().view(np.dtype(pkg._lib.EVENT_DTYPE)).reshape(P, -1)
+    for p in range(P):
+        inside = np.zeros(Q, bool)
+        inside[recs[p, :cnt[p]]["row"]] = True
+        np.testing.assert_array_equal(inside, g["result"][p] >= 0, err_msg=f"polygon {p}")
+        np.testing.assert_array_equal(recs[p, :cnt[p]]["row"], np.flatnonzero(inside))       # row order
+
+
+def test_facade_matches_oracle_with_arbitrary_track_lists(pkg, tmp_path):
+    """Ids vanish and come back, call order differs from first-seen order, duplicate zone names
+    share state, default dwell / cooldown, negative coordinates, table growth."""
+    rng = np.random.default_rng(42)
+    zones = pkg.synth.make_zones(seed=1, num_zones=7, width=640, height=480, kmin=3, kmax=8, dwell_time_sec=0.3, cooldown_sec=0.7)
+    zones[4]["name"] = zones[1]["name"]
+    zones[6] = dict(name="defaults", polygon=[[0, 0], [640, 0], [640, 480], [0, 480]])
+    for z in zones[:6]:
+        z["polygon"] = (np.asarray(z["polygon"]) // 2).tolist()
+    clock = {"t": 100.0}
+    eng = pkg.ZoneEventEngine(zones, log_path=str(tmp_path / "ev.jsonl"), clock=lambda: clock["t"], initial_rows=8)
+    orc = zone_ref.ZoneOracle(zones)
+    pos = rng.uniform(-20, 660, (40, 2))
+    total = 0
+    for f in range(200):
+        clock["t"] = 100.0 + f * 0.11
+        pos += rng.uniform(-6, 6, pos.shape)
+        ids = rng.permutation(40)[: int(rng.integers(0, 30))]
+        tracks = []
+        for i in ids:
+            b = np.array([pos[i, 0] - 5, pos[i, 1] - 9, pos[i, 0] + 5, pos[i, 1] + 9], np.float32)
+            tracks.append(types.SimpleNamespace(track_id=int(i) + 1, xyxy=b, class_id=int(i) % 5, class_name=f"c{i % 5}"))
+        got = eng.process(tracks, f)
+        exp = orc.process([(t.track_id, t.xyxy, t.class_id) for t in tracks], f, clock["t"])
+        assert [(e.track_id, e.zone_name, e.event_type, e.class_id, e.centroid, e.dwell_time_sec, e.bbox_xyxy, e.frame_id, e.class_name)
+                for e in got] == \
+               [(e.track_id, e.zone_name, e.event_type, e.class_id, e.centroid, e.dwell_time_sec, e.bbox_xyxy, e.frame_id, f"c{(e.track_id - 1) % 5}")
+                for e in exp]
+        total += len(got)
+    assert total > 20
+    lines = open(tmp_path / "ev.jsonl").read().splitlines()
+    assert len(lines) == total
+    import json
+    rec = json.loads(lines[0])
+    assert set(rec) == {"timestamp_utc", "event_type", "zone_name", "track_id", "class_id", "class_name",
+                        "dwell_time_sec", "bbox_xyxy", "centroid", "frame_id", "metadata"}
+    assert [n for n, _ in eng.get_zone_polygons()] == [z["name"] for z in zones]
+
+
+def test_reference_dwell_cooldown_schedule(pkg, tmp_path):
+    """SURVEY.md section 8a Z2 probe: dwell 2 s / cooldown 10 s at 30 fps fires at frames 60, 360, 660."""
+    clock = {"t": 0.0}
+    eng = pkg.ZoneEventEngine([dict(name="a", polygon=[[0, 0], [100, 0], [100, 100], [0, 100]])],
+                              log_path=str(tmp_path / "e.jsonl"), clock=lambda: clock["t"])
+    trk = [types.SimpleNamespace(track_id=1, xyxy=np.array([40, 40, 60, 60], np.float32), class_id=0)]
+    fired = []
+    for f in range(700):
+        clock["t"] = 1_700_000_000.0 + f / 30.0
+        for e in eng.process(trk, f):
+            fired.append((f, e.dwell_time_sec))
+    assert fired == [(60, 2.0), (360, 12.0), (660, 22.0)]
