@@ -1,0 +1,486 @@
+#!/usr/bin/env python
+"""bench.py - tracked frames/s of the post-backbone hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [--gpus N] [--steps K] ...    # the reference's CPU path
+
+Workload (config.workload): BASELINE.json configs[2] per GPU - 64 synthetic 1080p streams,
+YOLOv8 head tensors of 8400 anchors x (64 + 80) channels per stream-frame (planted objects,
+bf16 like the reference's half=True network output), class-aware NMS, ByteTrack-style
+association and 4 polygon zones per stream.  One step = one frame of every stream of the
+rank: decode + NMS -> tracker -> zones.  N ranks shard streams with no per-frame collective
+(weak scaling: 64 streams per GPU; N = 8 is configs[3], 512 streams); one NCCL reduction of
+the run summary happens after the timed region.
+
+The JSON line carries: `value` (device-resident inputs, CUDA-event timed, max over ranks),
+`e2e` (same step through rtm_post_backbone_step_host: pinned host head tensors -> H2D ->
+kernels -> D2H of detections/events, copies inside the timed region), `roofline` of the
+dominant kernel (decode_candidates: algorithmic bytes / measured launch time vs the measured
+HBM peak), `cpu_baseline` (the oracle port on one host core over a bounded sample), latency
+percentiles, clocks and a parity spot-check against the oracle.
+"""
+
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "tracked_frames_per_sec_post_backbone"
+UNIT = "frames/s"
+WANTED = [0, 1, 2, 3, 5, 7]
+STREAMS_PER_GPU = 64
+CYCLE_FRAMES = 16
+FPS = 30.0
+T0 = 1_700_000_000.0
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--streams", type=int, default=STREAMS_PER_GPU, help="streams per GPU")
+    ap.add_argument("--frames", type=int, default=CYCLE_FRAMES, help="distinct frames in the replayed cycle")
+    ap.add_argument("--head-dtype", default="bf16", choices=["bf16", "f16", "f32"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip letterbox / latency / f32-head side measurements")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed regions run."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, index: int, uuid=None) -> None:
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            try:
+                self._h = pynvml.nvmlDeviceGetHandleByUUID(f"GPU-{uuid}".encode() if uuid else b"")
+            except Exception:
+                self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nv = None
+
+    def _run(self):
+        nv = self._nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+                for b, name in self.REASONS.items():
+                    if bits & b:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def __enter__(self):
+        if self._nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ---------------------------------------------------------------------------
+# the oracle chain on the CPU (cpu_baseline leg and the reference arm)
+# ---------------------------------------------------------------------------
+def oracle_stream_step(heads_f32, trk, zon, frame_id, now, classes=WANTED):
+    """One stream-frame through the oracle port: decode + NMS -> tracker -> zones (CPU)."""
+    from oracle import detect_ref
+    det = detect_ref.detect_post(heads_f32, (1080, 1920), classes=classes)[0]
+    trk.step(det["xyxy"], det["conf"], det["cls"])
+    act = trk.active_rows()
+    ev = zon.process(zip(trk.track_id[act], trk.xyxy[act], trk.cls[act]), frame_id, now)
+    return len(det["conf"]), len(ev)
+
+
+def cpu_port_throughput(host_frames, zones, seconds):
+    """frames/s of the oracle port on ONE thread over `host_frames[f][level] (S,144,h,w)` replayed."""
+    import torch
+    from oracle import tracker_ref, zone_ref
+    torch.set_num_threads(1)
+    S = host_frames[0][0].shape[0]
+    trk = [tracker_ref.TrackerOracle() for _ in range(S)]
+    zon = [zone_ref.ZoneOracle(zones[s], pip=zone_ref.cv2_pip) for s in range(S)]
+    done, f = 0, 0
+    t0 = time.perf_counter()
+    while True:
+        heads = host_frames[f % len(host_frames)]
+        for s in range(S):
+            oracle_stream_step([h[s:s + 1] for h in heads], trk[s], zon[s], f, T0 + f / FPS)
+        done += S
+        f += 1
+        if time.perf_counter() - t0 >= seconds and f >= 2:
+            break
+    return done / (time.perf_counter() - t0), done
+
+
+def _reference_worker(args):
+    """Worker process of the reference arm: owns `streams`, steps them W + K times."""
+    (streams, frames, steps, warmup, threads, barrier_path) = args
+    import torch
+    torch.set_num_threads(threads)
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    pkg = importlib.import_module("rtmodt_b200")
+    from rtmodt_b200.workload import PostBackboneWorkload
+    from oracle import tracker_ref, zone_ref
+    wl = [PostBackboneWorkload(1, frames, first_stream=s, device="cpu", dtype=torch.float32) for s in streams]
+    trk = [tracker_ref.TrackerOracle() for _ in streams]
+    zon = [zone_ref.ZoneOracle(w.zones[0], pip=zone_ref.cv2_pip) for w in wl]
+    dets = evs = 0
+
+    def one(f):
+        nonlocal dets, evs
+        for w, t, z in zip(wl, trk, zon):
+            d, e = oracle_stream_step(w.heads[f % frames], t, z, f, T0 + f / FPS)
+            dets += d
+            evs += e
+
+    for f in range(warmup):
+        one(f)
+    # file-based barrier: all workers start the timed region together
+    open(f"{barrier_path}.{streams[0]}", "w").close()
+    deadline = time.time() + 600
+    want = int(open(barrier_path).read())
+    while len([n for n in os.listdir(os.path.dirname(barrier_path)) if n.startswith(os.path.basename(barrier_path) + ".")]) < want:
+        if time.time() > deadline:
+            raise RuntimeError("reference arm: workers did not reach the barrier")
+        time.sleep(0.005)
+    t0 = time.time()
+    for f in range(warmup, warmup + steps):
+        one(f)
+    t1 = time.time()
+    return t0, t1, len(streams) * steps, dets, evs
+
+
+def run_reference(args):
+    """The reference's CPU implementation of the path (oracle port) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    import tempfile
+    cores = os.cpu_count() or 1
+    total_streams = args.streams * args.gpus
+    workers = max(1, min(cores, total_streams))
+    threads = max(1, cores // workers)
+    shards = [list(range(total_streams))[w::workers] for w in range(workers)]
+    tmp = tempfile.mkdtemp(prefix="rtm_ref_")
+    barrier = os.path.join(tmp, "barrier")
+    with open(barrier, "w") as f:
+        f.write(str(workers))
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(workers) as pool:
+        res = pool.map(_reference_worker, [(s, args.frames, args.steps, args.warmup, threads, barrier) for s in shards])
+    t0 = min(r[0] for r in res)
+    t1 = max(r[1] for r in res)
+    frames = sum(r[2] for r in res)
+    value = frames / (t1 - t0)
+    sample = (f"{total_streams} streams x {args.steps} frames (after {args.warmup} warm-up frames) of the same seeded workload, "
+              f"{workers} worker processes x {threads} torch threads on {cores} host cores")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * (t1 - t0) / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, total_streams),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers * threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "detections": sum(r[3] for r in res), "events": sum(r[4] for r in res),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, total_streams):
+    return {"workload": "BASELINE.json configs[2] per GPU: 64 synthetic 1080p streams, 8400 anchors x 80 classes, "
+                        "ByteTrack + 4 zones (N=8: configs[3], 512 streams)",
+            "streams_per_gpu": args.streams, "total_streams": total_streams, "head_dtype": args.head_dtype,
+            "anchors": 8400, "classes": 80, "zones_per_stream": 4, "objects_per_stream": 30,
+            "cycle_frames": args.frames, "class_filter": WANTED, "conf": 0.35, "iou": 0.45, "max_det": 100,
+            "track_thresh": 0.5, "match_thresh": 0.8, "track_buffer": 30,
+            "l2_policy": "inputs larger than L2: every step reads a different frame of the cycle "
+                         "(streams x 8400 x 144 head elements per step, cycle of frames resident in HBM)"}
+
+
+# ---------------------------------------------------------------------------
+# the CUDA arm
+# ---------------------------------------------------------------------------
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ge = importlib.import_module("__graft_entry__")
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    pkg = importlib.import_module("rtmodt_b200")
+    from rtmodt_b200.workload import PostBackboneWorkload
+    from rtmodt_b200 import sharding, _lib
+
+    tdt = {"bf16": torch.bfloat16, "f16": torch.float16, "f32": torch.float32}[args.head_dtype]
+    S, F, K, W = args.streams, args.frames, args.steps, max(args.warmup, 3)
+    total_streams = S * world
+    my_streams = sharding.shard_streams(total_streams, world, rank)
+    wl = PostBackboneWorkload(S, F, first_stream=my_streams.start, device=dev, dtype=tdt)
+    sb = pkg.StreamBatch(S, wl.zones, src_hw=(1080, 1920), classes=WANTED, max_tracks=512, device=dev)
+    lib = sb.lib
+    hbm_peak, peak_src = peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def run_steps(first, n):
+        for f in range(first, first + n):
+            sb.step(wl.heads[f % F], now=T0 + f / FPS, frame_id=f)
+        return first + n
+
+    counters = {"detections": 0, "births0": 0, "events": 0}
+    sampler = ClockSampler(local, getattr(torch.cuda.get_device_properties(dev), "uuid", None))
+    with sampler:
+        # ---- warm-up + parity spot-check against the oracle (first frames, sampled streams) ----
+        parity = parity_check(pkg, wl, sb, args) if rank == 0 else None
+        f = run_steps(0, W) if rank != 0 else run_steps(parity["frames"], W)
+        sb.check_status()
+
+        # ---- timed region: K steps, device-resident inputs, CUDA events ----
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        f = run_steps(f, K)
+        ev1.record()
+        barrier()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms_total = float(ms.item())
+        value = total_streams * K / (ms_total / 1e3)
+        sb.check_status()
+
+        # ---- roofline pass: same steps with per-kernel CUDA events (rtm_profile_*) ----
+        lib.rtm_profile_enable(1)
+        _lib.profile_read()
+        barrier()
+        f = run_steps(f, K)
+        torch.cuda.synchronize(dev)
+        prof = _lib.profile_read()
+        lib.rtm_profile_enable(0)
+        kernels = {k: {"avg_us": 1e3 * v[0] / v[1], "launches": v[1]} for k, v in prof.items()}
+        dec_us = kernels["decode"]["avg_us"]
+        alg_bytes = S * wl.bytes_per_stream_frame
+        achieved = alg_bytes / (dec_us * 1e-6) / 1e9
+        roofline = {"bound": "hbm", "kernel": "decode_candidates_kernel", "achieved": achieved, "peak": hbm_peak,
+                    "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_us": dec_us,
+                    "share_of_step": dec_us / sum(v["avg_us"] for v in kernels.values()),
+                    "whole_step_frac": (alg_bytes * K / (ms_total / 1e3) / 1e9) / hbm_peak}
+
+        extras = {}
+        if not args.no_extras:
+            # ---- latency mode: one step at a time, p50 / p99 of the per-step device time ----
+            lat = []
+            for _ in range(min(300, max(50, K))):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                f = run_steps(f, 1)
+                b.record()
+                b.synchronize()
+                lat.append(a.elapsed_time(b))
+            lat.sort()
+            extras["latency_ms_per_step"] = {"p50": lat[len(lat) // 2], "p99": lat[min(len(lat) - 1, int(len(lat) * 0.99))],
+                                             "steps": len(lat), "streams_per_step": S}
+            if rank == 0:
+                extras["letterbox"] = letterbox_bench(pkg, lib, dev, S, hbm_peak)
+
+        # ---- e2e: the same step fed from pinned HOST head tensors through the C ABI ----
+        e2e = None
+        if not args.no_e2e:
+            e2e = e2e_bench(pkg, wl, sb, f, K, W, total_streams, world, dev)
+            f += K + W
+        sb.check_status()
+
+    # ---- run summary: the only collective of the run (NCCL all_reduce + all_gather) ----
+    tracks, next_id = sb.read_tracks()
+    ev_per_stream = [len(e) for e in sb.read_events()]
+    totals, gathered = sharding.reduce_summary(
+        [S * f, int(sb.det_count.sum().item()), int((next_id - 1).sum()), sum(ev_per_stream)], ev_per_stream, device=dev)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sample_streams = list(range(min(4, S)))
+        host_frames = [wl.host_frame(ff, sample_streams) for ff in range(F)]
+        v, n = cpu_port_throughput(host_frames, [wl.zones[s] for s in sample_streams], args.cpu_seconds)
+        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"{len(sample_streams)} streams of the same workload, {F}-frame cycle replayed for {n} stream-frames "
+                         f"(>= {args.cpu_seconds:.0f} s), oracle port (torch CPU decode + torchvision NMS + NumPy tracker + cv2 zones), 1 thread",
+               "host_cores_available": os.cpu_count()}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, total_streams),
+            "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": 4 * K, "roofline": roofline,
+            "cpu_baseline": cpu, "kernels": kernels, "parity": parity,
+            "summary": dict(zip(sharding.COUNTERS, totals), live_tracks_rank0=int(sum(len(t) for t in tracks)),
+                            streams_reporting=len(gathered)),
+        }
+        line.update(extras)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def parity_check(pkg, wl, sb, args, frames=6, streams=(0, 1, 2, 3)):
+    """First `frames` frames on the fresh StreamBatch: sampled streams against the oracle chain."""
+    import numpy as np
+    from oracle import detect_ref, tracker_ref, zone_ref
+    streams = [s for s in streams if s < wl.S]
+    trk = {s: tracker_ref.TrackerOracle() for s in streams}
+    zon = {s: zone_ref.ZoneOracle(wl.zones[s]) for s in streams}
+    flips = box_bad = id_bad = ev_bad = dets = 0
+    for f in range(frames):
+        now = T0 + f / FPS
+        sb.step(wl.heads[f % wl.F], now=now, frame_id=f)
+        got = sb.read_detections()
+        tracks, next_id = sb.read_tracks()
+        events = sb.read_events()
+        ref = detect_ref.detect_post(wl.host_frame(f, streams), (1080, 1920), classes=WANTED)
+        for k, s in enumerate(streams):
+            r, g = ref[k], got[s]
+            dets += len(r["conf"])
+            if len(r["conf"]) != len(g["confidence"]) or not np.array_equal(r["anchor"], g["anchor"]):
+                flips += 1
+                continue
+            box_bad += int(not np.allclose(g["xyxy"], r["xyxy"], rtol=1e-4, atol=1e-2))
+            tid, _ = trk[s].step(g["xyxy"], g["confidence"], g["class_id"])
+            id_bad += int(not np.array_equal(tid, g["track_id"])) + int(trk[s].next_id != int(next_id[s]))
+            id_bad += int([t["track_id"] for t in tracks[s]] != trk[s].track_id.tolist())
+            act = trk[s].active_rows()
+            exp = zon[s].process(zip(trk[s].track_id[act], trk[s].xyxy[act], trk[s].cls[act]), f, now)
+            ev_bad += int([(e.track_id, e.zone_name, e.centroid, e.dwell_time_sec) for e in events[s]] !=
+                          [(e.track_id, e.zone_name, e.centroid, e.dwell_time_sec) for e in exp])
+    ok = not (flips or box_bad or id_bad or ev_bad)
+    if not ok:
+        print(f"bench.py: PARITY FAILURE flips={flips} boxes={box_bad} ids={id_bad} events={ev_bad}", file=sys.stderr)
+    return {"ok": ok, "frames": frames, "streams": len(streams), "detections_checked": dets, "nms_index_flips": flips,
+            "box_mismatch": box_bad, "track_id_mismatch": id_bad, "event_mismatch": ev_bad,
+            "checked_against": "oracle port (torch CPU decode, torchvision NMS, NumPy tracker, zone engine restatement)"}
+
+
+def e2e_bench(pkg, wl, sb, f0, K, W, total_streams, world, dev):
+    """Same metric through rtm_post_backbone_step_host: pinned host heads -> H2D -> kernels -> D2H."""
+    import torch
+    import torch.distributed as dist
+    pinned = [[t.cpu().pin_memory() for t in frame] for frame in wl.heads]
+    feeder = pkg.HostFeeder(sb, wl.dtype)
+    results = []
+
+    def go(first, n):
+        for f in range(first, first + n):
+            res = feeder.step_pinned(pinned[f % wl.F], now=T0 + f / FPS, frame_id=f)
+            results.append(res)
+            if len(results) > 2:
+                results.pop(0).wait()                     # consume the results of step k-2 on the host
+        while results:
+            results.pop(0).wait()
+
+    go(f0, W)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    go(f0 + W, K)
+    torch.cuda.synchronize(dev)
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    dt = float(dt.item())
+    return {"value": total_streams * K / dt, "unit": UNIT, "h2d_bytes_per_step": feeder.h2d_bytes,
+            "d2h_bytes_per_step": feeder.d2h_bytes, "ms_per_step": 1e3 * dt / K,
+            "h2d_gbs": feeder.h2d_bytes * K / dt / 1e9,
+            "api": "HostFeeder.step_pinned -> rtm_post_backbone_step_host (2 CUDA streams, H2D of step k+1 overlaps step k)"}
+
+
+def letterbox_bench(pkg, lib, dev, S, hbm_peak, iters=20):
+    """P1 on its own: S 1080p u8 frames -> (S, 3, 640, 640) bf16 (reported beside the main metric)."""
+    import torch
+    from rtmodt_b200 import _lib
+    frames = torch.randint(0, 256, (S, 1080, 1920, 3), dtype=torch.uint8, device=dev)
+    out = torch.empty((S, 3, 640, 640), dtype=torch.bfloat16, device=dev)
+    call = lambda: _lib.check(lib.rtm_letterbox(frames.data_ptr(), S, 1080, 1920, 1920 * 3, 1080 * 1920 * 3, out.data_ptr(),
+                                                _lib.RTM_BF16, 640, 640, _lib.cuda_stream()))
+    for _ in range(3):
+        call()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    a.record()
+    for _ in range(iters):
+        call()
+    b.record()
+    b.synchronize()
+    us = 1e3 * a.elapsed_time(b) / iters
+    alg = S * (640 * 360 * 3 + 3 * 640 * 640 * 2)          # contributing source pixels + bf16 output
+    gbs = alg / (us * 1e-6) / 1e9
+    return {"frames_per_s": S / (us * 1e-6), "avg_launch_us": us, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / hbm_peak,
+            "algorithmic_bytes_per_launch": alg, "config": f"{S} x 1080p u8 BGR -> 640x640 bf16 CHW"}
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -287,6 +287,25 @@ typedef struct rtm_step_host_io {
 int rtm_post_backbone_step_host(const rtm_step_io* io, const rtm_step_host_io* host_io,
                                 const rtm_nms_params* params, rtm_cuda_stream stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Measurement aid (off by default; nothing below runs on the per-frame path unless enabled).
+ * While enabled, every kernel launch of the library is bracketed by a pair of CUDA events on
+ * the launching stream; rtm_profile_read synchronises them, adds the elapsed milliseconds and
+ * launch counts per kernel kind into ms_sum[RTM_K_COUNT] / launches[RTM_K_COUNT] and clears
+ * the record.  bench.py uses it for the per-kernel roofline figures.
+ * ---------------------------------------------------------------------------------------- */
+enum {
+  RTM_K_LETTERBOX = 0,
+  RTM_K_DECODE = 1, /* decode_candidates_kernel: the HBM-bound head scan */
+  RTM_K_NMS = 2,
+  RTM_K_TRACK = 3,
+  RTM_K_ZONE = 4,
+  RTM_K_PRED = 5,
+  RTM_K_COUNT = 8
+};
+int rtm_profile_enable(int32_t on);
+int rtm_profile_read(double* ms_sum, int32_t* launches);
+
 #ifdef __cplusplus
 }
 #endif

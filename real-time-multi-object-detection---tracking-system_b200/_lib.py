@@ -120,6 +120,8 @@ SIGNATURES = {
     "rtm_zone_step": (C.c_int, [C.POINTER(ZoneSet), C.POINTER(TrackTable), C.c_void_p,
                                 C.POINTER(ZoneState), C.POINTER(ZoneState), C.c_double, C.c_void_p,
                                 C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rtm_profile_enable": (C.c_int, [C.c_int32]),
+    "rtm_profile_read": (C.c_int, [f64p, i32p]),
     "rtm_post_backbone_step": (C.c_int, [C.POINTER(StepIO), C.POINTER(NmsParams), C.c_void_p]),
     "rtm_post_backbone_step_host": (C.c_int, [C.POINTER(StepIO), C.POINTER(StepHostIO),
                                               C.POINTER(NmsParams), C.c_void_p]),
@@ -167,6 +169,18 @@ def raise_on_status(status_host, what: str = "") -> None:
     msgs = [t for b, t in _STATUS_TEXT.items() if bits & b]
     streams = np.flatnonzero(st.reshape(-1))[:8].tolist()
     raise RtmError(f"{what}: {'; '.join(msgs)} (streams {streams})")
+
+
+K_LETTERBOX, K_DECODE, K_NMS, K_TRACK, K_ZONE, K_PRED, K_COUNT = 0, 1, 2, 3, 4, 5, 8
+KERNEL_NAMES = {K_LETTERBOX: "letterbox", K_DECODE: "decode", K_NMS: "nms", K_TRACK: "track", K_ZONE: "zone", K_PRED: "pred_filter"}
+
+
+def profile_read():
+    """{kernel name: (total ms, launches)} since the last read; needs rtm_profile_enable(1)."""
+    ms = (C.c_double * K_COUNT)()
+    n = (C.c_int32 * K_COUNT)()
+    check(load_library().rtm_profile_read(ms, n))
+    return {KERNEL_NAMES[k]: (ms[k], n[k]) for k in KERNEL_NAMES if n[k]}
 
 
 def ptr(t) -> int:

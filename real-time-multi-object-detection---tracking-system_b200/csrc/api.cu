@@ -3,6 +3,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <vector>
+
 #include "rtm_common.cuh"
 
 namespace rtm {
@@ -25,7 +27,65 @@ int sm_count() {
   return cached;
 }
 
+bool g_profile_on = false;
+
+namespace {
+struct ProfileRecord {
+  int kind;
+  cudaEvent_t start, stop;
+};
+std::vector<ProfileRecord> g_records;
+std::vector<cudaEvent_t> g_free_events;
+
+cudaEvent_t take_event() {
+  if (!g_free_events.empty()) {
+    cudaEvent_t e = g_free_events.back();
+    g_free_events.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+}  // namespace
+
+void profile_begin(int kind, cudaStream_t s) {
+  ProfileRecord r{kind, take_event(), take_event()};
+  cudaEventRecord(r.start, s);
+  g_records.push_back(r);
+}
+
+void profile_end(cudaStream_t s) {
+  if (!g_records.empty()) cudaEventRecord(g_records.back().stop, s);
+}
+
 }  // namespace rtm
+
+extern "C" int rtm_profile_enable(int32_t on) {
+  rtm::g_profile_on = on != 0;
+  return RTM_OK;
+}
+
+extern "C" int rtm_profile_read(double* ms_sum, int32_t* launches) {
+  RTM_REQUIRE(ms_sum && launches, "rtm_profile_read: null output");
+  for (int k = 0; k < RTM_K_COUNT; ++k) {
+    ms_sum[k] = 0.0;
+    launches[k] = 0;
+  }
+  for (const auto& r : rtm::g_records) {
+    RTM_CUDA(cudaEventSynchronize(r.stop));
+    float ms = 0.f;
+    RTM_CUDA(cudaEventElapsedTime(&ms, r.start, r.stop));
+    if (r.kind >= 0 && r.kind < RTM_K_COUNT) {
+      ms_sum[r.kind] += ms;
+      launches[r.kind] += 1;
+    }
+    rtm::g_free_events.push_back(r.start);
+    rtm::g_free_events.push_back(r.stop);
+  }
+  rtm::g_records.clear();
+  return RTM_OK;
+}
 
 extern "C" int rtm_version(void) { return RTM_VERSION; }
 

@@ -179,6 +179,7 @@ extern "C" int rtm_letterbox(const uint8_t* frames, int32_t num_streams, int32_t
   const int groups = (out_w / kPix) * out_h;
   dim3 grid((groups + 255) / 256, num_streams);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  rtm::ProfileScope prof(RTM_K_LETTERBOX, s);
   switch (out_dtype) {
     case RTM_F32:
       letterbox_kernel<float><<<grid, 256, 0, s>>>(a);

@@ -543,7 +543,10 @@ int run_nms(const Workspace& ws, int B, const rtm_nms_params& prm, const NmsOut&
                                   static_cast<int>(kNmsSmemBytes)));
     configured = true;
   }
-  nms_kernel<<<B, kNmsThreads, kNmsSmemBytes, stream>>>(ws, prm, iou_gate_for(prm.iou_thres), out);
+  {
+    rtm::ProfileScope prof(RTM_K_NMS, stream);
+    nms_kernel<<<B, kNmsThreads, kNmsSmemBytes, stream>>>(ws, prm, iou_gate_for(prm.iou_thres), out);
+  }
   RTM_LAUNCH_CHECK("nms_kernel");
   return RTM_OK;
 }
@@ -579,7 +582,10 @@ int launch_decode(const void* p3, const void* p4, const void* p5, const HeadGeom
   constexpr int THREADS = 128;
   const int groups = g.num_anchors / VEC;
   dim3 grid((groups + THREADS - 1) / THREADS, B);
-  decode_candidates_kernel<T, VEC, THREADS><<<grid, THREADS, 0, stream>>>(heads, g, prm, gate, ws, status);
+  {
+    rtm::ProfileScope prof(RTM_K_DECODE, stream);
+    decode_candidates_kernel<T, VEC, THREADS><<<grid, THREADS, 0, stream>>>(heads, g, prm, gate, ws, status);
+  }
   RTM_LAUNCH_CHECK("decode_candidates_kernel");
   return RTM_OK;
 }
@@ -644,7 +650,10 @@ extern "C" int rtm_nms_pred(const float* pred, int32_t num_streams, int32_t num_
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   RTM_CUDA(cudaMemsetAsync(ws.count, 0, sizeof(int32_t) * num_streams, s));
   dim3 grid((num_anchors + 255) / 256, num_streams);
-  pred_candidates_kernel<<<grid, 256, 0, s>>>(pred, num_anchors, params->num_classes, *params, ws, status);
+  {
+    rtm::ProfileScope prof(RTM_K_PRED, s);
+    pred_candidates_kernel<<<grid, 256, 0, s>>>(pred, num_anchors, params->num_classes, *params, ws, status);
+  }
   RTM_LAUNCH_CHECK("pred_candidates_kernel");
   NmsOut out{scale, det_xyxy, det_conf, det_cls, det_anchor, det_keep, det_count, det_stride, status};
   return run_nms(ws, num_streams, *params, out, s);

@@ -41,6 +41,21 @@ void set_error(const char* fmt, ...);
 
 int sm_count();  // cached multiProcessorCount of the current device
 
+// Brackets a kernel launch with CUDA events while rtm_profile_enable(1) is in effect.
+extern bool g_profile_on;
+void profile_begin(int kind, cudaStream_t s);
+void profile_end(cudaStream_t s);
+struct ProfileScope {
+  cudaStream_t s;
+  bool on;
+  ProfileScope(int kind, cudaStream_t stream) : s(stream), on(g_profile_on) {
+    if (on) profile_begin(kind, s);
+  }
+  ~ProfileScope() {
+    if (on) profile_end(s);
+  }
+};
+
 // ---- device helpers -------------------------------------------------------------------
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;

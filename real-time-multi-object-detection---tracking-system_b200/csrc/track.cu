@@ -283,7 +283,10 @@ int launch_track(const TrackArgs& a, cudaStream_t stream) {
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     configured = smem;
   }
-  track_step_kernel<THREADS><<<a.tin.num_streams, THREADS, smem, stream>>>(a);
+  {
+    rtm::ProfileScope prof(RTM_K_TRACK, stream);
+    track_step_kernel<THREADS><<<a.tin.num_streams, THREADS, smem, stream>>>(a);
+  }
   RTM_LAUNCH_CHECK("track_step_kernel");
   return RTM_OK;
 }

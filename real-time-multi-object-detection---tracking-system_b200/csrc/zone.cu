@@ -216,7 +216,10 @@ extern "C" int rtm_zone_step(const rtm_zone_set* zones, const rtm_track_table* t
   ZoneArgs a{*zones, *tracks, src_row, *state_in, *state_out, now, now_per_stream, frame_id,
              events, event_stride, event_count, status, 2048};
   const size_t smem = static_cast<size_t>(a.max_vertices) * sizeof(int2);
-  zone_step_kernel<<<tracks->num_streams, kZoneThreads, smem, static_cast<cudaStream_t>(stream)>>>(a);
+  {
+    rtm::ProfileScope prof(RTM_K_ZONE, static_cast<cudaStream_t>(stream));
+    zone_step_kernel<<<tracks->num_streams, kZoneThreads, smem, static_cast<cudaStream_t>(stream)>>>(a);
+  }
   RTM_LAUNCH_CHECK("zone_step_kernel");
   return RTM_OK;
 }

@@ -450,22 +450,34 @@ class HostFeeder:
             dst.copy_(src)
 
     def step(self, heads_host=None, now: Optional[float] = None, frame_id: Optional[int] = None) -> StepResult:
-        """Enqueue one step.  ``heads_host``: three host tensors (copied into the pinned buffers
-        first) or None when the slot's pinned buffers were filled with :meth:`stage`."""
+        """Enqueue one step.  ``heads_host``: three host tensors (copied into the slot's pinned
+        buffers first) or None when they were filled with :meth:`stage`."""
+        slot_index = self.k % self.depth
+        self.slots[slot_index]["done"].synchronize()          # the slot's previous results were consumed
+        if heads_host is not None:
+            self.stage(slot_index, heads_host)
+        return self._enqueue(self.slots[slot_index]["host_heads"], now, frame_id)
+
+    def step_pinned(self, pinned_heads, now: Optional[float] = None, frame_id: Optional[int] = None) -> StepResult:
+        """Enqueue one step whose inputs already sit in page-locked host tensors (no staging copy)."""
+        for t in pinned_heads:
+            if not t.is_pinned():
+                raise ValueError("step_pinned needs page-locked (pinned) host tensors")
+        self.slots[self.k % self.depth]["done"].synchronize()
+        return self._enqueue(pinned_heads, now, frame_id)
+
+    def _enqueue(self, host_heads, now, frame_id) -> StepResult:
         import torch
         b = self.batch
         slot = self.slots[self.k % self.depth]
         prev = self.slots[(self.k - 1) % self.depth]
-        slot["done"].synchronize()                            # the slot's previous results were consumed
-        if heads_host is not None:
-            self.stage(self.k % self.depth, heads_host)
         now = time.time() if now is None else now
         fid = b.frame_id if frame_id is None else frame_id
         io = b._io(None, now, fid)
         io.head_p3, io.head_p4, io.head_p5 = (t.data_ptr() for t in slot["dev_heads"])
         io.head_dtype = _lib.dtype_code(slot["dev_heads"][0].dtype)
         h = _lib.StepHostIO()
-        h.host_head_p3, h.host_head_p4, h.host_head_p5 = (t.data_ptr() for t in slot["host_heads"])
+        h.host_head_p3, h.host_head_p4, h.host_head_p5 = (t.data_ptr() for t in host_heads)
         if b.zones is not None:
             h.host_events, h.host_event_count = slot["events"].data_ptr(), slot["event_count"].data_ptr()
         h.host_det_xyxy, h.host_det_conf = slot["det_xyxy"].data_ptr(), slot["det_conf"].data_ptr()

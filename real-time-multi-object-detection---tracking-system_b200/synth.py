@@ -231,3 +231,98 @@ def synthetic_frame(rng: np.random.Generator, height: int = 1080, width: int = 1
         for k, (x1, y1, x2, y2) in enumerate(np.asarray(boxes_xyxy)):
             img[max(int(y1), 0):int(y2), max(int(x1), 0):int(x2)] = (37 * k + 11) % 256
     return img
+
+
+# ---------------------------------------------------------------------------
+# Vectorised planting (bench-sized workloads: configs 3 / 4 of BASELINE.json)
+# ---------------------------------------------------------------------------
+def pingpong_objects(seed: int, num_frames: int, num_objects: int = 30, src_hw=(1080, 1920),
+                     imgsz=(640, 640), w_range=(90.0, 240.0), h_range=(180.0, 480.0), vmax: float = 3.0,
+                     dropout: float = 0.05, logit_range=(-0.5, 3.0), distractor_frac: float = 0.1):
+    """Movers of one stream over a cycle of ``num_frames`` frames that can be replayed forever:
+    each object runs forward for half the cycle and back again, so frame ``F-1 -> 0`` is as
+    continuous as any other step (config-1 dynamics scaled to 1080p).
+
+    Returns ``dict(boxes (F, M, 4) letterbox px, cls (M,), logit (F, M), present (F, M))``.
+    """
+    rng = np.random.default_rng(seed)
+    h0, w0 = src_hw
+    m = num_objects
+    wh = np.stack([rng.uniform(*w_range, m), rng.uniform(*h_range, m)], 1)
+    vel = rng.uniform(-vmax, vmax, (m, 2))
+    reach = np.abs(vel) * (num_frames // 2)
+    lim = np.array([w0, h0], np.float64)
+    lo = wh / 2 + np.maximum(-vel, 0) * (num_frames // 2)
+    hi = lim - wh / 2 - np.maximum(vel, 0) * (num_frames // 2)
+    c0 = rng.uniform(lo, np.maximum(hi, lo + 1e-3))
+    del reach
+    tri = np.minimum(np.arange(num_frames), num_frames - np.arange(num_frames)).astype(np.float64)
+    c = c0[None] + vel[None] * tri[:, None, None]                       # (F, M, 2) source px
+    gain, pad_x, pad_y = scale_params(src_hw, imgsz)
+    half = wh[None] / 2
+    boxes = np.concatenate([c - half, c + half], -1) * gain
+    boxes[..., [0, 2]] += pad_x
+    boxes[..., [1, 3]] += pad_y
+    cls = rng.choice(np.asarray(WANTED_CLASSES, np.int32), m).astype(np.int32)
+    unwanted = np.setdiff1d(np.arange(NUM_CLASSES), WANTED_CLASSES)
+    distract = rng.uniform(size=m) < distractor_frac
+    cls[distract] = rng.choice(unwanted, int(distract.sum()))
+    logit = rng.uniform(*logit_range, (num_frames, m))
+    present = rng.uniform(size=(num_frames, m)) >= dropout
+    return dict(boxes=boxes, cls=cls, logit=logit, present=present)
+
+
+def plant_cells(boxes, cls, logit, owner, rng: np.random.Generator, imgsz=(640, 640), peak: float = 6.0):
+    """Which head cells to overwrite for a flat list of M objects (vectorised :func:`plant_head`).
+
+    ``owner[m]`` is the index of the (frame, stream) head tensor object m belongs to.  Returns one
+    dict per level with int64 ``owner, gy, gx, cls`` (K,), float32 ``logit`` (K,), int64 ``lo`` (K, 4)
+    and float32 ``vlo, vhi`` (K, 4): class channel ``64 + cls`` gets ``logit``; DFL bins ``lo`` /
+    ``lo + 1`` of side k get ``vlo`` / ``vhi``.  A cell claimed by two objects goes to the first.
+    """
+    boxes = np.asarray(boxes, np.float64).reshape(-1, 4)
+    x1, y1, x2, y2 = (boxes[:, k] for k in range(4))
+    cx, cy = (x1 + x2) / 2, (y1 + y2) / 2
+    dy, dx = (a.reshape(-1) for a in np.meshgrid([-1, 0, 1], [-1, 0, 1], indexing="ij"))
+    out = []
+    for s, (h, w) in zip(STRIDES, head_shapes(imgsz)):
+        gx = np.floor(cx / s).astype(np.int64)[:, None] + dx[None]
+        gy = np.floor(cy / s).astype(np.int64)[:, None] + dy[None]
+        ax, ay = (gx + 0.5) * s, (gy + 0.5) * s
+        dist = np.stack([ax - x1[:, None], ay - y1[:, None], x2[:, None] - ax, y2[:, None] - ay], -1) / s
+        ok = (gx >= 0) & (gx < w) & (gy >= 0) & (gy < h) & (dist.min(-1) >= 0) & (dist.max(-1) <= REG_MAX - 1.001)
+        m_idx, c_idx = np.nonzero(ok)
+        own, ggy, ggx = np.asarray(owner, np.int64)[m_idx], gy[ok], gx[ok]
+        key = (own * h + ggy) * w + ggx
+        _, first = np.unique(key, return_index=True)
+        first.sort()
+        m_idx, c_idx, own, ggy, ggx = m_idx[first], c_idx[first], own[first], ggy[first], ggx[first]
+        d = dist[ok][first]
+        lo = np.floor(d).astype(np.int64)
+        fr = d - lo
+        jitter = np.where(c_idx == 4, 0.0, rng.uniform(0.0, 1.0, len(m_idx)))     # centre cell scores best
+        out.append(dict(owner=own, gy=ggy, gx=ggx, cls=np.asarray(cls, np.int64)[m_idx],
+                        logit=(np.asarray(logit, np.float64)[m_idx] - jitter).astype(np.float32), lo=lo,
+                        vlo=(peak + np.log(np.maximum(1.0 - fr, 1e-3))).astype(np.float32),
+                        vhi=(peak + np.log(np.maximum(fr, 1e-3))).astype(np.float32)))
+    return out
+
+
+def scatter_cells(head, cells: dict) -> None:
+    """Write planted cells into ``head`` (N, 144, h, w): a NumPy array or a torch tensor (any device)."""
+    n, ch, h, w = head.shape
+    own, gy, gx = cells["owner"], cells["gy"], cells["gx"]
+    base = (own * ch * h + gy) * w + gx                                  # channel 0 of the cell
+    plane = h * w
+    idx = [base + (4 * REG_MAX + cells["cls"]) * plane]
+    val = [cells["logit"]]
+    for k in range(4):
+        idx += [base + (k * REG_MAX + cells["lo"][:, k]) * plane, base + (k * REG_MAX + cells["lo"][:, k] + 1) * plane]
+        val += [cells["vlo"][:, k], cells["vhi"][:, k]]
+    idx, val = np.concatenate(idx), np.concatenate(val)
+    if isinstance(head, np.ndarray):
+        head.reshape(-1)[idx] = val.astype(head.dtype)
+    else:
+        import torch
+        flat = head.view(-1)
+        flat[torch.from_numpy(idx).to(head.device)] = torch.from_numpy(val).to(head.device).to(head.dtype)
