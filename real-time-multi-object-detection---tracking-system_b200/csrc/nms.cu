@@ -25,10 +25,13 @@
 //                      against the newest survivor and the alive bitmask is rebuilt with warp
 //                      ballots (ping-pong buffers, one __syncthreads per survivor) - stopping at
 //                      max_det; survivors are rescaled and written in score order.
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through the runtime)
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <float.h>
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "rtm_common.cuh"
 
@@ -262,6 +265,185 @@ __global__ void __launch_bounds__(THREADS) decode_candidates_kernel(const HeadPt
       warp_decode_anchor<T>(sbase, slv, spix0 + e, nc, prm, ws, b, status);
     }
     lanes &= lanes - 1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// decode_tma: the production head scan.  Persistent CTAs pull whole tiles (all 64 + nc
+// channels x TW consecutive anchors of one stream and level) into shared memory with one
+// TMA tensor copy each (cp.async.bulk.tensor.3d, mbarrier completion, kStages deep), so every
+// head byte crosses HBM exactly once and no register is tied up by loads in flight.  A tile
+// is consumed by 4 x TW threads: thread (anchor a, quarter q) scans a quarter of the class
+// rows of its anchor; anchors whose best class passes the confidence test get their four DFL
+// sides decoded by their four threads straight from shared memory.
+// ---------------------------------------------------------------------------------------
+constexpr int kTileW = 80;    // divides 6400 / 1600 / 400 (and every level of a W=640, H%128==0 input)
+constexpr int kQuarters = 4;
+constexpr int kTmaThreads = kTileW * kQuarters;  // 320
+
+struct TmaGeom {
+  HeadGeom g;
+  int tiles_before[4];  // tiles of one stream before level l (prefix), [3] = tiles per stream
+  int total_tiles;
+  int stages;
+  int tile_bytes;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  // bounded: a lost TMA completion traps (launch error) instead of hanging the GPU
+  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
+    if (spin > (1u << 26)) __trap();
+}
+__device__ __forceinline__ void tma_load_tile(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int b) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(0), "r"(b)
+      : "memory");
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kTmaThreads) decode_tma_kernel(const __grid_constant__ CUtensorMap map0,
+                                                                 const __grid_constant__ CUtensorMap map1,
+                                                                 const __grid_constant__ CUtensorMap map2,
+                                                                 const TmaGeom tg, const rtm_nms_params prm,
+                                                                 const float logit_gate, const Workspace ws,
+                                                                 int32_t* status) {
+  extern __shared__ __align__(128) unsigned char tile_smem[];
+  __shared__ __align__(8) uint64_t full_bar[8];
+  __shared__ float s_score[kQuarters][kTileW];
+  __shared__ int s_class[kQuarters][kTileW];
+  __shared__ float s_dist[kQuarters][kTileW];
+
+  const int tid = threadIdx.x;
+  const int a = tid % kTileW, q = tid / kTileW;
+  const int nc = tg.g.num_classes, stages = tg.stages;
+  const int per_q = (nc + kQuarters - 1) / kQuarters;
+  const int c_lo = min(q * per_q, nc), c_hi = min(c_lo + per_q, nc);
+  const int tps = tg.tiles_before[3];
+
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) mbar_init(&full_bar[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int first = blockIdx.x, step = gridDim.x;
+  const int my_tiles = first < tg.total_tiles ? (tg.total_tiles - first + step - 1) / step : 0;
+
+  auto issue = [&](int it) {  // thread 0 only
+    const int t = first + it * step;
+    const int b = t / tps, r = t - b * tps;
+    const int li = r >= tg.tiles_before[2] ? 2 : (r >= tg.tiles_before[1] ? 1 : 0);
+    const int x = (r - tg.tiles_before[li]) * kTileW;
+    const int s = it % stages;
+    mbar_expect_tx(&full_bar[s], tg.tile_bytes);
+    tma_load_tile(tile_smem + static_cast<size_t>(s) * tg.tile_bytes, li == 0 ? &map0 : (li == 1 ? &map1 : &map2),
+                  &full_bar[s], x, b);
+  };
+  if (tid == 0)
+    for (int it = 0; it < min(stages, my_tiles); ++it) issue(it);
+
+  for (int it = 0; it < my_tiles; ++it) {
+    const int t = first + it * step;
+    const int b = t / tps, r = t - b * tps;
+    const int li = r >= tg.tiles_before[2] ? 2 : (r >= tg.tiles_before[1] ? 1 : 0);
+    const Level lv = tg.g.lv[li];
+    const int pix = (r - tg.tiles_before[li]) * kTileW + a;
+    const int s = it % stages;
+    mbar_wait(&full_bar[s], (it / stages) & 1);
+    const T* tile = reinterpret_cast<const T*>(tile_smem + static_cast<size_t>(s) * tg.tile_bytes);
+
+    // ---- class scan of this thread's quarter: running max, its first index, and the best
+    //      value seen BEFORE that index (to detect sigmoid ties between different logits) ----
+    float m = -FLT_MAX, m2 = -FLT_MAX;
+    int j = c_lo;
+#pragma unroll 4
+    for (int c = c_lo; c < c_hi; ++c) {
+      const float v = to_float(tile[(kBoxCh + c) * kTileW + a]);
+      if (v > m) {
+        m2 = m;
+        m = v;
+        j = c;
+      }
+    }
+    float sc = -1.f;
+    if (m > logit_gate) {
+      sc = sigmoidf_rn(m);
+      if (m2 > logit_gate && sigmoidf_rn(m2) == sc) {
+        // two different logits round to the same probability: the FIRST class reaching it wins
+        for (int c = c_lo; c < j; ++c)
+          if (sigmoidf_rn(to_float(tile[(kBoxCh + c) * kTileW + a])) == sc) {
+            j = c;
+            break;
+          }
+      }
+    }
+    s_score[q][a] = sc;
+    s_class[q][a] = j;
+    __syncthreads();
+
+    // ---- combine the quarters (ascending class order, strict >: first arg-max) ----
+    float best = s_score[0][a];
+    int bc = s_class[0][a];
+#pragma unroll
+    for (int k = 1; k < kQuarters; ++k) {
+      const float o = s_score[k][a];
+      if (o > best) {
+        best = o;
+        bc = s_class[k][a];
+      }
+    }
+    const bool cand = best > prm.conf_thres && class_wanted(prm, bc);
+    if (cand) {
+      // DFL side q of this anchor, same operation order as decode_head_kernel
+      float x[kRegMax], mx = -FLT_MAX;
+#pragma unroll
+      for (int k = 0; k < kRegMax; ++k) {
+        x[k] = to_float(tile[(q * kRegMax + k) * kTileW + a]);
+        mx = fmaxf(mx, x[k]);
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < kRegMax; ++k) {
+        x[k] = expf(__fsub_rn(x[k], mx));
+        sum = __fadd_rn(sum, x[k]);
+      }
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < kRegMax; ++k) acc = __fadd_rn(acc, __fmul_rn(static_cast<float>(k), __fdiv_rn(x[k], sum)));
+      s_dist[q][a] = acc;
+    }
+    __syncthreads();  // all reads of the tile are done: its stage can be refilled
+
+    if (tid == 0 && it + stages < my_tiles) issue(it + stages);
+    if (cand && q == 0) {
+      const float ax = static_cast<float>(pix % lv.w) + 0.5f, ay = static_cast<float>(pix / lv.w) + 0.5f;
+      const float4 box = dist_to_xyxy(s_dist[0][a], s_dist[1][a], s_dist[2][a], s_dist[3][a], ax, ay,
+                                      static_cast<float>(lv.stride), nullptr);
+      append_candidate(ws, b, box, best, bc, lv.anchor0 + pix, status);
+    }
   }
 }
 
@@ -562,6 +744,102 @@ int check_common(const rtm_nms_params* p, int B, float* det_xyxy, float* det_con
   return RTM_OK;
 }
 
+float logit_gate_for(float conf_thres) {
+  // gate on the raw logit: anything whose sigmoid could exceed conf_thres passes (the exact
+  // float32 test is repeated on the sigmoid itself)
+  if (conf_thres <= 0.f) return -FLT_MAX;
+  if (conf_thres >= 1.f) return FLT_MAX;
+  const double lg = log(static_cast<double>(conf_thres) / (1.0 - static_cast<double>(conf_thres)));
+  return static_cast<float>(lg - 1e-3 * (1.0 + fabs(lg)));
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// which head scan to use: RTM_DECODE_IMPL=tma (default when the shape allows) | ldg
+bool want_tma() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RTM_DECODE_IMPL");
+    v = (e && strcmp(e, "ldg") == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+
+template <typename T>
+CUtensorMapDataType tensor_map_dtype();
+template <>
+CUtensorMapDataType tensor_map_dtype<float>() { return CU_TENSOR_MAP_DATA_TYPE_FLOAT32; }
+template <>
+CUtensorMapDataType tensor_map_dtype<__half>() { return CU_TENSOR_MAP_DATA_TYPE_FLOAT16; }
+template <>
+CUtensorMapDataType tensor_map_dtype<__nv_bfloat16>() { return CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; }
+
+// returns 1 when the TMA path was launched, 0 when the caller should fall back, < 0 on error
+template <typename T>
+int try_launch_decode_tma(const void* p3, const void* p4, const void* p5, const HeadGeom& g, int B,
+                          const rtm_nms_params& prm, const Workspace& ws, int32_t* status, cudaStream_t stream) {
+  if (!want_tma()) return 0;
+  EncodeTiledFn encode = tensor_map_encoder();
+  if (!encode) return 0;
+  for (int l = 0; l < 3; ++l)
+    if (g.lv[l].hw % kTileW != 0) return 0;
+  const int ch = kBoxCh + g.num_classes;
+  const void* ptrs[3] = {p3, p4, p5};
+  CUtensorMap maps[3];
+  for (int l = 0; l < 3; ++l) {
+    const cuuint64_t dims[3] = {static_cast<cuuint64_t>(g.lv[l].hw), static_cast<cuuint64_t>(ch), static_cast<cuuint64_t>(B)};
+    const cuuint64_t strides[2] = {static_cast<cuuint64_t>(g.lv[l].hw) * sizeof(T),
+                                   static_cast<cuuint64_t>(g.lv[l].hw) * ch * sizeof(T)};
+    const cuuint32_t box[3] = {kTileW, static_cast<cuuint32_t>(ch), 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    if (ch > 256 || (strides[0] & 15) != 0) return 0;
+    const CUresult r = encode(&maps[l], tensor_map_dtype<T>(), 3, const_cast<void*>(ptrs[l]), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return 0;
+  }
+  TmaGeom tg;
+  tg.g = g;
+  tg.tiles_before[0] = 0;
+  for (int l = 0; l < 3; ++l) tg.tiles_before[l + 1] = tg.tiles_before[l] + g.lv[l].hw / kTileW;
+  tg.total_tiles = tg.tiles_before[3] * B;
+  tg.tile_bytes = ch * kTileW * static_cast<int>(sizeof(T));
+  if (tg.tile_bytes % 128 != 0) return 0;
+  // 16-bit heads: 4 stages x 22.5 KB, two CTAs per SM; f32 heads: 3 stages x 45 KB, one CTA per SM
+  tg.stages = sizeof(T) == 2 ? 4 : 3;
+  const int ctas_per_sm = sizeof(T) == 2 ? 2 : 1;
+  const size_t smem = static_cast<size_t>(tg.stages) * tg.tile_bytes;
+  static size_t configured = 0;
+  if (smem > configured) {
+    RTM_CUDA(cudaFuncSetAttribute(decode_tma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured = smem;
+  }
+  const int grid = min(tg.total_tiles, rtm::sm_count() * ctas_per_sm);
+  {
+    rtm::ProfileScope prof(RTM_K_DECODE, stream);
+    decode_tma_kernel<T><<<grid, kTmaThreads, smem, stream>>>(maps[0], maps[1], maps[2], tg, prm,
+                                                             logit_gate_for(prm.conf_thres), ws, status);
+  }
+  RTM_LAUNCH_CHECK("decode_tma_kernel");
+  return 1;
+}
+
 template <typename T, int VEC>
 int launch_decode(const void* p3, const void* p4, const void* p5, const HeadGeom& g, int B,
                   const rtm_nms_params& prm, const Workspace& ws, int32_t* status, cudaStream_t stream) {
@@ -570,15 +848,9 @@ int launch_decode(const void* p3, const void* p4, const void* p5, const HeadGeom
   HeadPtrs<T> heads{{static_cast<const T*>(p3), static_cast<const T*>(p4), static_cast<const T*>(p5)}};
   for (int l = 0; l < 3; ++l)
     RTM_REQUIRE((reinterpret_cast<uintptr_t>(heads.p[l]) & 15) == 0, "head level %d must be 16-byte aligned", l);
-  // gate on the raw logit: anything whose sigmoid could exceed conf_thres passes (the exact
-  // float32 test is repeated on the sigmoid itself inside warp_decode_anchor)
-  float gate;
-  if (prm.conf_thres <= 0.f) gate = -FLT_MAX;
-  else if (prm.conf_thres >= 1.f) gate = FLT_MAX;
-  else {
-    const double lg = log(static_cast<double>(prm.conf_thres) / (1.0 - static_cast<double>(prm.conf_thres)));
-    gate = static_cast<float>(lg - 1e-3 * (1.0 + fabs(lg)));
-  }
+  const int tma = try_launch_decode_tma<T>(p3, p4, p5, g, B, prm, ws, status, stream);
+  if (tma != 0) return tma < 0 ? tma : RTM_OK;
+  const float gate = logit_gate_for(prm.conf_thres);
   constexpr int THREADS = 128;
   const int groups = g.num_anchors / VEC;
   dim3 grid((groups + THREADS - 1) / THREADS, B);

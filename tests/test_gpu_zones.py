@@ -78,11 +78,10 @@ def test_facade_matches_oracle_with_arbitrary_track_lists(pkg, tmp_path):
     """Ids vanish and come back, call order differs from first-seen order, duplicate zone names
     share state, default dwell / cooldown, negative coordinates, table growth."""
     rng = np.random.default_rng(42)
-    zones = pkg.synth.make_zones(seed=1, num_zones=7, width=640, height=480, kmin=3, kmax=8, dwell_time_sec=0.3, cooldown_sec=0.7)
+    zones = pkg.synth.make_zones(seed=1, num_zones=7, width=640, height=480, kmin=3, kmax=8, dwell_time_sec=0.2, cooldown_sec=0.5)
     zones[4]["name"] = zones[1]["name"]
     zones[6] = dict(name="defaults", polygon=[[0, 0], [640, 0], [640, 480], [0, 480]])
-    for z in zones[:6]:
-        z["polygon"] = (np.asarray(z["polygon"]) // 2).tolist()
+    zones[5] = dict(name="left_half", polygon=[[0, 0], [320, 0], [320, 480], [0, 480]], dwell_time_sec=0.2, cooldown_sec=0.4)
     clock = {"t": 100.0}
     eng = pkg.ZoneEventEngine(zones, log_path=str(tmp_path / "ev.jsonl"), clock=lambda: clock["t"], initial_rows=8)
     orc = zone_ref.ZoneOracle(zones)
@@ -90,8 +89,8 @@ def test_facade_matches_oracle_with_arbitrary_track_lists(pkg, tmp_path):
     total = 0
     for f in range(200):
         clock["t"] = 100.0 + f * 0.11
-        pos += rng.uniform(-6, 6, pos.shape)
-        ids = rng.permutation(40)[: int(rng.integers(0, 30))]
+        pos += rng.uniform(-4, 4, pos.shape)
+        ids = rng.permutation(40)[: int(rng.integers(0, 41) if f % 17 else 0)]
         tracks = []
         for i in ids:
             b = np.array([pos[i, 0] - 5, pos[i, 1] - 9, pos[i, 0] + 5, pos[i, 1] + 9], np.float32)
