@@ -13,18 +13,22 @@
 //   N3  scale_boxes: subtract padding, divide by gain, clip to the source image
 //
 // Kernel plan
-//   decode_candidates  streams the class planes of the three head levels with 16-byte
-//                      loads (one thread = 8 bf16/f16 or 4 f32 consecutive anchors, running
-//                      max in registers), then the warp decodes the few anchors that can pass
-//                      the confidence test co-operatively (144 channels over 32 lanes, DFL
-//                      softmax with half-warp shuffles) and appends them to the stream's
-//                      candidate list in global memory
-//   nms                one CTA per stream: 64-bit key (score desc, anchor asc) bitonic sort
-//                      in shared memory, boxes gathered in sorted order, then the greedy scan
-//                      run one survivor at a time - every lane tests one later candidate
-//                      against the newest survivor and the alive bitmask is rebuilt with warp
-//                      ballots (ping-pong buffers, one __syncthreads per survivor) - stopping at
-//                      max_det; survivors are rescaled and written in score order.
+//   decode_tma   the production head scan.  Persistent CTAs; a producer warp pulls whole tiles
+//                (all 64 + nc channels x 80 consecutive anchors of one stream and level) into a
+//                ring of shared-memory stages with one TMA tensor copy each (full / empty
+//                mbarriers), so every head byte crosses HBM exactly once.  Ten consumer warps
+//                work independently of each other (no block barrier): a warp owns 8 anchors of
+//                the tile, its lanes are (anchor, class-quarter) pairs that scan the class rows
+//                bank-conflict free; the four lanes of an anchor combine by shuffle, and anchors
+//                that pass the confidence test get their four DFL sides decoded by their four
+//                lanes straight from shared memory.
+//   decode_ldg   fallback for shapes the tiling does not cover: 16-byte global loads of the
+//                class planes, warp-co-operative decode of the few passing anchors.
+//   candidates   are written dense by anchor plus a bitmask (see nms_body.cuh): no atomics, no
+//                per-frame reset, and the list order is ultralytics' filtered-tensor order.
+//   nms          one CTA per stream (nms_body.cuh): shuffle/shared-memory bitonic sort of 64-bit
+//                (score desc, rank asc) keys, greedy scan one survivor at a time with the alive
+//                bitmask rebuilt by warp ballots, stop at max_det, rescale, write in score order.
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through the runtime)
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -33,17 +37,17 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include "rtm_common.cuh"
+#include "nms_body.cuh"
 
 namespace {
 
+using rtm::kFull;
+using rtm::NmsOut;
+using rtm::Workspace;
+
 constexpr int kRegMax = 16;
 constexpr int kBoxCh = 4 * kRegMax;  // 64
-constexpr float kMaxWh = 7680.f;     // ultralytics non_max_suppression max_wh
 constexpr int kNmsThreads = 512;
-constexpr int kNmsSmemCand = 2048;   // candidates sorted / scanned from shared memory
-constexpr int kIdxBits = 15;         // candidate slot (< 32768) in the low key bits
-constexpr int kMaxAnchors = 1 << 15;
 
 struct Level {
   int h, w, hw, stride;
@@ -56,19 +60,6 @@ struct HeadGeom {
   int num_classes;
 };
 
-// candidate list of one stream inside the workspace
-struct Workspace {
-  int32_t* count;     // (B)
-  float4* box;        // (B, cap)  xyxy, letterbox pixels
-  float* score;       // (B, cap)
-  int32_t* meta;      // (B, cap)  anchor | cls << 16
-  uint64_t* keys;     // (B, cap_p2)  large-n fallback of the sort
-  float4* sbox;       // (B, cap)     large-n fallback of the sorted boxes
-  float* sarea;       // (B, cap)
-  uint32_t* alive;    // (B, 2, cap/32)
-  int cap, cap_p2;
-};
-
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int next_pow2(int v) {
@@ -78,31 +69,36 @@ int next_pow2(int v) {
 }
 
 size_t workspace_layout(int B, int A, char* base, Workspace* ws) {
-  const int cap = A, cap_p2 = next_pow2(A), words = (cap + 31) / 32;
+  const int words = (A + 31) / 32, cap_p2 = next_pow2(A);
   size_t off = 0;
   auto take = [&](size_t bytes) {
     size_t o = off;
     off = align_up(off + bytes, 256);
     return o;
   };
-  const size_t o_count = take(sizeof(int32_t) * B);
-  const size_t o_box = take(sizeof(float4) * B * cap);
-  const size_t o_score = take(sizeof(float) * B * cap);
-  const size_t o_meta = take(sizeof(int32_t) * B * cap);
+  const size_t o_mask = take(sizeof(uint32_t) * B * words);
+  const size_t o_box = take(sizeof(float4) * B * A);
+  const size_t o_score = take(sizeof(float) * B * A);
+  const size_t o_cls = take(sizeof(int32_t) * B * A);
   const size_t o_keys = take(sizeof(uint64_t) * B * cap_p2);
-  const size_t o_sbox = take(sizeof(float4) * B * cap);
-  const size_t o_sarea = take(sizeof(float) * B * cap);
+  const size_t o_ubox = take(sizeof(float4) * B * A);
+  const size_t o_sbox = take(sizeof(float4) * B * A);
+  const size_t o_sarea = take(sizeof(float) * B * A);
+  const size_t o_loc = take(sizeof(int32_t) * B * A);
   const size_t o_alive = take(sizeof(uint32_t) * B * 2 * words);
   if (ws) {
-    ws->count = reinterpret_cast<int32_t*>(base + o_count);
+    ws->mask = reinterpret_cast<uint32_t*>(base + o_mask);
     ws->box = reinterpret_cast<float4*>(base + o_box);
     ws->score = reinterpret_cast<float*>(base + o_score);
-    ws->meta = reinterpret_cast<int32_t*>(base + o_meta);
+    ws->cls = reinterpret_cast<int32_t*>(base + o_cls);
     ws->keys = reinterpret_cast<uint64_t*>(base + o_keys);
+    ws->ubox = reinterpret_cast<float4*>(base + o_ubox);
     ws->sbox = reinterpret_cast<float4*>(base + o_sbox);
     ws->sarea = reinterpret_cast<float*>(base + o_sarea);
+    ws->loc = reinterpret_cast<int32_t*>(base + o_loc);
     ws->alive = reinterpret_cast<uint32_t*>(base + o_alive);
-    ws->cap = cap;
+    ws->num_anchors = A;
+    ws->words = words;
     ws->cap_p2 = cap_p2;
   }
   return off;
@@ -134,152 +130,42 @@ __device__ __forceinline__ float4 dist_to_xyxy(float l, float t, float r, float 
   return make_float4(__fsub_rn(cx, dw), __fsub_rn(cy, dh), __fadd_rn(cx, dw), __fadd_rn(cy, dh));
 }
 
-__device__ __forceinline__ void append_candidate(const Workspace& ws, int b, float4 box, float score,
-                                                 int cls, int anchor, int32_t* status) {
-  const int slot = atomicAdd(&ws.count[b], 1);
-  if (slot < ws.cap) {
-    const size_t o = static_cast<size_t>(b) * ws.cap + slot;
-    ws.box[o] = box;
-    ws.score[o] = score;
-    ws.meta[o] = anchor | (cls << 16);
-  } else if (status) {
-    atomicOr(&status[b], RTM_STATUS_CAND_OVERFLOW);
+// DFL expectation of one side from 16 logits (sequential order, shared by all decode kernels)
+__device__ __forceinline__ float dfl_expectation(float (&x)[kRegMax]) {
+  float mx = -FLT_MAX;
+#pragma unroll
+  for (int k = 0; k < kRegMax; ++k) mx = fmaxf(mx, x[k]);
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < kRegMax; ++k) {
+    x[k] = expf(__fsub_rn(x[k], mx));
+    sum = __fadd_rn(sum, x[k]);
   }
+  float acc = 0.f;
+#pragma unroll
+  for (int k = 0; k < kRegMax; ++k) acc = __fadd_rn(acc, __fmul_rn(static_cast<float>(k), __fdiv_rn(x[k], sum)));
+  return acc;
 }
 
-// ---------------------------------------------------------------------------------------
-// decode_candidates
-// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_candidate(const Workspace& ws, int b, int anchor, float4 box, float score, int cls) {
+  const size_t o = static_cast<size_t>(b) * ws.num_anchors + anchor;
+  ws.box[o] = box;
+  ws.score[o] = score;
+  ws.cls[o] = cls;
+}
+
 template <typename T>
 struct HeadPtrs {
   const T* p[3];
 };
 
-template <typename T, int VEC>
-struct alignas(16) Pack {
-  T v[VEC];
-};
-
-// The warp decodes anchor `pix` of level `lv` of stream b: lane c handles channels
-// c, c+32, ... of the 64 + nc channels.  Returns nothing; lane 0 appends the candidate.
-template <typename T>
-__device__ __forceinline__ void warp_decode_anchor(const T* __restrict__ base, const Level lv, int pix,
-                                                   int nc, const rtm_nms_params& prm,
-                                                   const Workspace& ws, int b, int32_t* status) {
-  const int lane = threadIdx.x & 31;
-  // class part: first arg-max of sigmoid over nc classes
-  float best = -1.f;
-  int bc = 0x7fffffff;
-  for (int c = lane; c < nc; c += 32) {
-    const float s = sigmoidf_rn(to_float(base[static_cast<size_t>(kBoxCh + c) * lv.hw + pix]));
-    if (s > best) {
-      best = s;
-      bc = c;
-    }
-  }
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) {
-    const float ob = __shfl_xor_sync(rtm::kFull, best, d);
-    const int oc = __shfl_xor_sync(rtm::kFull, bc, d);
-    if (ob > best || (ob == best && oc < bc)) {
-      best = ob;
-      bc = oc;
-    }
-  }
-  if (!(best > prm.conf_thres)) return;  // amax(1) > conf_thres, strict
-  if (!class_wanted(prm, bc)) return;    // `classes` filter acts on the arg-max class
-
-  // box part: lanes 0-15 / 16-31 hold side l / t (first load) and r / b (second load)
-  float d4[2];
-#pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    const float x = to_float(base[static_cast<size_t>(lane + 32 * k) * lv.hw + pix]);
-    float m = x;
-#pragma unroll
-    for (int d = 8; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(rtm::kFull, m, d));
-    const float e = expf(__fsub_rn(x, m));
-    float s = e;
-#pragma unroll
-    for (int d = 8; d > 0; d >>= 1) s = __fadd_rn(s, __shfl_xor_sync(rtm::kFull, s, d));
-    float v = __fmul_rn(static_cast<float>(lane & 15), __fdiv_rn(e, s));
-#pragma unroll
-    for (int d = 8; d > 0; d >>= 1) v = __fadd_rn(v, __shfl_xor_sync(rtm::kFull, v, d));
-    d4[k] = v;
-  }
-  const float dl = __shfl_sync(rtm::kFull, d4[0], 0), dt = __shfl_sync(rtm::kFull, d4[0], 16);
-  const float dr = __shfl_sync(rtm::kFull, d4[1], 0), db = __shfl_sync(rtm::kFull, d4[1], 16);
-  if (lane == 0) {
-    const float ax = static_cast<float>(pix % lv.w) + 0.5f, ay = static_cast<float>(pix / lv.w) + 0.5f;
-    const float4 box = dist_to_xyxy(dl, dt, dr, db, ax, ay, static_cast<float>(lv.stride), nullptr);
-    append_candidate(ws, b, box, best, bc, lv.anchor0 + pix, status);
-  }
-}
-
-template <typename T, int VEC, int THREADS>
-__global__ void __launch_bounds__(THREADS) decode_candidates_kernel(const HeadPtrs<T> heads, const HeadGeom g,
-                                                                    const rtm_nms_params prm,
-                                                                    const float logit_gate, const Workspace ws,
-                                                                    int32_t* status) {
-  const int b = blockIdx.y;
-  const int grp = blockIdx.x * THREADS + threadIdx.x;  // group of VEC consecutive anchors
-  const int a0 = grp * VEC;
-  int li = 0;
-  if (a0 >= g.lv[1].anchor0) li = 1;
-  if (a0 >= g.lv[2].anchor0) li = 2;
-  const Level lv = g.lv[li];
-  const bool in_range = a0 < g.num_anchors;
-  const int pix0 = a0 - lv.anchor0;
-  const int nc = g.num_classes;
-  const T* base = heads.p[li] + static_cast<size_t>(b) * (kBoxCh + nc) * lv.hw;
-
-  float mx[VEC];
-#pragma unroll
-  for (int e = 0; e < VEC; ++e) mx[e] = -FLT_MAX;
-  if (in_range) {
-    const T* cls = base + static_cast<size_t>(kBoxCh) * lv.hw + pix0;
-#pragma unroll 8
-    for (int c = 0; c < nc; ++c) {
-      const Pack<T, VEC> v = *reinterpret_cast<const Pack<T, VEC>*>(cls + static_cast<size_t>(c) * lv.hw);
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) mx[e] = fmaxf(mx[e], to_float(v.v[e]));
-    }
-  }
-  unsigned pending = 0;
-#pragma unroll
-  for (int e = 0; e < VEC; ++e)
-    if (in_range && mx[e] > logit_gate) pending |= 1u << e;
-
-  // warp-cooperative decode of the anchors that passed the gate, in (lane, e) order
-  unsigned lanes = __ballot_sync(rtm::kFull, pending != 0);
-  while (lanes) {
-    const int src = __ffs(lanes) - 1;
-    const unsigned bits = __shfl_sync(rtm::kFull, pending, src);
-    const int spix0 = __shfl_sync(rtm::kFull, pix0, src);
-    const int sli = __shfl_sync(rtm::kFull, li, src);
-    const Level slv = g.lv[sli];
-    const T* sbase = heads.p[sli] + static_cast<size_t>(b) * (kBoxCh + nc) * slv.hw;
-    unsigned rem = bits;
-    while (rem) {
-      const int e = __ffs(rem) - 1;
-      rem &= rem - 1;
-      warp_decode_anchor<T>(sbase, slv, spix0 + e, nc, prm, ws, b, status);
-    }
-    lanes &= lanes - 1;
-  }
-}
-
 // ---------------------------------------------------------------------------------------
-// decode_tma: the production head scan.  Persistent CTAs pull whole tiles (all 64 + nc
-// channels x TW consecutive anchors of one stream and level) into shared memory with one
-// TMA tensor copy each (cp.async.bulk.tensor.3d, mbarrier completion, kStages deep), so every
-// head byte crosses HBM exactly once and no register is tied up by loads in flight.  A tile
-// is consumed by 4 x TW threads: thread (anchor a, quarter q) scans a quarter of the class
-// rows of its anchor; anchors whose best class passes the confidence test get their four DFL
-// sides decoded by their four threads straight from shared memory.
+// decode_tma
 // ---------------------------------------------------------------------------------------
-constexpr int kTileW = 80;    // divides 6400 / 1600 / 400 (and every level of a W=640, H%128==0 input)
-constexpr int kQuarters = 4;
-constexpr int kTmaThreads = kTileW * kQuarters;  // 320
+constexpr int kTileW = 80;  // divides 6400 / 1600 / 400 (and every level of a W = 640, H % 128 == 0 input)
+constexpr int kConsumerWarps = kTileW / 8;              // 10: a warp owns 8 anchors of the tile
+constexpr int kTmaThreads = (kConsumerWarps + 1) * 32;  // + one producer warp
+constexpr int kMaxStages = 8;
 
 struct TmaGeom {
   HeadGeom g;
@@ -298,6 +184,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -312,7 +201,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  // bounded: a lost TMA completion traps (launch error) instead of hanging the GPU
+  // bounded: a lost completion traps (launch error) instead of hanging the GPU
   for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
     if (spin > (1u << 26)) __trap();
 }
@@ -328,23 +217,19 @@ __global__ void __launch_bounds__(kTmaThreads) decode_tma_kernel(const __grid_co
                                                                  const __grid_constant__ CUtensorMap map1,
                                                                  const __grid_constant__ CUtensorMap map2,
                                                                  const TmaGeom tg, const rtm_nms_params prm,
-                                                                 const float logit_gate, const Workspace ws,
-                                                                 int32_t* status) {
+                                                                 const float logit_gate, const Workspace ws) {
   extern __shared__ __align__(128) unsigned char tile_smem[];
-  __shared__ __align__(8) uint64_t full_bar[8];
-  __shared__ float s_score[kQuarters][kTileW];
-  __shared__ int s_class[kQuarters][kTileW];
-  __shared__ float s_dist[kQuarters][kTileW];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
 
-  const int tid = threadIdx.x;
-  const int a = tid % kTileW, q = tid / kTileW;
-  const int nc = tg.g.num_classes, stages = tg.stages;
-  const int per_q = (nc + kQuarters - 1) / kQuarters;
-  const int c_lo = min(q * per_q, nc), c_hi = min(c_lo + per_q, nc);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int stages = tg.stages;
   const int tps = tg.tiles_before[3];
-
   if (tid == 0) {
-    for (int s = 0; s < stages; ++s) mbar_init(&full_bar[s], 1);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], kConsumerWarps);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -352,99 +237,217 @@ __global__ void __launch_bounds__(kTmaThreads) decode_tma_kernel(const __grid_co
   const int first = blockIdx.x, step = gridDim.x;
   const int my_tiles = first < tg.total_tiles ? (tg.total_tiles - first + step - 1) / step : 0;
 
-  auto issue = [&](int it) {  // thread 0 only
-    const int t = first + it * step;
-    const int b = t / tps, r = t - b * tps;
-    const int li = r >= tg.tiles_before[2] ? 2 : (r >= tg.tiles_before[1] ? 1 : 0);
-    const int x = (r - tg.tiles_before[li]) * kTileW;
-    const int s = it % stages;
-    mbar_expect_tx(&full_bar[s], tg.tile_bytes);
-    tma_load_tile(tile_smem + static_cast<size_t>(s) * tg.tile_bytes, li == 0 ? &map0 : (li == 1 ? &map1 : &map2),
-                  &full_bar[s], x, b);
-  };
-  if (tid == 0)
-    for (int it = 0; it < min(stages, my_tiles); ++it) issue(it);
+  if (warp == kConsumerWarps) {
+    // ===== producer warp: one elected lane keeps the ring full =====
+    if (lane == 0) {
+      for (int it = 0; it < my_tiles; ++it) {
+        const int s = it % stages, fill = it / stages;
+        if (fill > 0) mbar_wait(&empty_bar[s], (fill - 1) & 1);
+        const int t = first + it * step;
+        const int b = t / tps, r = t - b * tps;
+        const int li = r >= tg.tiles_before[2] ? 2 : (r >= tg.tiles_before[1] ? 1 : 0);
+        const int x = (r - tg.tiles_before[li]) * kTileW;
+        mbar_expect_tx(&full_bar[s], tg.tile_bytes);
+        tma_load_tile(tile_smem + static_cast<size_t>(s) * tg.tile_bytes, li == 0 ? &map0 : (li == 1 ? &map1 : &map2),
+                      &full_bar[s], x, b);
+      }
+    }
+    return;
+  }
+
+  // ===== consumer warps =====
+  const int al = lane & 7, q = lane >> 3;  // anchor within the warp's 8, class quarter / DFL side
+  const int col = warp * 8 + al;           // anchor column inside the tile
+  const int nc = tg.g.num_classes;
+  const int iters = (nc + 3) >> 2;         // quarter q scans classes q, q + 4, q + 8, ... (bank-conflict free)
 
   for (int it = 0; it < my_tiles; ++it) {
     const int t = first + it * step;
     const int b = t / tps, r = t - b * tps;
     const int li = r >= tg.tiles_before[2] ? 2 : (r >= tg.tiles_before[1] ? 1 : 0);
-    const Level lv = tg.g.lv[li];
-    const int pix = (r - tg.tiles_before[li]) * kTileW + a;
+    const int lv_w = tg.g.lv[li].w, lv_stride = tg.g.lv[li].stride, lv_anchor0 = tg.g.lv[li].anchor0;
+    const int pix = (r - tg.tiles_before[li]) * kTileW + col;
     const int s = it % stages;
     mbar_wait(&full_bar[s], (it / stages) & 1);
     const T* tile = reinterpret_cast<const T*>(tile_smem + static_cast<size_t>(s) * tg.tile_bytes);
+    const T* cls_col = tile + kBoxCh * kTileW + col;
 
-    // ---- class scan of this thread's quarter: running max, its first index, and the best
-    //      value seen BEFORE that index (to detect sigmoid ties between different logits) ----
-    float m = -FLT_MAX, m2 = -FLT_MAX;
-    int j = c_lo;
-#pragma unroll 4
-    for (int c = c_lo; c < c_hi; ++c) {
-      const float v = to_float(tile[(kBoxCh + c) * kTileW + a]);
-      if (v > m) {
-        m2 = m;
-        m = v;
-        j = c;
-      }
+    // ---- N1 gate: max class logit of the anchor (quarter maxima combined by shuffle) ----
+    float m = -FLT_MAX;
+#pragma unroll 5
+    for (int i = 0; i < iters; ++i) {
+      const int c = 4 * i + q;
+      if (c < nc) m = fmaxf(m, to_float(cls_col[c * kTileW]));
     }
-    float sc = -1.f;
-    if (m > logit_gate) {
-      sc = sigmoidf_rn(m);
-      if (m2 > logit_gate && sigmoidf_rn(m2) == sc) {
-        // two different logits round to the same probability: the FIRST class reaching it wins
-        for (int c = c_lo; c < j; ++c)
-          if (sigmoidf_rn(to_float(tile[(kBoxCh + c) * kTileW + a])) == sc) {
-            j = c;
-            break;
+    float am = fmaxf(m, __shfl_xor_sync(kFull, m, 8));
+    am = fmaxf(am, __shfl_xor_sync(kFull, am, 16));
+
+    bool cand = false;
+    float best = -1.f;
+    int bc = 0;
+    if (__any_sync(kFull, am > logit_gate)) {
+      // ---- exact N1 for the anchors that can pass: first arg-max of the float32 sigmoid ----
+      float sc = -1.f;
+      int j = 0x7fffffff;
+      if (m > logit_gate) {
+        sc = sigmoidf_rn(m);
+        for (int i = 0; i < iters; ++i) {  // first class of this quarter whose probability equals the maximum
+          const int c = 4 * i + q;
+          if (c < nc) {
+            const float v = to_float(cls_col[c * kTileW]);
+            if (v > logit_gate && sigmoidf_rn(v) == sc) {
+              j = c;
+              break;
+            }
           }
+        }
+      }
+      best = sc;
+      bc = j;
+#pragma unroll
+      for (int d = 8; d <= 16; d <<= 1) {
+        const float ob = __shfl_xor_sync(kFull, best, d);
+        const int oc = __shfl_xor_sync(kFull, bc, d);
+        if (ob > best || (ob == best && oc < bc)) {
+          best = ob;
+          bc = oc;
+        }
+      }
+      cand = best > prm.conf_thres && class_wanted(prm, bc & 255);
+      if (__any_sync(kFull, cand)) {
+        // ---- D1 for the survivors: lane q decodes side q; the q = 0 lane assembles the box ----
+        float dist = 0.f;
+        if (cand) {
+          float x[kRegMax];
+#pragma unroll
+          for (int k = 0; k < kRegMax; ++k) x[k] = to_float(tile[(q * kRegMax + k) * kTileW + col]);
+          dist = dfl_expectation(x);
+        }
+        const float dt = __shfl_down_sync(kFull, dist, 8);
+        const float dr = __shfl_down_sync(kFull, dist, 16);
+        const float db = __shfl_down_sync(kFull, dist, 24);
+        if (cand && q == 0) {
+          const float ax = static_cast<float>(pix % lv_w) + 0.5f, ay = static_cast<float>(pix / lv_w) + 0.5f;
+          store_candidate(ws, b, lv_anchor0 + pix,
+                          dist_to_xyxy(dist, dt, dr, db, ax, ay, static_cast<float>(lv_stride), nullptr), best, bc);
+        }
       }
     }
-    s_score[q][a] = sc;
-    s_class[q][a] = j;
-    __syncthreads();
+    // candidate bits of this warp's 8 anchors: one byte of the stream's mask
+    const uint32_t bits = __ballot_sync(kFull, cand && q == 0) & 0xffu;
+    if (lane == 0)
+      reinterpret_cast<uint8_t*>(ws.mask + static_cast<size_t>(b) * ws.words)[(lv_anchor0 + pix) >> 3] = static_cast<uint8_t>(bits);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);  // this warp is done with the stage
+  }
+}
 
-    // ---- combine the quarters (ascending class order, strict >: first arg-max) ----
-    float best = s_score[0][a];
-    int bc = s_class[0][a];
-#pragma unroll
-    for (int k = 1; k < kQuarters; ++k) {
-      const float o = s_score[k][a];
-      if (o > best) {
-        best = o;
-        bc = s_class[k][a];
-      }
-    }
-    const bool cand = best > prm.conf_thres && class_wanted(prm, bc);
-    if (cand) {
-      // DFL side q of this anchor, same operation order as decode_head_kernel
-      float x[kRegMax], mx = -FLT_MAX;
-#pragma unroll
-      for (int k = 0; k < kRegMax; ++k) {
-        x[k] = to_float(tile[(q * kRegMax + k) * kTileW + a]);
-        mx = fmaxf(mx, x[k]);
-      }
-      float sum = 0.f;
-#pragma unroll
-      for (int k = 0; k < kRegMax; ++k) {
-        x[k] = expf(__fsub_rn(x[k], mx));
-        sum = __fadd_rn(sum, x[k]);
-      }
-      float acc = 0.f;
-#pragma unroll
-      for (int k = 0; k < kRegMax; ++k) acc = __fadd_rn(acc, __fmul_rn(static_cast<float>(k), __fdiv_rn(x[k], sum)));
-      s_dist[q][a] = acc;
-    }
-    __syncthreads();  // all reads of the tile are done: its stage can be refilled
+// ---------------------------------------------------------------------------------------
+// decode_ldg (fallback)
+// ---------------------------------------------------------------------------------------
+constexpr int kVec = 8;  // anchors per thread = one byte of the candidate mask
 
-    if (tid == 0 && it + stages < my_tiles) issue(it + stages);
-    if (cand && q == 0) {
-      const float ax = static_cast<float>(pix % lv.w) + 0.5f, ay = static_cast<float>(pix / lv.w) + 0.5f;
-      const float4 box = dist_to_xyxy(s_dist[0][a], s_dist[1][a], s_dist[2][a], s_dist[3][a], ax, ay,
-                                      static_cast<float>(lv.stride), nullptr);
-      append_candidate(ws, b, box, best, bc, lv.anchor0 + pix, status);
+// The warp decodes anchor `pix` of level `lv` of stream b: lane c handles channels c, c+32, ...
+// Returns (uniformly) whether the anchor is a candidate; lane 0 stores it.
+template <typename T>
+__device__ __forceinline__ bool warp_decode_anchor(const T* __restrict__ base, const Level lv, int pix, int nc,
+                                                   const rtm_nms_params& prm, const Workspace& ws, int b) {
+  const int lane = threadIdx.x & 31;
+  float best = -1.f;
+  int bc = 0x7fffffff;
+  for (int c = lane; c < nc; c += 32) {
+    const float s = sigmoidf_rn(to_float(base[static_cast<size_t>(kBoxCh + c) * lv.hw + pix]));
+    if (s > best) {
+      best = s;
+      bc = c;
     }
   }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const float ob = __shfl_xor_sync(kFull, best, d);
+    const int oc = __shfl_xor_sync(kFull, bc, d);
+    if (ob > best || (ob == best && oc < bc)) {
+      best = ob;
+      bc = oc;
+    }
+  }
+  if (!(best > prm.conf_thres)) return false;  // amax(1) > conf_thres, strict
+  if (!class_wanted(prm, bc)) return false;    // `classes` filter acts on the arg-max class
+  // box part: 4 lanes, one side each, sequential DFL (same operation order as the other kernels)
+  float dist = 0.f;
+  if (lane < 4) {
+    float x[kRegMax];
+#pragma unroll
+    for (int k = 0; k < kRegMax; ++k) x[k] = to_float(base[static_cast<size_t>(lane * kRegMax + k) * lv.hw + pix]);
+    dist = dfl_expectation(x);
+  }
+  const float dt = __shfl_sync(kFull, dist, 1), dr = __shfl_sync(kFull, dist, 2), db = __shfl_sync(kFull, dist, 3);
+  if (lane == 0) {
+    const float ax = static_cast<float>(pix % lv.w) + 0.5f, ay = static_cast<float>(pix / lv.w) + 0.5f;
+    store_candidate(ws, b, lv.anchor0 + pix, dist_to_xyxy(dist, dt, dr, db, ax, ay, static_cast<float>(lv.stride), nullptr),
+                    best, bc);
+  }
+  return true;
+}
+
+template <typename T, int THREADS>
+__global__ void __launch_bounds__(THREADS) decode_ldg_kernel(const HeadPtrs<T> heads, const HeadGeom g,
+                                                             const rtm_nms_params prm, const float logit_gate,
+                                                             const Workspace ws) {
+  const int b = blockIdx.y;
+  const int grp = blockIdx.x * THREADS + threadIdx.x;  // group of 8 consecutive anchors
+  const int a0 = grp * kVec;
+  int li = 0;
+  if (a0 >= g.lv[1].anchor0) li = 1;
+  if (a0 >= g.lv[2].anchor0) li = 2;
+  const Level lv = g.lv[li];
+  const bool in_range = a0 < g.num_anchors;
+  const int pix0 = a0 - lv.anchor0;
+  const int nc = g.num_classes;
+  const T* base = heads.p[li] + static_cast<size_t>(b) * (kBoxCh + nc) * lv.hw;
+  constexpr int kPer16 = 16 / sizeof(T);  // elements per 16-byte load
+
+  float mx[kVec];
+#pragma unroll
+  for (int e = 0; e < kVec; ++e) mx[e] = -FLT_MAX;
+  if (in_range) {
+    const T* cls = base + static_cast<size_t>(kBoxCh) * lv.hw + pix0;
+#pragma unroll 4
+    for (int c = 0; c < nc; ++c) {
+#pragma unroll
+      for (int h = 0; h < kVec / kPer16; ++h) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(cls + static_cast<size_t>(c) * lv.hw + h * kPer16);
+        const T* v = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+        for (int e = 0; e < kPer16; ++e) mx[h * kPer16 + e] = fmaxf(mx[h * kPer16 + e], to_float(v[e]));
+      }
+    }
+  }
+  unsigned pending = 0;
+#pragma unroll
+  for (int e = 0; e < kVec; ++e)
+    if (in_range && mx[e] > logit_gate) pending |= 1u << e;
+
+  unsigned mine = 0;  // candidate bits of this thread's 8 anchors
+  unsigned lanes = __ballot_sync(kFull, pending != 0);
+  while (lanes) {
+    const int src = __ffs(lanes) - 1;
+    const unsigned bits = __shfl_sync(kFull, pending, src);
+    const int spix0 = __shfl_sync(kFull, pix0, src);
+    const int sli = __shfl_sync(kFull, li, src);
+    const Level slv = g.lv[sli];
+    const T* sbase = heads.p[sli] + static_cast<size_t>(b) * (kBoxCh + nc) * slv.hw;
+    unsigned rem = bits;
+    while (rem) {
+      const int e = __ffs(rem) - 1;
+      rem &= rem - 1;
+      const bool is_cand = warp_decode_anchor<T>(sbase, slv, spix0 + e, nc, prm, ws, b);
+      if (is_cand && (threadIdx.x & 31) == src) mine |= 1u << e;
+    }
+    lanes &= lanes - 1;
+  }
+  if (in_range)
+    reinterpret_cast<uint8_t*>(ws.mask + static_cast<size_t>(b) * ws.words)[a0 >> 3] = static_cast<uint8_t>(mine);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -464,22 +467,10 @@ __global__ void decode_head_kernel(const HeadPtrs<T> heads, const HeadGeom g, fl
   const T* base = heads.p[li] + static_cast<size_t>(b) * (kBoxCh + nc) * lv.hw + pix;
   float dist[4];
   for (int s = 0; s < 4; ++s) {
-    float x[kRegMax], m = -FLT_MAX;
+    float x[kRegMax];
 #pragma unroll
-    for (int k = 0; k < kRegMax; ++k) {
-      x[k] = to_float(base[static_cast<size_t>(s * kRegMax + k) * lv.hw]);
-      m = fmaxf(m, x[k]);
-    }
-    float sum = 0.f;
-#pragma unroll
-    for (int k = 0; k < kRegMax; ++k) {
-      x[k] = expf(__fsub_rn(x[k], m));
-      sum = __fadd_rn(sum, x[k]);
-    }
-    float acc = 0.f;
-#pragma unroll
-    for (int k = 0; k < kRegMax; ++k) acc = __fadd_rn(acc, __fmul_rn(static_cast<float>(k), __fdiv_rn(x[k], sum)));
-    dist[s] = acc;
+    for (int k = 0; k < kRegMax; ++k) x[k] = to_float(base[static_cast<size_t>(s * kRegMax + k) * lv.hw]);
+    dist[s] = dfl_expectation(x);
   }
   float4 xywh;
   dist_to_xyxy(dist[0], dist[1], dist[2], dist[3], static_cast<float>(pix % lv.w) + 0.5f,
@@ -497,204 +488,59 @@ __global__ void decode_head_kernel(const HeadPtrs<T> heads, const HeadGeom g, fl
 // ---------------------------------------------------------------------------------------
 // pred_candidates: N1 on an already decoded (B, 4 + nc, A) tensor (rtm_nms_pred)
 // ---------------------------------------------------------------------------------------
-__global__ void pred_candidates_kernel(const float* __restrict__ pred, int A, int nc, const rtm_nms_params prm,
-                                       const Workspace ws, int32_t* status) {
+__global__ void __launch_bounds__(256) pred_candidates_kernel(const float* __restrict__ pred, int A, int nc,
+                                                              const rtm_nms_params prm, const Workspace ws) {
   const int b = blockIdx.y;
-  const int a = blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= A) return;
-  const float* p = pred + static_cast<size_t>(b) * (4 + nc) * A + a;
-  float best = p[4 * static_cast<size_t>(A)];
-  int bc = 0;
-  for (int c = 1; c < nc; ++c) {
-    const float s = p[(4 + c) * static_cast<size_t>(A)];
-    if (s > best) {  // strict: first arg-max
-      best = s;
-      bc = c;
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;  // blockDim is a multiple of 32: a warp = one mask word
+  bool cand = false;
+  if (a < A) {
+    const float* p = pred + static_cast<size_t>(b) * (4 + nc) * A + a;
+    float best = p[4 * static_cast<size_t>(A)];
+    int bc = 0;
+    for (int c = 1; c < nc; ++c) {
+      const float s = p[(4 + c) * static_cast<size_t>(A)];
+      if (s > best) {  // strict: first arg-max
+        best = s;
+        bc = c;
+      }
+    }
+    cand = best > prm.conf_thres && class_wanted(prm, bc);
+    if (cand) {
+      const float cx = p[0], cy = p[A], w = p[2 * static_cast<size_t>(A)], h = p[3 * static_cast<size_t>(A)];
+      const float dw = __fdiv_rn(w, 2.f), dh = __fdiv_rn(h, 2.f);
+      store_candidate(ws, b, a, make_float4(__fsub_rn(cx, dw), __fsub_rn(cy, dh), __fadd_rn(cx, dw), __fadd_rn(cy, dh)),
+                      best, bc);
     }
   }
-  if (!(best > prm.conf_thres) || !class_wanted(prm, bc)) return;
-  const float cx = p[0], cy = p[A], w = p[2 * static_cast<size_t>(A)], h = p[3 * static_cast<size_t>(A)];
-  const float dw = __fdiv_rn(w, 2.f), dh = __fdiv_rn(h, 2.f);
-  append_candidate(ws, b, make_float4(__fsub_rn(cx, dw), __fsub_rn(cy, dh), __fadd_rn(cx, dw), __fadd_rn(cy, dh)),
-                   best, bc, a, status);
+  const uint32_t word = __ballot_sync(kFull, cand);
+  if ((threadIdx.x & 31) == 0 && a < A) ws.mask[static_cast<size_t>(b) * ws.words + (a >> 5)] = word;
 }
 
 // ---------------------------------------------------------------------------------------
 // nms
 // ---------------------------------------------------------------------------------------
-struct NmsOut {
-  const float* scale;
-  float* xyxy;
-  float* conf;
-  int32_t* cls;
-  int32_t* anchor;
-  int32_t* keep;
-  int32_t* count;
-  int32_t stride;
-  int32_t* status;
-};
-
-__device__ __forceinline__ void bitonic_sort(uint64_t* keys, int P) {
-  for (int k = 2; k <= P; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < P; i += kNmsThreads) {
-        const int ixj = i ^ j;
-        if (ixj > i) {
-          const uint64_t x = keys[i], y = keys[ixj];
-          const bool up = (i & k) == 0;
-          if ((x > y) == up) {
-            keys[i] = y;
-            keys[ixj] = x;
-          }
-        }
-      }
-      __syncthreads();
-    }
-  }
-}
-
 __global__ void __launch_bounds__(kNmsThreads) nms_kernel(const Workspace ws, const rtm_nms_params prm,
                                                           const float iou_gate, const NmsOut out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int s_keep[1024];
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int kWarps = kNmsThreads / 32;
-  int n = ws.count[b];
-  if (n > ws.cap) n = ws.cap;  // overflow already flagged by the producer
-  const size_t c0 = static_cast<size_t>(b) * ws.cap;
-  const int max_det = min(min(prm.max_det, out.stride), 1024);
-
-  if (n <= 0) {
-    if (tid == 0) out.count[b] = 0;
-    return;
-  }
-  int P = 1;
-  while (P < n) P <<= 1;
-  const int words = (n + 31) >> 5;
-  const bool in_smem = n <= kNmsSmemCand;
-  uint64_t* keys = in_smem ? reinterpret_cast<uint64_t*>(smem_raw) : ws.keys + static_cast<size_t>(b) * ws.cap_p2;
-  float4* sbox = in_smem ? reinterpret_cast<float4*>(smem_raw + sizeof(uint64_t) * kNmsSmemCand) : ws.sbox + c0;
-  float* sarea = in_smem ? reinterpret_cast<float*>(smem_raw + (sizeof(uint64_t) + sizeof(float4)) * kNmsSmemCand)
-                         : ws.sarea + c0;
-  uint32_t* alive0 = in_smem ? reinterpret_cast<uint32_t*>(smem_raw + (sizeof(uint64_t) + sizeof(float4) + sizeof(float)) * kNmsSmemCand)
-                             : ws.alive + static_cast<size_t>(b) * 2 * ((ws.cap + 31) / 32);
-  uint32_t* alive1 = alive0 + (in_smem ? kNmsSmemCand / 32 : (ws.cap + 31) / 32);
-
-  // keys: descending score, then ascending anchor (= torchvision's stable sort of the
-  // filtered list, whose order is anchor order); low bits carry the candidate slot
-  for (int i = tid; i < P; i += kNmsThreads) {
-    uint64_t key = ~0ull;
-    if (i < n) {
-      const uint32_t s = ~rtm::float_orderable(ws.score[c0 + i]);
-      const uint32_t anchor = static_cast<uint32_t>(ws.meta[c0 + i]) & 0xffffu;
-      key = (static_cast<uint64_t>(s) << 32) | (static_cast<uint64_t>(anchor) << kIdxBits) | static_cast<uint32_t>(i);
-    }
-    keys[i] = key;
-  }
-  __syncthreads();
-  bitonic_sort(keys, P);
-
-  // gather boxes in sorted order, add the class offset (float32), areas as torchvision does
-  for (int i = tid; i < n; i += kNmsThreads) {
-    const int slot = static_cast<int>(keys[i] & ((1u << kIdxBits) - 1u));
-    float4 bx = ws.box[c0 + slot];
-    const int cls = ws.meta[c0 + slot] >> 16;
-    const float off = prm.agnostic ? 0.f : __fmul_rn(static_cast<float>(cls), kMaxWh);
-    bx.x = __fadd_rn(bx.x, off);
-    bx.y = __fadd_rn(bx.y, off);
-    bx.z = __fadd_rn(bx.z, off);
-    bx.w = __fadd_rn(bx.w, off);
-    sbox[i] = bx;
-    sarea[i] = __fmul_rn(__fsub_rn(bx.z, bx.x), __fsub_rn(bx.w, bx.y));
-  }
-  for (int w = tid; w < words; w += kNmsThreads) {
-    const int rem = n - (w << 5);
-    alive0[w] = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
-  }
-  __syncthreads();
-
-  // greedy scan, one survivor per iteration
-  uint32_t* cur = alive0;
-  uint32_t* nxt = alive1;
-  int w0 = 0, kept = 0;
-  while (kept < max_det) {
-    while (w0 < words && cur[w0] == 0u) ++w0;
-    if (w0 >= words) break;
-    const int i = (w0 << 5) + __ffs(cur[w0]) - 1;
-    const float4 kb = sbox[i];
-    const float ka = sarea[i];
-    if (tid == 0) s_keep[kept] = i;
-    ++kept;
-    for (int w = w0 + warp; w < words; w += kWarps) {
-      const uint32_t word = cur[w];
-      const int j = (w << 5) + lane;
-      bool alive = ((word >> lane) & 1u) && j != i;
-      if (alive) {
-        const float4 jb = sbox[j];
-        const float iw = fmaxf(0.f, __fsub_rn(fminf(kb.z, jb.z), fmaxf(kb.x, jb.x)));
-        const float ih = fmaxf(0.f, __fsub_rn(fminf(kb.w, jb.w), fmaxf(kb.y, jb.y)));
-        const float inter = __fmul_rn(iw, ih);
-        const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ka, sarea[j]), inter));
-        alive = !(ovr >= iou_gate);  // iou_gate: smallest float32 that is > iou_thres in double
-      }
-      const uint32_t nw = __ballot_sync(rtm::kFull, alive);
-      if (lane == 0) nxt[w] = nw;
-    }
-    __syncthreads();
-    uint32_t* t = cur;
-    cur = nxt;
-    nxt = t;
-  }
-  __syncthreads();
-
-  // write the survivors in score order: original box -> scale_boxes -> clip
-  float gain = 1.f, padx = 0.f, pady = 0.f, sw = 0.f, sh = 0.f;
-  if (out.scale) {
-    gain = out.scale[b * 5 + 0];
-    padx = out.scale[b * 5 + 1];
-    pady = out.scale[b * 5 + 2];
-    sw = out.scale[b * 5 + 3];
-    sh = out.scale[b * 5 + 4];
-  }
-  const size_t o0 = static_cast<size_t>(b) * out.stride;
-  for (int o = tid; o < kept; o += kNmsThreads) {
-    const uint64_t key = keys[s_keep[o]];
-    const int slot = static_cast<int>(key & ((1u << kIdxBits) - 1u));
-    float4 bx = ws.box[c0 + slot];
-    if (out.scale) {
-      bx.x = fminf(fmaxf(__fdiv_rn(__fsub_rn(bx.x, padx), gain), 0.f), sw);
-      bx.y = fminf(fmaxf(__fdiv_rn(__fsub_rn(bx.y, pady), gain), 0.f), sh);
-      bx.z = fminf(fmaxf(__fdiv_rn(__fsub_rn(bx.z, padx), gain), 0.f), sw);
-      bx.w = fminf(fmaxf(__fdiv_rn(__fsub_rn(bx.w, pady), gain), 0.f), sh);
-    }
-    reinterpret_cast<float4*>(out.xyxy)[o0 + o] = bx;
-    out.conf[o0 + o] = ws.score[c0 + slot];
-    const int meta = ws.meta[c0 + slot];
-    out.cls[o0 + o] = meta >> 16;
-    if (out.anchor) out.anchor[o0 + o] = meta & 0xffff;
-  }
-  if (out.keep) {
-    // torchvision's index = rank of the survivor's anchor among all candidates
-    for (int o = warp; o < kept; o += kWarps) {
-      const uint32_t my = static_cast<uint32_t>((keys[s_keep[o]] & 0xffffffffull) >> kIdxBits);
-      int cnt = 0;
-      for (int i = lane; i < n; i += 32) cnt += (static_cast<uint32_t>(ws.meta[c0 + i]) & 0xffffu) < my;
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(rtm::kFull, cnt, d);
-      if (lane == 0) out.keep[o0 + o] = cnt;
-    }
-  }
-  if (tid == 0) out.count[b] = kept;
+  __shared__ int s_keep[rtm::kMaxDetCap];
+  __shared__ int s_scan[33];
+  rtm::nms_stream<kNmsThreads>(ws, prm, iou_gate, out, blockIdx.x, smem_raw, s_keep, s_scan);
 }
 
-constexpr size_t kNmsSmemBytes =
-    (sizeof(uint64_t) + sizeof(float4) + sizeof(float)) * kNmsSmemCand + 2 * sizeof(uint32_t) * (kNmsSmemCand / 32);
-
-// smallest float32 g with (double)g > thr, so that `ovr >= g` == `(double)ovr > thr`
+// smallest float32 g with (double)g > thr, so that `iou >= g` == `(double)iou > thr`
 // (torchvision compares the float32 IoU with the double threshold)
 float iou_gate_for(double thr) {
   const float f = static_cast<float>(thr);
   return static_cast<double>(f) > thr ? f : nextafterf(f, INFINITY);
+}
+
+float logit_gate_for(float conf_thres) {
+  // gate on the raw logit: anything whose sigmoid could exceed conf_thres passes (the exact
+  // float32 test is repeated on the sigmoid itself)
+  if (conf_thres <= 0.f) return -FLT_MAX;
+  if (conf_thres >= 1.f) return FLT_MAX;
+  const double lg = log(static_cast<double>(conf_thres) / (1.0 - static_cast<double>(conf_thres)));
+  return static_cast<float>(lg - 1e-3 * (1.0 + fabs(lg)));
 }
 
 int make_geom(int img_h, int img_w, int nc, HeadGeom* g) {
@@ -714,7 +560,9 @@ int make_geom(int img_h, int img_w, int nc, HeadGeom* g) {
   }
   g->num_anchors = a0;
   g->num_classes = nc;
-  RTM_REQUIRE(a0 < kMaxAnchors, "%d anchors exceed the supported %d", a0, kMaxAnchors - 1);
+  RTM_REQUIRE(a0 < rtm::kMaxAnchors, "%d anchors exceed the supported %d", a0, rtm::kMaxAnchors - 1);
+  for (int l = 0; l < 3; ++l)
+    RTM_REQUIRE(g->lv[l].hw % kVec == 0, "level %d has %d anchors, not a multiple of %d", l, g->lv[l].hw, kVec);
   return RTM_OK;
 }
 
@@ -722,12 +570,12 @@ int run_nms(const Workspace& ws, int B, const rtm_nms_params& prm, const NmsOut&
   static bool configured = false;
   if (!configured) {
     RTM_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(kNmsSmemBytes)));
+                                  static_cast<int>(rtm::kNmsSmemBytes)));
     configured = true;
   }
   {
     rtm::ProfileScope prof(RTM_K_NMS, stream);
-    nms_kernel<<<B, kNmsThreads, kNmsSmemBytes, stream>>>(ws, prm, iou_gate_for(prm.iou_thres), out);
+    nms_kernel<<<B, kNmsThreads, rtm::kNmsSmemBytes, stream>>>(ws, prm, iou_gate_for(prm.iou_thres), out);
   }
   RTM_LAUNCH_CHECK("nms_kernel");
   return RTM_OK;
@@ -738,19 +586,11 @@ int check_common(const rtm_nms_params* p, int B, float* det_xyxy, float* det_con
   RTM_REQUIRE(p, "null rtm_nms_params");
   RTM_REQUIRE(B > 0, "num_streams must be positive");
   RTM_REQUIRE(det_xyxy && det_conf && det_cls && det_count && workspace, "null output / workspace pointer");
-  RTM_REQUIRE(p->max_det > 0 && p->max_det <= 1024, "max_det %d out of range (1..1024)", p->max_det);
+  RTM_REQUIRE(p->max_det > 0 && p->max_det <= rtm::kMaxDetCap, "max_det %d out of range (1..%d)", p->max_det,
+              rtm::kMaxDetCap);
   RTM_REQUIRE(det_stride >= p->max_det, "det_stride %d < max_det %d", det_stride, p->max_det);
   RTM_REQUIRE((reinterpret_cast<uintptr_t>(det_xyxy) & 15) == 0, "det_xyxy must be 16-byte aligned");
   return RTM_OK;
-}
-
-float logit_gate_for(float conf_thres) {
-  // gate on the raw logit: anything whose sigmoid could exceed conf_thres passes (the exact
-  // float32 test is repeated on the sigmoid itself)
-  if (conf_thres <= 0.f) return -FLT_MAX;
-  if (conf_thres >= 1.f) return FLT_MAX;
-  const double lg = log(static_cast<double>(conf_thres) / (1.0 - static_cast<double>(conf_thres)));
-  return static_cast<float>(lg - 1e-3 * (1.0 + fabs(lg)));
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -769,6 +609,11 @@ EncodeTiledFn tensor_map_encoder() {
       fn = reinterpret_cast<EncodeTiledFn>(p);
   }
   return fn;
+}
+
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e && *e ? atoi(e) : dflt;
 }
 
 // which head scan to use: RTM_DECODE_IMPL=tma (default when the shape allows) | ldg
@@ -793,7 +638,7 @@ CUtensorMapDataType tensor_map_dtype<__nv_bfloat16>() { return CU_TENSOR_MAP_DAT
 // returns 1 when the TMA path was launched, 0 when the caller should fall back, < 0 on error
 template <typename T>
 int try_launch_decode_tma(const void* p3, const void* p4, const void* p5, const HeadGeom& g, int B,
-                          const rtm_nms_params& prm, const Workspace& ws, int32_t* status, cudaStream_t stream) {
+                          const rtm_nms_params& prm, const Workspace& ws, cudaStream_t stream) {
   if (!want_tma()) return 0;
   EncodeTiledFn encode = tensor_map_encoder();
   if (!encode) return 0;
@@ -821,9 +666,12 @@ int try_launch_decode_tma(const void* p3, const void* p4, const void* p5, const 
   tg.total_tiles = tg.tiles_before[3] * B;
   tg.tile_bytes = ch * kTileW * static_cast<int>(sizeof(T));
   if (tg.tile_bytes % 128 != 0) return 0;
-  // 16-bit heads: 4 stages x 22.5 KB, two CTAs per SM; f32 heads: 3 stages x 45 KB, one CTA per SM
-  tg.stages = sizeof(T) == 2 ? 4 : 3;
-  const int ctas_per_sm = sizeof(T) == 2 ? 2 : 1;
+  // ring depth and residency: 16-bit heads 4 x 22.5 KB and two CTAs per SM, f32 heads 4 x 45 KB and one
+  static const int stages_env = env_int("RTM_TMA_STAGES", 0), ctas_env = env_int("RTM_TMA_CTAS", 0);
+  const int ctas_per_sm = ctas_env > 0 ? ctas_env : (sizeof(T) == 2 ? 2 : 1);
+  tg.stages = stages_env > 0 ? stages_env : 4;
+  if (tg.stages > kMaxStages) tg.stages = kMaxStages;
+  while (tg.stages > 1 && static_cast<size_t>(tg.stages) * tg.tile_bytes * ctas_per_sm > 216 * 1024) --tg.stages;
   const size_t smem = static_cast<size_t>(tg.stages) * tg.tile_bytes;
   static size_t configured = 0;
   if (smem > configured) {
@@ -834,31 +682,28 @@ int try_launch_decode_tma(const void* p3, const void* p4, const void* p5, const 
   {
     rtm::ProfileScope prof(RTM_K_DECODE, stream);
     decode_tma_kernel<T><<<grid, kTmaThreads, smem, stream>>>(maps[0], maps[1], maps[2], tg, prm,
-                                                             logit_gate_for(prm.conf_thres), ws, status);
+                                                             logit_gate_for(prm.conf_thres), ws);
   }
   RTM_LAUNCH_CHECK("decode_tma_kernel");
   return 1;
 }
 
-template <typename T, int VEC>
+template <typename T>
 int launch_decode(const void* p3, const void* p4, const void* p5, const HeadGeom& g, int B,
-                  const rtm_nms_params& prm, const Workspace& ws, int32_t* status, cudaStream_t stream) {
-  for (int l = 0; l < 3; ++l)
-    RTM_REQUIRE(g.lv[l].hw % VEC == 0, "level %d has %d anchors, not a multiple of %d", l, g.lv[l].hw, VEC);
+                  const rtm_nms_params& prm, const Workspace& ws, cudaStream_t stream) {
   HeadPtrs<T> heads{{static_cast<const T*>(p3), static_cast<const T*>(p4), static_cast<const T*>(p5)}};
   for (int l = 0; l < 3; ++l)
     RTM_REQUIRE((reinterpret_cast<uintptr_t>(heads.p[l]) & 15) == 0, "head level %d must be 16-byte aligned", l);
-  const int tma = try_launch_decode_tma<T>(p3, p4, p5, g, B, prm, ws, status, stream);
+  const int tma = try_launch_decode_tma<T>(p3, p4, p5, g, B, prm, ws, stream);
   if (tma != 0) return tma < 0 ? tma : RTM_OK;
-  const float gate = logit_gate_for(prm.conf_thres);
   constexpr int THREADS = 128;
-  const int groups = g.num_anchors / VEC;
+  const int groups = g.num_anchors / kVec;
   dim3 grid((groups + THREADS - 1) / THREADS, B);
   {
     rtm::ProfileScope prof(RTM_K_DECODE, stream);
-    decode_candidates_kernel<T, VEC, THREADS><<<grid, THREADS, 0, stream>>>(heads, g, prm, gate, ws, status);
+    decode_ldg_kernel<T, THREADS><<<grid, THREADS, 0, stream>>>(heads, g, prm, logit_gate_for(prm.conf_thres), ws);
   }
-  RTM_LAUNCH_CHECK("decode_candidates_kernel");
+  RTM_LAUNCH_CHECK("decode_ldg_kernel");
   return RTM_OK;
 }
 
@@ -886,16 +731,15 @@ extern "C" int rtm_decode_nms(const void* head_p3, const void* head_p4, const vo
   RTM_REQUIRE(workspace_bytes >= need, "rtm_decode_nms: workspace has %zu bytes, %zu needed", workspace_bytes, need);
   RTM_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  RTM_CUDA(cudaMemsetAsync(ws.count, 0, sizeof(int32_t) * num_streams, s));
   switch (head_dtype) {
     case RTM_F32:
-      rc = launch_decode<float, 4>(head_p3, head_p4, head_p5, g, num_streams, *params, ws, status, s);
+      rc = launch_decode<float>(head_p3, head_p4, head_p5, g, num_streams, *params, ws, s);
       break;
     case RTM_F16:
-      rc = launch_decode<__half, 8>(head_p3, head_p4, head_p5, g, num_streams, *params, ws, status, s);
+      rc = launch_decode<__half>(head_p3, head_p4, head_p5, g, num_streams, *params, ws, s);
       break;
     case RTM_BF16:
-      rc = launch_decode<__nv_bfloat16, 8>(head_p3, head_p4, head_p5, g, num_streams, *params, ws, status, s);
+      rc = launch_decode<__nv_bfloat16>(head_p3, head_p4, head_p5, g, num_streams, *params, ws, s);
       break;
     default:
       RTM_REQUIRE(false, "rtm_decode_nms: unknown head_dtype %d", head_dtype);
@@ -913,18 +757,17 @@ extern "C" int rtm_nms_pred(const float* pred, int32_t num_streams, int32_t num_
   int rc = check_common(params, num_streams, det_xyxy, det_conf, det_cls, det_count, det_stride, workspace);
   if (rc) return rc;
   RTM_REQUIRE(pred, "rtm_nms_pred: null prediction tensor");
-  RTM_REQUIRE(num_anchors > 0 && num_anchors < kMaxAnchors, "rtm_nms_pred: num_anchors %d out of range", num_anchors);
+  RTM_REQUIRE(num_anchors > 0 && num_anchors < rtm::kMaxAnchors, "rtm_nms_pred: num_anchors %d out of range", num_anchors);
   RTM_REQUIRE(params->num_classes > 0 && params->num_classes <= 256, "num_classes out of range");
   Workspace ws;
   const size_t need = workspace_layout(num_streams, num_anchors, static_cast<char*>(workspace), &ws);
   RTM_REQUIRE(workspace_bytes >= need, "rtm_nms_pred: workspace has %zu bytes, %zu needed", workspace_bytes, need);
   RTM_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  RTM_CUDA(cudaMemsetAsync(ws.count, 0, sizeof(int32_t) * num_streams, s));
   dim3 grid((num_anchors + 255) / 256, num_streams);
   {
     rtm::ProfileScope prof(RTM_K_PRED, s);
-    pred_candidates_kernel<<<grid, 256, 0, s>>>(pred, num_anchors, params->num_classes, *params, ws, status);
+    pred_candidates_kernel<<<grid, 256, 0, s>>>(pred, num_anchors, params->num_classes, *params, ws);
   }
   RTM_LAUNCH_CHECK("pred_candidates_kernel");
   NmsOut out{scale, det_xyxy, det_conf, det_cls, det_anchor, det_keep, det_count, det_stride, status};

@@ -88,10 +88,43 @@ __device__ __forceinline__ int block_exclusive_count(bool flag, int* scratch, in
   return base + within;
 }
 
+// Exclusive prefix sum of `v` over the threads of the block (thread order) plus the block
+// total.  `scratch` holds 33 ints.  All threads must call it; three __syncthreads().
+__device__ __forceinline__ int block_exclusive_sum(int v, int* scratch, int* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+  int incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int o = __shfl_up_sync(kFull, incl, d);
+    if (lane >= d) incl += o;
+  }
+  if (lane == 31) scratch[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    const int w = lane < nwarp ? scratch[lane] : 0;
+    int inc2 = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(kFull, inc2, d);
+      if (lane >= d) inc2 += o;
+    }
+    if (lane < nwarp) scratch[lane] = inc2 - w;
+    if (lane == 31) scratch[32] = inc2;
+  }
+  __syncthreads();
+  const int base = scratch[warp];
+  *total = scratch[32];
+  __syncthreads();
+  return base + incl - v;
+}
+
 // total order on floats as unsigned ints (ascending)
 __device__ __forceinline__ uint32_t float_orderable(float f) {
   uint32_t u = __float_as_uint(f);
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float float_from_orderable(uint32_t u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
 }  // namespace rtm
