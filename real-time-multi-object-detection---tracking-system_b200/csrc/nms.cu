@@ -16,12 +16,12 @@
 //   decode_tma   the production head scan.  Persistent CTAs; a producer warp pulls whole tiles
 //                (all 64 + nc channels x 80 consecutive anchors of one stream and level) into a
 //                ring of shared-memory stages with one TMA tensor copy each (full / empty
-//                mbarriers), so every head byte crosses HBM exactly once.  Ten consumer warps
-//                work independently of each other (no block barrier): a warp owns 8 anchors of
-//                the tile, its lanes are (anchor, class-quarter) pairs that scan the class rows
-//                bank-conflict free; the four lanes of an anchor combine by shuffle, and anchors
-//                that pass the confidence test get their four DFL sides decoded by their four
-//                lanes straight from shared memory.
+//                mbarriers), so every head byte crosses HBM exactly once.  Five consumer warps
+//                work independently of each other (no block barrier): a warp owns 16 anchors of
+//                the tile, a lane owns two adjacent anchors x one class quarter and keeps a packed
+//                (bf16x2 / f16x2) running maximum over its class rows, bank-conflict free; the
+//                four lanes of an anchor combine by shuffle, and anchors that pass the confidence
+//                test get their four DFL sides decoded by their four lanes from shared memory.
 //   decode_ldg   fallback for shapes the tiling does not cover: 16-byte global loads of the
 //                class planes, warp-co-operative decode of the few passing anchors.
 //   candidates   are written dense by anchor plus a bitmask (see nms_body.cuh): no atomics, no
@@ -130,21 +130,22 @@ __device__ __forceinline__ float4 dist_to_xyxy(float l, float t, float r, float 
   return make_float4(__fsub_rn(cx, dw), __fsub_rn(cy, dh), __fadd_rn(cx, dw), __fadd_rn(cy, dh));
 }
 
-// DFL expectation of one side from 16 logits (sequential order, shared by all decode kernels)
+// DFL expectation of one side from 16 logits: sum_k k * softmax(x)_k.  Shared by all decode
+// kernels so that they agree bit for bit; checked against the oracle within 1e-4 relative
+// (D1 is the tolerance-checked stage: torch's CPU softmax rounds differently anyway), hence
+// the fast exponential and a single division.
 __device__ __forceinline__ float dfl_expectation(float (&x)[kRegMax]) {
-  float mx = -FLT_MAX;
+  float mx = x[0];
 #pragma unroll
-  for (int k = 0; k < kRegMax; ++k) mx = fmaxf(mx, x[k]);
-  float sum = 0.f;
+  for (int k = 1; k < kRegMax; ++k) mx = fmaxf(mx, x[k]);
+  float sum = 0.f, acc = 0.f;
 #pragma unroll
   for (int k = 0; k < kRegMax; ++k) {
-    x[k] = expf(__fsub_rn(x[k], mx));
-    sum = __fadd_rn(sum, x[k]);
+    const float e = __expf(x[k] - mx);
+    sum += e;
+    acc = __fmaf_rn(static_cast<float>(k), e, acc);
   }
-  float acc = 0.f;
-#pragma unroll
-  for (int k = 0; k < kRegMax; ++k) acc = __fadd_rn(acc, __fmul_rn(static_cast<float>(k), __fdiv_rn(x[k], sum)));
-  return acc;
+  return __fdiv_rn(acc, sum);
 }
 
 __device__ __forceinline__ void store_candidate(const Workspace& ws, int b, int anchor, float4 box, float score, int cls) {
@@ -163,8 +164,9 @@ struct HeadPtrs {
 // decode_tma
 // ---------------------------------------------------------------------------------------
 constexpr int kTileW = 80;  // divides 6400 / 1600 / 400 (and every level of a W = 640, H % 128 == 0 input)
-constexpr int kConsumerWarps = kTileW / 8;              // 10: a warp owns 8 anchors of the tile
-constexpr int kTmaThreads = (kConsumerWarps + 1) * 32;  // + one producer warp
+constexpr int kAnchorsPerWarp = 16;                      // a lane owns 2 adjacent anchors x one class quarter
+constexpr int kConsumerWarps = kTileW / kAnchorsPerWarp;  // 5
+constexpr int kTmaThreads = (kConsumerWarps + 1) * 32;    // + one producer warp
 constexpr int kMaxStages = 8;
 
 struct TmaGeom {
@@ -212,7 +214,73 @@ __device__ __forceinline__ void tma_load_tile(void* dst, const CUtensorMap* map,
       : "memory");
 }
 
+// two horizontally adjacent anchors of one channel row: one 4-byte (16-bit heads) or 8-byte load,
+// running maximum kept packed (HMNMX2 on bf16x2 / f16x2)
 template <typename T>
+struct Pair;
+template <>
+struct Pair<__nv_bfloat16> {
+  using V = __nv_bfloat162;
+  static __device__ __forceinline__ V lowest() { return __float2bfloat162_rn(-INFINITY); }
+  static __device__ __forceinline__ V load(const __nv_bfloat16* p) { return *reinterpret_cast<const V*>(p); }
+  static __device__ __forceinline__ V vmax(V a, V b) { return __hmax2(a, b); }
+  static __device__ __forceinline__ float lo(V v) { return __low2float(v); }
+  static __device__ __forceinline__ float hi(V v) { return __high2float(v); }
+};
+template <>
+struct Pair<__half> {
+  using V = __half2;
+  static __device__ __forceinline__ V lowest() { return __float2half2_rn(-INFINITY); }
+  static __device__ __forceinline__ V load(const __half* p) { return *reinterpret_cast<const V*>(p); }
+  static __device__ __forceinline__ V vmax(V a, V b) { return __hmax2(a, b); }
+  static __device__ __forceinline__ float lo(V v) { return __low2float(v); }
+  static __device__ __forceinline__ float hi(V v) { return __high2float(v); }
+};
+template <>
+struct Pair<float> {
+  using V = float2;
+  static __device__ __forceinline__ V lowest() { return make_float2(-INFINITY, -INFINITY); }
+  static __device__ __forceinline__ V load(const float* p) { return *reinterpret_cast<const V*>(p); }
+  static __device__ __forceinline__ V vmax(V a, V b) { return make_float2(fmaxf(a.x, b.x), fmaxf(a.y, b.y)); }
+  static __device__ __forceinline__ float lo(V v) { return v.x; }
+  static __device__ __forceinline__ float hi(V v) { return v.y; }
+};
+
+// exact N1 of one anchor column for the lanes of its four class quarters: probability and index
+// of the FIRST class attaining the maximum float32 sigmoid; lanes whose quarter cannot pass
+// contribute (-1, INT_MAX).  `m` is the lane's maximum logit over its classes q, q+4, ...
+template <typename T>
+__device__ __forceinline__ void anchor_best(const T* cls_col, const int q, const int iters, const int nc, const float m,
+                                            const float logit_gate, float* best, int* bc) {
+  float sc = -1.f;
+  int j = 0x7fffffff;
+  if (m > logit_gate) {
+    sc = sigmoidf_rn(m);
+    for (int i = 0; i < iters; ++i) {
+      const int c = 4 * i + q;
+      if (c < nc) {
+        const float v = to_float(cls_col[c * kTileW]);
+        if (v > logit_gate && sigmoidf_rn(v) == sc) {
+          j = c;
+          break;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int d = 8; d <= 16; d <<= 1) {
+    const float ob = __shfl_xor_sync(kFull, sc, d);
+    const int oc = __shfl_xor_sync(kFull, j, d);
+    if (ob > sc || (ob == sc && oc < j)) {
+      sc = ob;
+      j = oc;
+    }
+  }
+  *best = sc;
+  *bc = j;
+}
+
+template <typename T, bool NC80>
 __global__ void __launch_bounds__(kTmaThreads) decode_tma_kernel(const __grid_constant__ CUtensorMap map0,
                                                                  const __grid_constant__ CUtensorMap map1,
                                                                  const __grid_constant__ CUtensorMap map2,
@@ -221,10 +289,11 @@ __global__ void __launch_bounds__(kTmaThreads) decode_tma_kernel(const __grid_co
   extern __shared__ __align__(128) unsigned char tile_smem[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  using P = Pair<T>;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int stages = tg.stages;
-  const int tps = tg.tiles_before[3];
+  const int tps = tg.tiles_before[3], tb1 = tg.tiles_before[1], tb2 = tg.tiles_before[2];
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -236,109 +305,132 @@ __global__ void __launch_bounds__(kTmaThreads) decode_tma_kernel(const __grid_co
 
   const int first = blockIdx.x, step = gridDim.x;
   const int my_tiles = first < tg.total_tiles ? (tg.total_tiles - first + step - 1) / step : 0;
+  // tile t = (stream b, tile r of the stream); advanced incrementally, no division per tile
+  const int step_b = step / tps, step_r = step - step_b * tps;
+  int b = first / tps, r = first - b * tps;
 
   if (warp == kConsumerWarps) {
     // ===== producer warp: one elected lane keeps the ring full =====
     if (lane == 0) {
+      int s = 0, fill = 0;
       for (int it = 0; it < my_tiles; ++it) {
-        const int s = it % stages, fill = it / stages;
         if (fill > 0) mbar_wait(&empty_bar[s], (fill - 1) & 1);
-        const int t = first + it * step;
-        const int b = t / tps, r = t - b * tps;
-        const int li = r >= tg.tiles_before[2] ? 2 : (r >= tg.tiles_before[1] ? 1 : 0);
-        const int x = (r - tg.tiles_before[li]) * kTileW;
+        const int li = r >= tb2 ? 2 : (r >= tb1 ? 1 : 0);
+        const int x = (r - (li == 2 ? tb2 : (li == 1 ? tb1 : 0))) * kTileW;
         mbar_expect_tx(&full_bar[s], tg.tile_bytes);
         tma_load_tile(tile_smem + static_cast<size_t>(s) * tg.tile_bytes, li == 0 ? &map0 : (li == 1 ? &map1 : &map2),
                       &full_bar[s], x, b);
+        if (++s == stages) {
+          s = 0;
+          ++fill;
+        }
+        b += step_b;
+        r += step_r;
+        if (r >= tps) {
+          r -= tps;
+          ++b;
+        }
       }
     }
     return;
   }
 
   // ===== consumer warps =====
-  const int al = lane & 7, q = lane >> 3;  // anchor within the warp's 8, class quarter / DFL side
-  const int col = warp * 8 + al;           // anchor column inside the tile
-  const int nc = tg.g.num_classes;
-  const int iters = (nc + 3) >> 2;         // quarter q scans classes q, q + 4, q + 8, ... (bank-conflict free)
+  const int pr = lane & 7, q = lane >> 3;          // anchor pair within the warp's 16, class quarter / DFL side
+  const int col = warp * kAnchorsPerWarp + 2 * pr;  // first of the lane's two anchor columns in the tile
+  const int nc = NC80 ? 80 : tg.g.num_classes;
+  const int iters = (nc + 3) >> 2;  // quarter q scans classes q, q + 4, q + 8, ... (bank-conflict free)
+  const int w0 = tg.g.lv[0].w, w1 = tg.g.lv[1].w, w2 = tg.g.lv[2].w;
+  const int a1 = tg.g.lv[1].anchor0, a2 = tg.g.lv[2].anchor0;
+  const int st0 = tg.g.lv[0].stride, st1 = tg.g.lv[1].stride, st2 = tg.g.lv[2].stride;
+  uint8_t* mask_bytes = reinterpret_cast<uint8_t*>(ws.mask);
 
+  int s = 0, phase = 0;
   for (int it = 0; it < my_tiles; ++it) {
-    const int t = first + it * step;
-    const int b = t / tps, r = t - b * tps;
-    const int li = r >= tg.tiles_before[2] ? 2 : (r >= tg.tiles_before[1] ? 1 : 0);
-    const int lv_w = tg.g.lv[li].w, lv_stride = tg.g.lv[li].stride, lv_anchor0 = tg.g.lv[li].anchor0;
-    const int pix = (r - tg.tiles_before[li]) * kTileW + col;
-    const int s = it % stages;
-    mbar_wait(&full_bar[s], (it / stages) & 1);
+    const int li = r >= tb2 ? 2 : (r >= tb1 ? 1 : 0);
+    const int lv_w = li == 2 ? w2 : (li == 1 ? w1 : w0);
+    const int lv_stride = li == 2 ? st2 : (li == 1 ? st1 : st0);
+    const int lv_anchor0 = li == 2 ? a2 : (li == 1 ? a1 : 0);
+    const int pix = (r - (li == 2 ? tb2 : (li == 1 ? tb1 : 0))) * kTileW + col;
+    mbar_wait(&full_bar[s], phase);
     const T* tile = reinterpret_cast<const T*>(tile_smem + static_cast<size_t>(s) * tg.tile_bytes);
-    const T* cls_col = tile + kBoxCh * kTileW + col;
+    const T* cls_col = tile + (kBoxCh + q) * kTileW + col;  // row of class q
 
-    // ---- N1 gate: max class logit of the anchor (quarter maxima combined by shuffle) ----
-    float m = -FLT_MAX;
-#pragma unroll 5
-    for (int i = 0; i < iters; ++i) {
-      const int c = 4 * i + q;
-      if (c < nc) m = fmaxf(m, to_float(cls_col[c * kTileW]));
+    // ---- N1 gate: packed running maximum over this quarter's classes for both anchors ----
+    typename P::V mv = P::lowest();
+    if (NC80) {
+#pragma unroll
+      for (int i = 0; i < 20; ++i) mv = P::vmax(mv, P::load(cls_col + 4 * i * kTileW));
+    } else {
+      for (int i = 0; i < iters; ++i)
+        if (4 * i + q < nc) mv = P::vmax(mv, P::load(cls_col + 4 * i * kTileW));
     }
-    float am = fmaxf(m, __shfl_xor_sync(kFull, m, 8));
+    const float m0 = P::lo(mv), m1 = P::hi(mv);
+    float am = fmaxf(m0, m1);
+    am = fmaxf(am, __shfl_xor_sync(kFull, am, 8));
     am = fmaxf(am, __shfl_xor_sync(kFull, am, 16));
 
-    bool cand = false;
-    float best = -1.f;
-    int bc = 0;
+    bool cand0 = false, cand1 = false;
     if (__any_sync(kFull, am > logit_gate)) {
-      // ---- exact N1 for the anchors that can pass: first arg-max of the float32 sigmoid ----
-      float sc = -1.f;
-      int j = 0x7fffffff;
-      if (m > logit_gate) {
-        sc = sigmoidf_rn(m);
-        for (int i = 0; i < iters; ++i) {  // first class of this quarter whose probability equals the maximum
-          const int c = 4 * i + q;
-          if (c < nc) {
-            const float v = to_float(cls_col[c * kTileW]);
-            if (v > logit_gate && sigmoidf_rn(v) == sc) {
-              j = c;
-              break;
-            }
-          }
-        }
-      }
-      best = sc;
-      bc = j;
-#pragma unroll
-      for (int d = 8; d <= 16; d <<= 1) {
-        const float ob = __shfl_xor_sync(kFull, best, d);
-        const int oc = __shfl_xor_sync(kFull, bc, d);
-        if (ob > best || (ob == best && oc < bc)) {
-          best = ob;
-          bc = oc;
-        }
-      }
-      cand = best > prm.conf_thres && class_wanted(prm, bc & 255);
-      if (__any_sync(kFull, cand)) {
-        // ---- D1 for the survivors: lane q decodes side q; the q = 0 lane assembles the box ----
-        float dist = 0.f;
-        if (cand) {
+      // ---- exact N1 for the anchors that can pass, then D1 for the survivors ----
+      float best0, best1;
+      int bc0, bc1;
+      anchor_best<T>(tile + kBoxCh * kTileW + col, q, iters, nc, m0, logit_gate, &best0, &bc0);
+      anchor_best<T>(tile + kBoxCh * kTileW + col + 1, q, iters, nc, m1, logit_gate, &best1, &bc1);
+      cand0 = best0 > prm.conf_thres && class_wanted(prm, bc0 & 255);
+      cand1 = best1 > prm.conf_thres && class_wanted(prm, bc1 & 255);
+      if (__any_sync(kFull, cand0 || cand1)) {
+        float d0 = 0.f, d1 = 0.f;  // side q of the lane's two anchors
+        if (cand0) {
           float x[kRegMax];
 #pragma unroll
           for (int k = 0; k < kRegMax; ++k) x[k] = to_float(tile[(q * kRegMax + k) * kTileW + col]);
-          dist = dfl_expectation(x);
+          d0 = dfl_expectation(x);
         }
-        const float dt = __shfl_down_sync(kFull, dist, 8);
-        const float dr = __shfl_down_sync(kFull, dist, 16);
-        const float db = __shfl_down_sync(kFull, dist, 24);
-        if (cand && q == 0) {
-          const float ax = static_cast<float>(pix % lv_w) + 0.5f, ay = static_cast<float>(pix / lv_w) + 0.5f;
-          store_candidate(ws, b, lv_anchor0 + pix,
-                          dist_to_xyxy(dist, dt, dr, db, ax, ay, static_cast<float>(lv_stride), nullptr), best, bc);
+        if (cand1) {
+          float x[kRegMax];
+#pragma unroll
+          for (int k = 0; k < kRegMax; ++k) x[k] = to_float(tile[(q * kRegMax + k) * kTileW + col + 1]);
+          d1 = dfl_expectation(x);
+        }
+        const float t0 = __shfl_down_sync(kFull, d0, 8), r0 = __shfl_down_sync(kFull, d0, 16), b0 = __shfl_down_sync(kFull, d0, 24);
+        const float t1 = __shfl_down_sync(kFull, d1, 8), r1 = __shfl_down_sync(kFull, d1, 16), b1 = __shfl_down_sync(kFull, d1, 24);
+        if (q == 0) {
+          const int y = pix / lv_w, x = pix - y * lv_w;  // both anchors are in the same grid row (w is even)
+          const float ay = static_cast<float>(y) + 0.5f, fs = static_cast<float>(lv_stride);
+          if (cand0)
+            store_candidate(ws, b, lv_anchor0 + pix, dist_to_xyxy(d0, t0, r0, b0, static_cast<float>(x) + 0.5f, ay, fs, nullptr),
+                            best0, bc0);
+          if (cand1)
+            store_candidate(ws, b, lv_anchor0 + pix + 1,
+                            dist_to_xyxy(d1, t1, r1, b1, static_cast<float>(x + 1) + 0.5f, ay, fs, nullptr), best1, bc1);
         }
       }
     }
-    // candidate bits of this warp's 8 anchors: one byte of the stream's mask
-    const uint32_t bits = __ballot_sync(kFull, cand && q == 0) & 0xffu;
-    if (lane == 0)
-      reinterpret_cast<uint8_t*>(ws.mask + static_cast<size_t>(b) * ws.words)[(lv_anchor0 + pix) >> 3] = static_cast<uint8_t>(bits);
+    // candidate bits of this warp's 16 anchors: two bytes of the stream's mask
+    uint32_t even = __ballot_sync(kFull, cand0 && q == 0) & 0xffu, odd = __ballot_sync(kFull, cand1 && q == 0) & 0xffu;
+    if (lane == 0) {
+      even = (even | (even << 4)) & 0x0f0fu;
+      even = (even | (even << 2)) & 0x3333u;
+      even = (even | (even << 1)) & 0x5555u;
+      odd = (odd | (odd << 4)) & 0x0f0fu;
+      odd = (odd | (odd << 2)) & 0x3333u;
+      odd = (odd | (odd << 1)) & 0x5555u;
+      *reinterpret_cast<uint16_t*>(mask_bytes + static_cast<size_t>(b) * ws.words * 4 + ((lv_anchor0 + pix) >> 3)) =
+          static_cast<uint16_t>(even | (odd << 1));
+    }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[s]);  // this warp is done with the stage
+    if (++s == stages) {
+      s = 0;
+      phase ^= 1;
+    }
+    b += step_b;
+    r += step_r;
+    if (r >= tps) {
+      r -= tps;
+      ++b;
+    }
   }
 }
 
@@ -643,7 +735,7 @@ int try_launch_decode_tma(const void* p3, const void* p4, const void* p5, const 
   EncodeTiledFn encode = tensor_map_encoder();
   if (!encode) return 0;
   for (int l = 0; l < 3; ++l)
-    if (g.lv[l].hw % kTileW != 0) return 0;
+    if (g.lv[l].hw % kTileW != 0 || g.lv[l].w % 2 != 0) return 0;
   const int ch = kBoxCh + g.num_classes;
   const void* ptrs[3] = {p3, p4, p5};
   CUtensorMap maps[3];
@@ -666,23 +758,29 @@ int try_launch_decode_tma(const void* p3, const void* p4, const void* p5, const 
   tg.total_tiles = tg.tiles_before[3] * B;
   tg.tile_bytes = ch * kTileW * static_cast<int>(sizeof(T));
   if (tg.tile_bytes % 128 != 0) return 0;
-  // ring depth and residency: 16-bit heads 4 x 22.5 KB and two CTAs per SM, f32 heads 4 x 45 KB and one
+  // ring depth and residency (measured best): 16-bit heads 3 x 22.5 KB and three CTAs per SM,
+  // f32 heads 4 x 45 KB and one CTA per SM
   static const int stages_env = env_int("RTM_TMA_STAGES", 0), ctas_env = env_int("RTM_TMA_CTAS", 0);
-  const int ctas_per_sm = ctas_env > 0 ? ctas_env : (sizeof(T) == 2 ? 2 : 1);
-  tg.stages = stages_env > 0 ? stages_env : 4;
+  const int ctas_per_sm = ctas_env > 0 ? ctas_env : (sizeof(T) == 2 ? 3 : 1);
+  tg.stages = stages_env > 0 ? stages_env : (sizeof(T) == 2 ? 3 : 4);
   if (tg.stages > kMaxStages) tg.stages = kMaxStages;
   while (tg.stages > 1 && static_cast<size_t>(tg.stages) * tg.tile_bytes * ctas_per_sm > 216 * 1024) --tg.stages;
   const size_t smem = static_cast<size_t>(tg.stages) * tg.tile_bytes;
   static size_t configured = 0;
   if (smem > configured) {
-    RTM_CUDA(cudaFuncSetAttribute(decode_tma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    RTM_CUDA(cudaFuncSetAttribute(decode_tma_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    RTM_CUDA(cudaFuncSetAttribute(decode_tma_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     configured = smem;
   }
   const int grid = min(tg.total_tiles, rtm::sm_count() * ctas_per_sm);
   {
     rtm::ProfileScope prof(RTM_K_DECODE, stream);
-    decode_tma_kernel<T><<<grid, kTmaThreads, smem, stream>>>(maps[0], maps[1], maps[2], tg, prm,
-                                                             logit_gate_for(prm.conf_thres), ws);
+    if (g.num_classes == 80)
+      decode_tma_kernel<T, true><<<grid, kTmaThreads, smem, stream>>>(maps[0], maps[1], maps[2], tg, prm,
+                                                                     logit_gate_for(prm.conf_thres), ws);
+    else
+      decode_tma_kernel<T, false><<<grid, kTmaThreads, smem, stream>>>(maps[0], maps[1], maps[2], tg, prm,
+                                                                      logit_gate_for(prm.conf_thres), ws);
   }
   RTM_LAUNCH_CHECK("decode_tma_kernel");
   return 1;
