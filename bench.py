@@ -371,7 +371,7 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args, total_streams),
-            "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": 4 * K, "roofline": roofline,
+            "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": sum(v["launches"] for v in kernels.values()), "roofline": roofline,
             "cpu_baseline": cpu, "kernels": kernels, "parity": parity,
             "summary": dict(zip(sharding.COUNTERS, totals), live_tracks_rank0=int(sum(len(t) for t in tracks)),
                             streams_reporting=len(gathered)),

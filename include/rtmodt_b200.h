@@ -301,6 +301,7 @@ enum {
   RTM_K_TRACK = 3,
   RTM_K_ZONE = 4,
   RTM_K_PRED = 5,
+  RTM_K_POST = 6, /* fused NMS + tracker + zones of rtm_post_backbone_step */
   RTM_K_COUNT = 8
 };
 int rtm_profile_enable(int32_t on);

@@ -171,8 +171,8 @@ def raise_on_status(status_host, what: str = "") -> None:
     raise RtmError(f"{what}: {'; '.join(msgs)} (streams {streams})")
 
 
-K_LETTERBOX, K_DECODE, K_NMS, K_TRACK, K_ZONE, K_PRED, K_COUNT = 0, 1, 2, 3, 4, 5, 8
-KERNEL_NAMES = {K_LETTERBOX: "letterbox", K_DECODE: "decode", K_NMS: "nms", K_TRACK: "track", K_ZONE: "zone", K_PRED: "pred_filter"}
+K_LETTERBOX, K_DECODE, K_NMS, K_TRACK, K_ZONE, K_PRED, K_POST, K_COUNT = 0, 1, 2, 3, 4, 5, 6, 8
+KERNEL_NAMES = {K_LETTERBOX: "letterbox", K_DECODE: "decode", K_NMS: "nms", K_TRACK: "track", K_ZONE: "zone", K_PRED: "pred_filter", K_POST: "post"}
 
 
 def profile_read():

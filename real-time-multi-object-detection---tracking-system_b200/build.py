@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librtmodt_b200.so")
-SOURCES = ["api.cu", "letterbox.cu", "nms.cu", "track.cu", "zone.cu"]
+SOURCES = ["api.cu", "letterbox.cu", "nms.cu", "post.cu", "track.cu", "zone.cu"]
 
 
 def nvcc_path() -> str:

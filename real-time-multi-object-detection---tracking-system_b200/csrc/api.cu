@@ -107,26 +107,6 @@ extern "C" int rtm_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc
   return RTM_OK;
 }
 
-extern "C" int rtm_post_backbone_step(const rtm_step_io* io, const rtm_nms_params* params,
-                                      rtm_cuda_stream stream) {
-  RTM_REQUIRE(io && params, "rtm_post_backbone_step: null argument");
-  RTM_REQUIRE(io->table_in && io->table_out, "rtm_post_backbone_step: null track table");
-  const int B = io->table_in->num_streams;
-  int rc = rtm_decode_nms(io->head_p3, io->head_p4, io->head_p5, io->head_dtype, B, io->img_h, io->img_w,
-                          params, io->scale, io->det_xyxy, io->det_conf, io->det_cls, io->det_anchor,
-                          io->det_keep, io->det_count, io->det_stride, io->status, io->workspace,
-                          io->workspace_bytes, stream);
-  if (rc) return rc;
-  rc = rtm_track_step(io->table_in, io->table_out, io->det_xyxy, io->det_conf, io->det_cls, io->det_count,
-                      io->det_stride, io->track_thresh, io->match_thresh, io->track_buffer, io->det_track_id,
-                      io->det_kind, io->src_row, io->status, stream);
-  if (rc) return rc;
-  if (!io->zones) return RTM_OK;
-  return rtm_zone_step(io->zones, io->table_out, io->src_row, io->state_in, io->state_out, io->now,
-                       io->now_per_stream, io->frame_id, io->events, io->event_stride, io->event_count,
-                       io->status, stream);
-}
-
 namespace {
 
 size_t elem_size(int dtype) { return dtype == RTM_F32 ? 4 : 2; }

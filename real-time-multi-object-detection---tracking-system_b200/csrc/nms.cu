@@ -619,13 +619,6 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(const Workspace ws, co
   rtm::nms_stream<kNmsThreads>(ws, prm, iou_gate, out, blockIdx.x, smem_raw, s_keep, s_scan);
 }
 
-// smallest float32 g with (double)g > thr, so that `iou >= g` == `(double)iou > thr`
-// (torchvision compares the float32 IoU with the double threshold)
-float iou_gate_for(double thr) {
-  const float f = static_cast<float>(thr);
-  return static_cast<double>(f) > thr ? f : nextafterf(f, INFINITY);
-}
-
 float logit_gate_for(float conf_thres) {
   // gate on the raw logit: anything whose sigmoid could exceed conf_thres passes (the exact
   // float32 test is repeated on the sigmoid itself)
@@ -667,7 +660,7 @@ int run_nms(const Workspace& ws, int B, const rtm_nms_params& prm, const NmsOut&
   }
   {
     rtm::ProfileScope prof(RTM_K_NMS, stream);
-    nms_kernel<<<B, kNmsThreads, rtm::kNmsSmemBytes, stream>>>(ws, prm, iou_gate_for(prm.iou_thres), out);
+    nms_kernel<<<B, kNmsThreads, rtm::kNmsSmemBytes, stream>>>(ws, prm, rtm::iou_gate_for(prm.iou_thres), out);
   }
   RTM_LAUNCH_CHECK("nms_kernel");
   return RTM_OK;
@@ -812,6 +805,29 @@ extern "C" size_t rtm_nms_workspace_bytes(int32_t num_streams, int32_t num_ancho
   return workspace_layout(num_streams, num_anchors, nullptr, nullptr);
 }
 
+int rtm::launch_decode_stage(const void* head_p3, const void* head_p4, const void* head_p5, int head_dtype,
+                             int num_streams, int img_h, int img_w, const rtm_nms_params* params, void* workspace,
+                             size_t workspace_bytes, Workspace* ws, cudaStream_t s) {
+  RTM_REQUIRE(head_p3 && head_p4 && head_p5, "null head tensor");
+  HeadGeom g;
+  int rc = make_geom(img_h, img_w, params->num_classes, &g);
+  if (rc) return rc;
+  const size_t need = workspace_layout(num_streams, g.num_anchors, static_cast<char*>(workspace), ws);
+  RTM_REQUIRE(workspace_bytes >= need, "workspace has %zu bytes, %zu needed", workspace_bytes, need);
+  RTM_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
+  switch (head_dtype) {
+    case RTM_F32:
+      return launch_decode<float>(head_p3, head_p4, head_p5, g, num_streams, *params, *ws, s);
+    case RTM_F16:
+      return launch_decode<__half>(head_p3, head_p4, head_p5, g, num_streams, *params, *ws, s);
+    case RTM_BF16:
+      return launch_decode<__nv_bfloat16>(head_p3, head_p4, head_p5, g, num_streams, *params, *ws, s);
+    default:
+      RTM_REQUIRE(false, "unknown head_dtype %d", head_dtype);
+  }
+  return RTM_OK;
+}
+
 extern "C" int rtm_decode_nms(const void* head_p3, const void* head_p4, const void* head_p5,
                               int32_t head_dtype, int32_t num_streams, int32_t img_h, int32_t img_w,
                               const rtm_nms_params* params, const float* scale, float* det_xyxy,
@@ -820,28 +836,10 @@ extern "C" int rtm_decode_nms(const void* head_p3, const void* head_p4, const vo
                               size_t workspace_bytes, rtm_cuda_stream stream) {
   int rc = check_common(params, num_streams, det_xyxy, det_conf, det_cls, det_count, det_stride, workspace);
   if (rc) return rc;
-  RTM_REQUIRE(head_p3 && head_p4 && head_p5, "rtm_decode_nms: null head tensor");
-  HeadGeom g;
-  rc = make_geom(img_h, img_w, params->num_classes, &g);
-  if (rc) return rc;
-  Workspace ws;
-  const size_t need = workspace_layout(num_streams, g.num_anchors, static_cast<char*>(workspace), &ws);
-  RTM_REQUIRE(workspace_bytes >= need, "rtm_decode_nms: workspace has %zu bytes, %zu needed", workspace_bytes, need);
-  RTM_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  switch (head_dtype) {
-    case RTM_F32:
-      rc = launch_decode<float>(head_p3, head_p4, head_p5, g, num_streams, *params, ws, s);
-      break;
-    case RTM_F16:
-      rc = launch_decode<__half>(head_p3, head_p4, head_p5, g, num_streams, *params, ws, s);
-      break;
-    case RTM_BF16:
-      rc = launch_decode<__nv_bfloat16>(head_p3, head_p4, head_p5, g, num_streams, *params, ws, s);
-      break;
-    default:
-      RTM_REQUIRE(false, "rtm_decode_nms: unknown head_dtype %d", head_dtype);
-  }
+  Workspace ws;
+  rc = rtm::launch_decode_stage(head_p3, head_p4, head_p5, head_dtype, num_streams, img_h, img_w, params, workspace,
+                                workspace_bytes, &ws, s);
   if (rc) return rc;
   NmsOut out{scale, det_xyxy, det_conf, det_cls, det_anchor, det_keep, det_count, det_stride, status};
   return run_nms(ws, num_streams, *params, out, s);

@@ -12,6 +12,7 @@
 #pragma once
 
 #include <float.h>
+#include <math.h>
 
 #include "rtm_common.cuh"
 
@@ -49,6 +50,19 @@ struct NmsOut {
   int32_t stride;
   int32_t* status;
 };
+
+// smallest float32 g with (double)g > thr, so that `iou >= g` == `(double)iou > thr`
+// (torchvision compares the float32 IoU with the double threshold)
+inline float iou_gate_for(double thr) {
+  const float f = static_cast<float>(thr);
+  return static_cast<double>(f) > thr ? f : nextafterf(f, INFINITY);
+}
+
+// D1 + N1 only (defined in nms.cu): scans the head tensors and leaves the candidate list of every
+// stream in `workspace`; *ws describes it for the NMS stage.
+int launch_decode_stage(const void* head_p3, const void* head_p4, const void* head_p5, int head_dtype, int num_streams,
+                        int img_h, int img_w, const rtm_nms_params* params, void* workspace, size_t workspace_bytes,
+                        Workspace* ws, cudaStream_t stream);
 
 // bytes of dynamic shared memory nms_stream needs
 constexpr size_t kNmsSmemBytes = (sizeof(uint64_t) + 2 * sizeof(float4) + sizeof(float) + sizeof(int32_t)) * kNmsSmemCand +

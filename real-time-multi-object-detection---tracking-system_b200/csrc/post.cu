@@ -1,0 +1,126 @@
+// rtm_post_backbone_step: the whole post-backbone step of B streams in two launches.
+//
+//   1. decode_tma / decode_ldg (nms.cu)   head scan, candidate lists            HBM-bound
+//   2. post_kernel (this file)            one CTA per stream: NMS -> tracker step -> zone step
+//
+// The three per-stream stages are small and strictly ordered; as separate kernels each paid a
+// launch / drain overhead that was larger than its work (profiles/r1_*: 64-CTA kernels of
+// 12-30 us whose SMs were busy a fraction of that).  Fused, the detections of a stream stay with
+// the CTA that produced them (the tracker reads them back through L1 right after the block
+// barrier) and the step costs one dependent launch instead of three.  The stage bodies are the
+// same device functions the stand-alone kernels run (nms_body.cuh, track_body.cuh, zone_body.cuh),
+// so the fused step is bit-identical to rtm_decode_nms + rtm_track_step + rtm_zone_step.
+#include <stdlib.h>
+
+#include "nms_body.cuh"
+#include "track_body.cuh"
+#include "zone_body.cuh"
+
+namespace {
+
+constexpr int kPostThreads = 512;
+
+struct PostArgs {
+  rtm::Workspace ws;
+  rtm_nms_params prm;
+  float iou_gate;
+  rtm::NmsOut out;
+  rtm::TrackArgs trk;
+  rtm::ZoneArgs zone;
+  int has_zones;
+};
+
+__global__ void __launch_bounds__(kPostThreads) post_kernel(const __grid_constant__ PostArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_keep[rtm::kMaxDetCap];
+  __shared__ int s_scan[33];
+  const int b = blockIdx.x;
+  rtm::nms_stream<kPostThreads>(a.ws, a.prm, a.iou_gate, a.out, b, smem_raw, s_keep, s_scan);  // ends with a barrier
+  rtm::track_stream<kPostThreads>(a.trk, b, smem_raw);
+  __syncthreads();
+  if (a.has_zones) rtm::zone_stream<kPostThreads>(a.zone, b, smem_raw, s_scan);
+}
+
+bool fuse_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RTM_FUSE_POST");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+}  // namespace
+
+extern "C" int rtm_post_backbone_step(const rtm_step_io* io, const rtm_nms_params* params,
+                                      rtm_cuda_stream stream) {
+  RTM_REQUIRE(io && params, "rtm_post_backbone_step: null argument");
+  RTM_REQUIRE(io->table_in && io->table_out, "rtm_post_backbone_step: null track table");
+  const int B = io->table_in->num_streams;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+
+  const size_t track_smem = rtm::track_smem_bytes(io->det_stride, io->table_in->capacity);
+  const int max_vertices = 2048;
+  size_t smem = rtm::kNmsSmemBytes;
+  if (track_smem > smem) smem = track_smem;
+  if (io->zones && static_cast<size_t>(max_vertices) * 8 > smem) smem = static_cast<size_t>(max_vertices) * 8;
+
+  if (!fuse_enabled() || smem > 200 * 1024) {
+    // unfused fallback: the three stand-alone entry points back to back
+    int rc = rtm_decode_nms(io->head_p3, io->head_p4, io->head_p5, io->head_dtype, B, io->img_h, io->img_w, params,
+                            io->scale, io->det_xyxy, io->det_conf, io->det_cls, io->det_anchor, io->det_keep,
+                            io->det_count, io->det_stride, io->status, io->workspace, io->workspace_bytes, stream);
+    if (rc) return rc;
+    rc = rtm_track_step(io->table_in, io->table_out, io->det_xyxy, io->det_conf, io->det_cls, io->det_count,
+                        io->det_stride, io->track_thresh, io->match_thresh, io->track_buffer, io->det_track_id,
+                        io->det_kind, io->src_row, io->status, stream);
+    if (rc) return rc;
+    if (!io->zones) return RTM_OK;
+    return rtm_zone_step(io->zones, io->table_out, io->src_row, io->state_in, io->state_out, io->now,
+                         io->now_per_stream, io->frame_id, io->events, io->event_stride, io->event_count,
+                         io->status, stream);
+  }
+
+  // ---- argument checks of the three stages ----
+  RTM_REQUIRE(io->det_xyxy && io->det_conf && io->det_cls && io->det_count && io->workspace, "rtm_post_backbone_step: null detection buffers");
+  RTM_REQUIRE(params->max_det > 0 && params->max_det <= rtm::kMaxDetCap && io->det_stride >= params->max_det,
+              "rtm_post_backbone_step: max_det %d / det_stride %d out of range", params->max_det, io->det_stride);
+  RTM_REQUIRE((reinterpret_cast<uintptr_t>(io->det_xyxy) & 15) == 0, "det_xyxy must be 16-byte aligned");
+  RTM_REQUIRE(io->table_in->num_streams == io->table_out->num_streams && io->table_in->capacity == io->table_out->capacity &&
+                  io->table_in->capacity > 0 && B > 0, "rtm_post_backbone_step: bad track tables");
+  RTM_REQUIRE(io->table_in->xyxy != io->table_out->xyxy, "rtm_post_backbone_step: table_in and table_out must be distinct");
+  if (io->zones) {
+    RTM_REQUIRE(io->state_in && io->state_out && io->events && io->event_count && io->event_stride > 0 && io->src_row,
+                "rtm_post_backbone_step: incomplete zone arguments");
+    RTM_REQUIRE(io->zones->num_streams == B && io->zones->num_columns > 0, "rtm_post_backbone_step: zone set shape");
+    RTM_REQUIRE(io->state_in->first_seen != io->state_out->first_seen, "rtm_post_backbone_step: zone state must ping-pong");
+  }
+
+  PostArgs a;
+  int rc = rtm::launch_decode_stage(io->head_p3, io->head_p4, io->head_p5, io->head_dtype, B, io->img_h, io->img_w, params,
+                                    io->workspace, io->workspace_bytes, &a.ws, s);
+  if (rc) return rc;
+  a.prm = *params;
+  a.iou_gate = rtm::iou_gate_for(params->iou_thres);
+  a.out = rtm::NmsOut{io->scale, io->det_xyxy, io->det_conf, io->det_cls, io->det_anchor, io->det_keep, io->det_count,
+                      io->det_stride, io->status};
+  a.trk = rtm::TrackArgs{*io->table_in, *io->table_out, io->det_xyxy, io->det_conf, io->det_cls, io->det_count,
+                         io->det_stride, io->track_thresh, io->match_thresh, io->track_buffer, io->det_track_id,
+                         io->det_kind, io->src_row, io->status};
+  a.has_zones = io->zones != nullptr;
+  if (a.has_zones)
+    a.zone = rtm::ZoneArgs{*io->zones, *io->table_out, io->src_row, *io->state_in, *io->state_out, io->now,
+                           io->now_per_stream, io->frame_id, io->events, io->event_stride, io->event_count,
+                           io->status, max_vertices};
+  static size_t configured = 0;
+  if (smem > configured) {
+    RTM_CUDA(cudaFuncSetAttribute(post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured = smem;
+  }
+  {
+    rtm::ProfileScope prof(RTM_K_POST, s);
+    post_kernel<<<B, kPostThreads, smem, s>>>(a);
+  }
+  RTM_LAUNCH_CHECK("post_kernel");
+  return RTM_OK;
+}
