@@ -124,35 +124,88 @@ class ClockSampler:
 # ---------------------------------------------------------------------------
 # the oracle chain on the CPU (cpu_baseline leg and the reference arm)
 # ---------------------------------------------------------------------------
-def oracle_stream_step(heads_f32, trk, zon, frame_id, now, classes=WANTED):
-    """One stream-frame through the oracle port: decode + NMS -> tracker -> zones (CPU)."""
-    from oracle import detect_ref
-    det = detect_ref.detect_post(heads_f32, (1080, 1920), classes=classes)[0]
-    trk.step(det["xyxy"], det["conf"], det["cls"])
-    act = trk.active_rows()
-    ev = zon.process(zip(trk.track_id[act], trk.xyxy[act], trk.cls[act]), frame_id, now)
-    return len(det["conf"]), len(ev)
+def load_reference_modules():
+    """The UNMODIFIED reference tracker / zone engine from baseline/_ref (pip --no-deps install of
+    /root/reference), or None.  Its detector cannot be imported anywhere: it needs
+    ultralytics, which is not installable offline."""
+    path = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isfile(os.path.join(path, "src", "tracking", "tracker.py")):
+        return None
+    try:
+        if path not in sys.path:
+            sys.path.insert(0, path)
+        from loguru import logger
+        logger.remove()
+        rt = importlib.import_module("src.tracking.tracker")
+        rz = importlib.import_module("src.events.zone_engine")
+        return rt, rz
+    except Exception:
+        return None
+
+
+class CpuStream:
+    """One stream of the CPU arm: oracle port of ultralytics' decode + NMS + rescale (torch CPU,
+    torchvision.ops.nms), then the reference's own MultiObjectTracker.update and
+    ZoneEventEngine.process when baseline/_ref is present, else their oracle restatements."""
+
+    def __init__(self, zones, ref=None, tmpdir=None):
+        import types
+        from oracle import tracker_ref, zone_ref
+        self.ref, self.types = ref, types
+        if ref is not None:
+            rt, rz = ref
+            self.trk = rt.MultiObjectTracker("bytetrack", bytetrack=dict(track_thresh=0.5, track_buffer=30, match_thresh=0.8))
+            self.eng = rz.ZoneEventEngine(zones, log_path=os.path.join(tmpdir or "/tmp", f"rtm_events_{os.getpid()}_{id(self)}.jsonl"))
+            self.clock = [0.0]
+            rz.time.time = lambda c=self.clock: c[0]         # zone_engine.py:84 reads time.time()
+        else:
+            self.trk = tracker_ref.TrackerOracle()
+            self.eng = zone_ref.ZoneOracle(zones, pip=zone_ref.cv2_pip)
+
+    def step(self, heads_f32, frame_id, now):
+        from oracle import detect_ref
+        det = detect_ref.detect_post(heads_f32, (1080, 1920), classes=WANTED)[0]
+        if self.ref is not None:
+            self.ref[1].time.time = lambda c=self.clock: c[0]
+            self.clock[0] = now
+            out = self.trk.update(self.types.SimpleNamespace(xyxy=det["xyxy"], confidence=det["conf"], class_id=det["cls"]))
+            assert out == []                                   # SURVEY.md section 0 F2
+            active = [self.types.SimpleNamespace(track_id=t["track_id"], xyxy=t["xyxy"], class_id=t["class_id"])
+                      for t in self.trk._core._tracks if t["time_since_update"] == 1]
+            ev = self.eng.process(active, frame_id)
+        else:
+            self.trk.step(det["xyxy"], det["conf"], det["cls"])
+            act = self.trk.active_rows()
+            ev = self.eng.process(zip(self.trk.track_id[act], self.trk.xyxy[act], self.trk.cls[act]), frame_id, now)
+        return len(det["conf"]), len(ev)
+
+
+def cpu_chain_description(ref):
+    tail = ("the reference's unmodified MultiObjectTracker.update + ZoneEventEngine.process (baseline/_ref)" if ref is not None
+            else "oracle restatements of the reference tracker / zone engine (baseline/_ref absent)")
+    return "oracle port of ultralytics decode + non_max_suppression + scale_boxes (torch CPU, torchvision.ops.nms; ultralytics is not installable) -> " + tail
 
 
 def cpu_port_throughput(host_frames, zones, seconds):
-    """frames/s of the oracle port on ONE thread over `host_frames[f][level] (S,144,h,w)` replayed."""
+    """frames/s of the CPU chain on ONE thread over `host_frames[f][level] (S,144,h,w)` replayed."""
+    import tempfile
     import torch
-    from oracle import tracker_ref, zone_ref
     torch.set_num_threads(1)
+    ref = load_reference_modules()
     S = host_frames[0][0].shape[0]
-    trk = [tracker_ref.TrackerOracle() for _ in range(S)]
-    zon = [zone_ref.ZoneOracle(zones[s], pip=zone_ref.cv2_pip) for s in range(S)]
+    tmp = tempfile.mkdtemp(prefix="rtm_cpu_")
+    streams = [CpuStream(zones[s], ref, tmp) for s in range(S)]
     done, f = 0, 0
     t0 = time.perf_counter()
     while True:
         heads = host_frames[f % len(host_frames)]
         for s in range(S):
-            oracle_stream_step([h[s:s + 1] for h in heads], trk[s], zon[s], f, T0 + f / FPS)
+            streams[s].step([h[s:s + 1] for h in heads], f, T0 + f / FPS)
         done += S
         f += 1
         if time.perf_counter() - t0 >= seconds and f >= 2:
             break
-    return done / (time.perf_counter() - t0), done
+    return done / (time.perf_counter() - t0), done, ref is not None
 
 
 def _reference_worker(args):
@@ -162,18 +215,17 @@ def _reference_worker(args):
     torch.set_num_threads(threads)
     if ROOT not in sys.path:
         sys.path.insert(0, ROOT)
-    pkg = importlib.import_module("rtmodt_b200")
+    importlib.import_module("rtmodt_b200")
     from rtmodt_b200.workload import PostBackboneWorkload
-    from oracle import tracker_ref, zone_ref
+    ref = load_reference_modules()
     wl = [PostBackboneWorkload(1, frames, first_stream=s, device="cpu", dtype=torch.float32) for s in streams]
-    trk = [tracker_ref.TrackerOracle() for _ in streams]
-    zon = [zone_ref.ZoneOracle(w.zones[0], pip=zone_ref.cv2_pip) for w in wl]
+    cpu = [CpuStream(w.zones[0], ref, os.path.dirname(barrier_path)) for w in wl]
     dets = evs = 0
 
     def one(f):
         nonlocal dets, evs
-        for w, t, z in zip(wl, trk, zon):
-            d, e = oracle_stream_step(w.heads[f % frames], t, z, f, T0 + f / FPS)
+        for w, c in zip(wl, cpu):
+            d, e = c.step(w.heads[f % frames], f, T0 + f / FPS)
             dets += d
             evs += e
 
@@ -191,7 +243,7 @@ def _reference_worker(args):
     for f in range(warmup, warmup + steps):
         one(f)
     t1 = time.time()
-    return t0, t1, len(streams) * steps, dets, evs
+    return t0, t1, len(streams) * steps, dets, evs, ref is not None
 
 
 def run_reference(args):
@@ -217,8 +269,10 @@ def run_reference(args):
     t1 = max(r[1] for r in res)
     frames = sum(r[2] for r in res)
     value = frames / (t1 - t0)
+    used_ref = all(r[5] for r in res)
     sample = (f"{total_streams} streams x {args.steps} frames (after {args.warmup} warm-up frames) of the same seeded workload, "
-              f"{workers} worker processes x {threads} torch threads on {cores} host cores")
+              f"{workers} worker processes x {threads} torch threads on {cores} host cores; "
+              + cpu_chain_description(True if used_ref else None))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * (t1 - t0) / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -329,7 +383,7 @@ def run_b200(args):
         extras = {}
         if not args.no_extras:
             # ---- latency mode: one step at a time, p50 / p99 of the per-step device time ----
-            lat = []
+            lat, ev_seen = [], 0
             for _ in range(min(300, max(50, K))):
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
@@ -337,9 +391,10 @@ def run_b200(args):
                 b.record()
                 b.synchronize()
                 lat.append(a.elapsed_time(b))
+                ev_seen += int(sb.zones.event_count.sum().item())
             lat.sort()
             extras["latency_ms_per_step"] = {"p50": lat[len(lat) // 2], "p99": lat[min(len(lat) - 1, int(len(lat) * 0.99))],
-                                             "steps": len(lat), "streams_per_step": S}
+                                             "steps": len(lat), "streams_per_step": S, "zone_events_emitted": ev_seen}
             if rank == 0:
                 extras["letterbox"] = letterbox_bench(pkg, lib, dev, S, hbm_peak)
 
@@ -360,10 +415,10 @@ def run_b200(args):
     if rank == 0 and world == 1 and not args.no_cpu:
         sample_streams = list(range(min(4, S)))
         host_frames = [wl.host_frame(ff, sample_streams) for ff in range(F)]
-        v, n = cpu_port_throughput(host_frames, [wl.zones[s] for s in sample_streams], args.cpu_seconds)
+        v, n, used_ref = cpu_port_throughput(host_frames, [wl.zones[s] for s in sample_streams], args.cpu_seconds)
         cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": f"{len(sample_streams)} streams of the same workload, {F}-frame cycle replayed for {n} stream-frames "
-                         f"(>= {args.cpu_seconds:.0f} s), oracle port (torch CPU decode + torchvision NMS + NumPy tracker + cv2 zones), 1 thread",
+                         f"(>= {args.cpu_seconds:.0f} s), 1 thread; " + cpu_chain_description(True if used_ref else None),
                "host_cores_available": os.cpu_count()}
 
     if rank == 0:

@@ -11,7 +11,7 @@ All arithmetic runs in ``librtmodt_b200.so`` (hand-written CUDA, sm_100a); there
 fallback - entry points raise ``RtmError`` when the library or the GPU is missing.
 """
 
-from . import _lib, synth  # noqa: F401
+from . import _lib, sharding, synth, workload  # noqa: F401
 from ._lib import RtmError  # noqa: F401
 from .streams import DeviceTrackTable, HostFeeder, StreamBatch, Zone, ZoneEvent, ZoneTables  # noqa: F401
 from .tracking import ByteTracker, MultiObjectTracker, Track  # noqa: F401

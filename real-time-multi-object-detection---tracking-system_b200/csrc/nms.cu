@@ -611,7 +611,7 @@ __global__ void __launch_bounds__(256) pred_candidates_kernel(const float* __res
 // ---------------------------------------------------------------------------------------
 // nms
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kNmsThreads) nms_kernel(const Workspace ws, const rtm_nms_params prm,
+__global__ void __launch_bounds__(kNmsThreads, 1) nms_kernel(const Workspace ws, const rtm_nms_params prm,
                                                           const float iou_gate, const NmsOut out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_keep[rtm::kMaxDetCap];

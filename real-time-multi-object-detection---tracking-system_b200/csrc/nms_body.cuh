@@ -236,10 +236,96 @@ __device__ __forceinline__ int nms_run(const Workspace& ws, const rtm_nms_params
   }
   __syncthreads();
 
+  int kept = 0;
+  if (IN_SMEM) {
+    // ---- greedy scan, register-resident: lane (warp, lane) owns candidates j = tid + k*THREADS
+    //      (word k*kWarps + warp of the alive bitmask); each barrier round settles the first
+    //      kBatch alive candidates exactly as the serial scan would: the first is a survivor, each
+    //      next one survives unless an earlier survivor of the batch suppresses it, and every
+    //      other candidate is tested against the batch's survivors ----
+    constexpr int KMAX = kNmsSmemCand / THREADS;
+    constexpr int kBatch = 4;
+    float4 mybox[KMAX];
+    float myarea[KMAX];
+    bool myalive[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      const int j = tid + k * THREADS;
+      myalive[k] = j < n;
+      mybox[k] = myalive[k] ? sbox[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+      myarea[k] = myalive[k] ? sarea[j] : 0.f;
+    }
+    uint32_t* cur = alive0;
+    uint32_t* nxt = alive1;
+    int w0 = 0;
+    while (kept < max_det) {
+      // first kBatch alive candidates in score order (uniform across the block)
+      int c[kBatch], nb = 0;
+      {
+        int w = w0;
+        uint32_t word = w < words ? cur[w] : 0u;
+        while (w < words && nb < kBatch) {
+          if (word == 0u) {
+            ++w;
+            if (nb == 0) w0 = w;
+            word = w < words ? cur[w] : 0u;
+          } else {
+            c[nb++] = (w << 5) + __ffs(word) - 1;
+            word &= word - 1;
+          }
+        }
+      }
+      if (nb == 0) break;
+      float4 bb[kBatch];
+      float ba[kBatch];
+      bool surv[kBatch];
+#pragma unroll
+      for (int i = 0; i < kBatch; ++i) {
+        const int ci = i < nb ? c[i] : c[0];
+        bb[i] = sbox[ci];
+        ba[i] = sarea[ci];
+        surv[i] = i < nb;
+      }
+#pragma unroll
+      for (int i = 1; i < kBatch; ++i)
+#pragma unroll
+        for (int p2 = 0; p2 < i; ++p2)
+          if (surv[i] && surv[p2] && suppresses(bb[p2], ba[p2], bb[i], ba[i], iou_gate)) surv[i] = false;
+#pragma unroll
+      for (int i = 0; i < kBatch; ++i) {
+        if (surv[i]) {
+          if (kept < max_det) {
+            if (tid == 0) s_keep[kept] = c[i];
+            ++kept;
+          } else {
+            surv[i] = false;  // beyond max_det: never reported (the scan stops after this round)
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        const int j = tid + k * THREADS;
+        bool alive = myalive[k];
+        if (alive) {
+#pragma unroll
+          for (int i = 0; i < kBatch; ++i) {
+            if (i < nb && (j == c[i] || (surv[i] && suppresses(bb[i], ba[i], mybox[k], myarea[k], iou_gate)))) alive = false;
+          }
+        }
+        myalive[k] = alive;
+        const uint32_t nw = __ballot_sync(kFull, alive);
+        if (lane == 0 && k * kWarps + warp < words) nxt[k * kWarps + warp] = nw;
+      }
+      __syncthreads();
+      uint32_t* t = cur;
+      cur = nxt;
+      nxt = t;
+    }
+  } else {
   // ---- greedy scan, one survivor per iteration; alive bits rebuilt by ballot (ping-pong) ----
   uint32_t* cur = alive0;
   uint32_t* nxt = alive1;
-  int w0 = 0, kept = 0;
+  int w0 = 0;
   while (kept < max_det) {
     while (w0 < words && cur[w0] == 0u) ++w0;
     if (w0 >= words) break;
@@ -260,6 +346,7 @@ __device__ __forceinline__ int nms_run(const Workspace& ws, const rtm_nms_params
     uint32_t* t = cur;
     cur = nxt;
     nxt = t;
+  }
   }
   __syncthreads();
 

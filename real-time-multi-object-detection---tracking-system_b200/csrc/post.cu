@@ -30,7 +30,7 @@ struct PostArgs {
   int has_zones;
 };
 
-__global__ void __launch_bounds__(kPostThreads) post_kernel(const __grid_constant__ PostArgs a) {
+__global__ void __launch_bounds__(kPostThreads, 1) post_kernel(const __grid_constant__ PostArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_keep[rtm::kMaxDetCap];
   __shared__ int s_scan[33];

@@ -54,12 +54,24 @@ template <int THREADS>
 __device__ __forceinline__ void zone_stream(const ZoneArgs& a, const int b, unsigned char* smem_raw, int* s_scan) {
   const int tid = threadIdx.x;
   constexpr int kZoneThreads = THREADS;
+  // per-stream zone table staged once (one global round trip instead of several per zone test)
+  __shared__ int s_zoff[kMaxZonesPerStream + 1];
+  __shared__ int s_zcol[kMaxZonesPerStream];
+  __shared__ double s_zdwell[kMaxZonesPerStream];
+  __shared__ double s_zcool[kMaxZonesPerStream];
   const int cap = a.trk.capacity, C = a.zs.num_columns;
   const int z0 = a.zs.zone_offsets[b], z1 = a.zs.zone_offsets[b + 1];
   const int nz = min(z1 - z0, kMaxZonesPerStream);
   if (tid == 0 && z1 - z0 > kMaxZonesPerStream && a.status) atomicOr(&a.status[b], RTM_STATUS_ZONE_LIMIT);
-  const int v0 = a.zs.poly_offsets[z0], v1 = a.zs.poly_offsets[z0 + nz];
-  const int nv = v1 - v0;
+  const int v0 = a.zs.poly_offsets[z0];
+  if (tid <= nz) s_zoff[tid] = a.zs.poly_offsets[z0 + tid] - v0;
+  if (tid < nz) {
+    s_zcol[tid] = a.zs.column[z0 + tid];
+    s_zdwell[tid] = a.zs.dwell_sec[z0 + tid];
+    s_zcool[tid] = a.zs.cooldown_sec[z0 + tid];
+  }
+  __syncthreads();
+  const int nv = s_zoff[nz];
 
   // stage the stream's polygons (falls back to global memory when they do not fit)
   int2* s_poly = reinterpret_cast<int2*>(smem_raw);
@@ -90,40 +102,39 @@ __device__ __forceinline__ void zone_stream(const ZoneArgs& a, const int b, unsi
     if (live) {
       const int src = a.src_row ? a.src_row[row0 + r] : r;
       const bool active = a.trk.time_since_update[row0 + r] == 1;
-      // carry the row's state over (purging dwell timers of rows absent from this call)
+      if (active) box = boxes[r];
+      // the row's state, all columns loaded before anything is stored (independent loads in
+      // flight together); rows absent from this call lose their dwell timers, keep cooldowns
+      double fs[kMaxZonesPerStream], la[kMaxZonesPerStream];
       for (int c = 0; c < C; ++c) {
-        double fs = kNaN, la = 0.0;
+        fs[c] = kNaN;
+        la[c] = 0.0;
         if (src >= 0) {
-          la = a.sin.last_alert[st0 + static_cast<size_t>(c) * cap + src];
-          if (active) fs = a.sin.first_seen[st0 + static_cast<size_t>(c) * cap + src];
+          la[c] = a.sin.last_alert[st0 + static_cast<size_t>(c) * cap + src];
+          if (active) fs[c] = a.sin.first_seen[st0 + static_cast<size_t>(c) * cap + src];
         }
-        a.sout.first_seen[st0 + static_cast<size_t>(c) * cap + r] = fs;
-        a.sout.last_alert[st0 + static_cast<size_t>(c) * cap + r] = la;
       }
       if (active) {
-        box = boxes[r];
         cx = __float2int_rz(__fdiv_rn(__fadd_rn(box.x, box.z), 2.0f));
         cy = __float2int_rz(__fdiv_rn(__fadd_rn(box.y, box.w), 2.0f));
         for (int z = 0; z < nz; ++z) {
-          const int p0 = a.zs.poly_offsets[z0 + z] - v0;
-          const int k = a.zs.poly_offsets[z0 + z + 1] - v0 - p0;
-          const size_t si = st0 + static_cast<size_t>(a.zs.column[z0 + z]) * cap + r;
+          const int p0 = s_zoff[z], k = s_zoff[z + 1] - p0, c = s_zcol[z];
           if (point_in_polygon(poly + p0, k, cx, cy) >= 0) {
-            double fs = a.sout.first_seen[si];
-            if (fs != fs) {  // not in the zone before: start the dwell timer
-              fs = now;
-              a.sout.first_seen[si] = fs;
-            }
-            const double dwell = now - fs;
-            if (dwell >= a.zs.dwell_sec[z0 + z] && now - a.sout.last_alert[si] >= a.zs.cooldown_sec[z0 + z]) {
+            if (fs[c] != fs[c]) fs[c] = now;  // not in the zone before: start the dwell timer
+            const double dwell = now - fs[c];
+            if (dwell >= s_zdwell[z] && now - la[c] >= s_zcool[z]) {
               fired |= 1ull << z;
               dwell_of[z] = dwell;
-              a.sout.last_alert[si] = now;
+              la[c] = now;
             }
           } else {
-            a.sout.first_seen[si] = kNaN;
+            fs[c] = kNaN;
           }
         }
+      }
+      for (int c = 0; c < C; ++c) {
+        a.sout.first_seen[st0 + static_cast<size_t>(c) * cap + r] = fs[c];
+        a.sout.last_alert[st0 + static_cast<size_t>(c) * cap + r] = la[c];
       }
     }
     // rank this round's events in (row, zone) order
