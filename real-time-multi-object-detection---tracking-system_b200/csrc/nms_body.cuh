@@ -146,7 +146,7 @@ __device__ __forceinline__ int nms_count(const Workspace& ws, const int b, int* 
 
 // The NMS proper for a stream with n > 0 candidates.  IN_SMEM: working arrays live in `smem`
 // (kNmsSmemBytes, n <= kNmsSmemCand); otherwise in the workspace spill arrays.
-template <int THREADS, bool IN_SMEM>
+template <int THREADS, bool IN_SMEM, int kBatch>
 __device__ __forceinline__ int nms_run(const Workspace& ws, const rtm_nms_params& prm, const float iou_gate,
                                        const NmsOut& out, const int b, const int n, unsigned char* smem,
                                        int* s_keep, int* s_scan) {
@@ -244,7 +244,6 @@ __device__ __forceinline__ int nms_run(const Workspace& ws, const rtm_nms_params
     //      next one survives unless an earlier survivor of the batch suppresses it, and every
     //      other candidate is tested against the batch's survivors ----
     constexpr int KMAX = kNmsSmemCand / THREADS;
-    constexpr int kBatch = 4;
     float4 mybox[KMAX];
     float myarea[KMAX];
     bool myalive[KMAX];
@@ -385,7 +384,7 @@ __device__ __forceinline__ int nms_run(const Workspace& ws, const rtm_nms_params
 // One stream.  `smem` = kNmsSmemBytes of dynamic shared memory, `s_keep` = kMaxDetCap ints,
 // `s_scan` = 33 ints.  All THREADS threads of the block must call it.  On return (after a
 // trailing __syncthreads) s_keep[0..kept) and the output slabs are written; returns kept.
-template <int THREADS>
+template <int THREADS, int kBatch = 1>
 __device__ __forceinline__ int nms_stream(const Workspace& ws, const rtm_nms_params& prm, const float iou_gate,
                                           const NmsOut& out, const int b, unsigned char* smem, int* s_keep,
                                           int* s_scan) {
@@ -395,8 +394,8 @@ __device__ __forceinline__ int nms_stream(const Workspace& ws, const rtm_nms_par
     __syncthreads();
     return 0;
   }
-  if (n <= kNmsSmemCand) return nms_run<THREADS, true>(ws, prm, iou_gate, out, b, n, smem, s_keep, s_scan);
-  return nms_run<THREADS, false>(ws, prm, iou_gate, out, b, n, smem, s_keep, s_scan);
+  if (n <= kNmsSmemCand) return nms_run<THREADS, true, kBatch>(ws, prm, iou_gate, out, b, n, smem, s_keep, s_scan);
+  return nms_run<THREADS, false, 1>(ws, prm, iou_gate, out, b, n, smem, s_keep, s_scan);
 }
 
 }  // namespace rtm

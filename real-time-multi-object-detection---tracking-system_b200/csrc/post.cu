@@ -30,12 +30,13 @@ struct PostArgs {
   int has_zones;
 };
 
+template <int kBatch>
 __global__ void __launch_bounds__(kPostThreads, 1) post_kernel(const __grid_constant__ PostArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_keep[rtm::kMaxDetCap];
   __shared__ int s_scan[33];
   const int b = blockIdx.x;
-  rtm::nms_stream<kPostThreads>(a.ws, a.prm, a.iou_gate, a.out, b, smem_raw, s_keep, s_scan);  // ends with a barrier
+  rtm::nms_stream<kPostThreads, kBatch>(a.ws, a.prm, a.iou_gate, a.out, b, smem_raw, s_keep, s_scan);  // ends with a barrier
   rtm::track_stream<kPostThreads>(a.trk, b, smem_raw);
   __syncthreads();
   if (a.has_zones) rtm::zone_stream<kPostThreads>(a.zone, b, smem_raw, s_scan);
@@ -114,12 +115,21 @@ extern "C" int rtm_post_backbone_step(const rtm_step_io* io, const rtm_nms_param
                            io->status, max_vertices};
   static size_t configured = 0;
   if (smem > configured) {
-    RTM_CUDA(cudaFuncSetAttribute(post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    RTM_CUDA(cudaFuncSetAttribute(post_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    RTM_CUDA(cudaFuncSetAttribute(post_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    RTM_CUDA(cudaFuncSetAttribute(post_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     configured = smem;
+  }
+  static int batch = -1;  // survivors settled per barrier round of the NMS scan (tuning knob)
+  if (batch < 0) {
+    const char* e = getenv("RTM_NMS_BATCH");
+    batch = e ? atoi(e) : 1;
   }
   {
     rtm::ProfileScope prof(RTM_K_POST, s);
-    post_kernel<<<B, kPostThreads, smem, s>>>(a);
+    if (batch == 4) post_kernel<4><<<B, kPostThreads, smem, s>>>(a);
+    else if (batch == 2) post_kernel<2><<<B, kPostThreads, smem, s>>>(a);
+    else post_kernel<1><<<B, kPostThreads, smem, s>>>(a);
   }
   RTM_LAUNCH_CHECK("post_kernel");
   return RTM_OK;
