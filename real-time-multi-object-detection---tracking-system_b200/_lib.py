@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librtmodt_b200.so")
+#: RTM_LIB_PATH selects another build of the same library (diagnosis builds of tools/post_timeline.py)
+LIB_PATH = os.environ.get("RTM_LIB_PATH") or os.path.join(HERE, "librtmodt_b200.so")
 
 RTM_F32, RTM_F16, RTM_BF16 = 0, 1, 2
 STATUS_TRACK_OVERFLOW, STATUS_DET_OVERFLOW, STATUS_CAND_OVERFLOW = 1, 2, 4

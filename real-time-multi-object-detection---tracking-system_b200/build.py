@@ -34,16 +34,16 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, out: str = LIB, defines=()) -> str:
     """Compile every CUDA source for sm_100a into one shared library; returns its path."""
-    if not force and not is_stale():
+    if out == LIB and not force and not is_stale():
         return LIB
     cmd = [nvcc_path(), "-shared", "-Xcompiler", "-fPIC", "-std=c++17", "-O3", "-lineinfo",
            "-gencode", "arch=compute_100a,code=sm_100a",
            # float decisions must reproduce NumPy / torch CPU bit for bit: no FMA contraction,
            # IEEE division and square root, no flush-to-zero (SURVEY.md section 7, hard parts)
            "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
-           "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", LIB]
+           "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", out] + [f"-D{d}" for d in defines]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += [os.path.join(CSRC, s) for s in SOURCES]
@@ -52,7 +52,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
     if verbose:
         sys.stderr.write(proc.stderr)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

@@ -163,11 +163,14 @@ struct HeadPtrs {
 // ---------------------------------------------------------------------------------------
 // decode_tma
 // ---------------------------------------------------------------------------------------
-constexpr int kTileW = 80;  // divides 6400 / 1600 / 400 (and every level of a W = 640, H % 128 == 0 input)
-constexpr int kAnchorsPerWarp = 16;                      // a lane owns 2 adjacent anchors x one class quarter
-constexpr int kConsumerWarps = kTileW / kAnchorsPerWarp;  // 5
-constexpr int kTmaThreads = (kConsumerWarps + 1) * 32;    // + one producer warp
+// Tile width (anchors per tile) is a template parameter: 64 / 128 make every channel row of a
+// 16-bit tile a whole number of 128-byte lines (one or two full-line L2 requests per row), 80
+// divides 6400 / 1600 / 400 exactly but gives 160-byte rows that straddle lines.  Tiles that run
+// past the end of a level are zero-filled by the TMA unit and their anchors masked out.
+constexpr int kAnchorsPerWarp = 16;  // a lane owns 2 adjacent anchors x one class quarter
 constexpr int kMaxStages = 8;
+constexpr int tma_consumer_warps(int tile_w) { return tile_w / kAnchorsPerWarp; }
+constexpr int tma_threads(int tile_w) { return (tma_consumer_warps(tile_w) + 1) * 32; }  // + one producer warp
 
 struct TmaGeom {
   HeadGeom g;
@@ -249,7 +252,7 @@ struct Pair<float> {
 // exact N1 of one anchor column for the lanes of its four class quarters: probability and index
 // of the FIRST class attaining the maximum float32 sigmoid; lanes whose quarter cannot pass
 // contribute (-1, INT_MAX).  `m` is the lane's maximum logit over its classes q, q+4, ...
-template <typename T>
+template <typename T, int kTileW>
 __device__ __forceinline__ void anchor_best(const T* cls_col, const int q, const int iters, const int nc, const float m,
                                             const float logit_gate, float* best, int* bc) {
   float sc = -1.f;
@@ -280,8 +283,8 @@ __device__ __forceinline__ void anchor_best(const T* cls_col, const int q, const
   *bc = j;
 }
 
-template <typename T, bool NC80>
-__global__ void __launch_bounds__(kTmaThreads) decode_tma_kernel(const __grid_constant__ CUtensorMap map0,
+template <typename T, bool NC80, int kTileW>
+__global__ void __launch_bounds__(tma_threads(kTileW)) decode_tma_kernel(const __grid_constant__ CUtensorMap map0,
                                                                  const __grid_constant__ CUtensorMap map1,
                                                                  const __grid_constant__ CUtensorMap map2,
                                                                  const TmaGeom tg, const rtm_nms_params prm,
@@ -290,6 +293,7 @@ __global__ void __launch_bounds__(kTmaThreads) decode_tma_kernel(const __grid_co
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   using P = Pair<T>;
+  constexpr int kConsumerWarps = kTileW / kAnchorsPerWarp;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int stages = tg.stages;
@@ -343,6 +347,7 @@ __global__ void __launch_bounds__(kTmaThreads) decode_tma_kernel(const __grid_co
   const int w0 = tg.g.lv[0].w, w1 = tg.g.lv[1].w, w2 = tg.g.lv[2].w;
   const int a1 = tg.g.lv[1].anchor0, a2 = tg.g.lv[2].anchor0;
   const int st0 = tg.g.lv[0].stride, st1 = tg.g.lv[1].stride, st2 = tg.g.lv[2].stride;
+  const int hw0 = tg.g.lv[0].hw, hw1 = tg.g.lv[1].hw, hw2 = tg.g.lv[2].hw;
   uint8_t* mask_bytes = reinterpret_cast<uint8_t*>(ws.mask);
 
   int s = 0, phase = 0;
@@ -351,6 +356,7 @@ __global__ void __launch_bounds__(kTmaThreads) decode_tma_kernel(const __grid_co
     const int lv_w = li == 2 ? w2 : (li == 1 ? w1 : w0);
     const int lv_stride = li == 2 ? st2 : (li == 1 ? st1 : st0);
     const int lv_anchor0 = li == 2 ? a2 : (li == 1 ? a1 : 0);
+    const int lv_hw = li == 2 ? hw2 : (li == 1 ? hw1 : hw0);
     const int pix = (r - (li == 2 ? tb2 : (li == 1 ? tb1 : 0))) * kTileW + col;
     mbar_wait(&full_bar[s], phase);
     const T* tile = reinterpret_cast<const T*>(tile_smem + static_cast<size_t>(s) * tg.tile_bytes);
@@ -365,7 +371,10 @@ __global__ void __launch_bounds__(kTmaThreads) decode_tma_kernel(const __grid_co
       for (int i = 0; i < iters; ++i)
         if (4 * i + q < nc) mv = P::vmax(mv, P::load(cls_col + 4 * i * kTileW));
     }
-    const float m0 = P::lo(mv), m1 = P::hi(mv);
+    // anchors past the end of the level (zero-filled tail of the last tile) never pass; the test is
+    // warp-uniform because every level holds a multiple of 16 anchors
+    const bool in_level = pix < lv_hw;
+    const float m0 = in_level ? P::lo(mv) : -INFINITY, m1 = in_level ? P::hi(mv) : -INFINITY;
     float am = fmaxf(m0, m1);
     am = fmaxf(am, __shfl_xor_sync(kFull, am, 8));
     am = fmaxf(am, __shfl_xor_sync(kFull, am, 16));
@@ -375,8 +384,8 @@ __global__ void __launch_bounds__(kTmaThreads) decode_tma_kernel(const __grid_co
       // ---- exact N1 for the anchors that can pass, then D1 for the survivors ----
       float best0, best1;
       int bc0, bc1;
-      anchor_best<T>(tile + kBoxCh * kTileW + col, q, iters, nc, m0, logit_gate, &best0, &bc0);
-      anchor_best<T>(tile + kBoxCh * kTileW + col + 1, q, iters, nc, m1, logit_gate, &best1, &bc1);
+      anchor_best<T, kTileW>(tile + kBoxCh * kTileW + col, q, iters, nc, m0, logit_gate, &best0, &bc0);
+      anchor_best<T, kTileW>(tile + kBoxCh * kTileW + col + 1, q, iters, nc, m1, logit_gate, &best1, &bc1);
       cand0 = best0 > prm.conf_thres && class_wanted(prm, bc0 & 255);
       cand1 = best1 > prm.conf_thres && class_wanted(prm, bc1 & 255);
       if (__any_sync(kFull, cand0 || cand1)) {
@@ -409,7 +418,7 @@ __global__ void __launch_bounds__(kTmaThreads) decode_tma_kernel(const __grid_co
     }
     // candidate bits of this warp's 16 anchors: two bytes of the stream's mask
     uint32_t even = __ballot_sync(kFull, cand0 && q == 0) & 0xffu, odd = __ballot_sync(kFull, cand1 && q == 0) & 0xffu;
-    if (lane == 0) {
+    if (lane == 0 && in_level) {
       even = (even | (even << 4)) & 0x0f0fu;
       even = (even | (even << 2)) & 0x3333u;
       even = (even | (even << 1)) & 0x5555u;
@@ -721,14 +730,16 @@ template <>
 CUtensorMapDataType tensor_map_dtype<__nv_bfloat16>() { return CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; }
 
 // returns 1 when the TMA path was launched, 0 when the caller should fall back, < 0 on error
-template <typename T>
-int try_launch_decode_tma(const void* p3, const void* p4, const void* p5, const HeadGeom& g, int B,
-                          const rtm_nms_params& prm, const Workspace& ws, cudaStream_t stream) {
-  if (!want_tma()) return 0;
+template <typename T, int kTileW>
+int launch_decode_tma_w(const void* p3, const void* p4, const void* p5, const HeadGeom& g, int B,
+                        const rtm_nms_params& prm, const Workspace& ws, cudaStream_t stream) {
   EncodeTiledFn encode = tensor_map_encoder();
   if (!encode) return 0;
+  // a warp owns 16 consecutive anchors = two bytes of the stream's mask: every level must hold a
+  // multiple of 16 anchors (so that groups never straddle levels) and have an even width (a lane's
+  // two anchors share a grid row)
   for (int l = 0; l < 3; ++l)
-    if (g.lv[l].hw % kTileW != 0 || g.lv[l].w % 2 != 0) return 0;
+    if (g.lv[l].hw % kAnchorsPerWarp != 0 || g.lv[l].w % 2 != 0) return 0;
   const int ch = kBoxCh + g.num_classes;
   const void* ptrs[3] = {p3, p4, p5};
   CUtensorMap maps[3];
@@ -747,36 +758,64 @@ int try_launch_decode_tma(const void* p3, const void* p4, const void* p5, const 
   TmaGeom tg;
   tg.g = g;
   tg.tiles_before[0] = 0;
-  for (int l = 0; l < 3; ++l) tg.tiles_before[l + 1] = tg.tiles_before[l] + g.lv[l].hw / kTileW;
+  for (int l = 0; l < 3; ++l) tg.tiles_before[l + 1] = tg.tiles_before[l] + (g.lv[l].hw + kTileW - 1) / kTileW;
   tg.total_tiles = tg.tiles_before[3] * B;
   tg.tile_bytes = ch * kTileW * static_cast<int>(sizeof(T));
   if (tg.tile_bytes % 128 != 0) return 0;
-  // ring depth and residency (measured best): 16-bit heads 3 x 22.5 KB and three CTAs per SM,
-  // f32 heads 4 x 45 KB and one CTA per SM
+  // ring depth and residency: as many tiles in flight per SM as fit (RTM_TMA_STAGES / RTM_TMA_CTAS override)
   static const int stages_env = env_int("RTM_TMA_STAGES", 0), ctas_env = env_int("RTM_TMA_CTAS", 0);
-  const int ctas_per_sm = ctas_env > 0 ? ctas_env : (sizeof(T) == 2 ? 3 : 1);
+  const size_t smem_budget = 216 * 1024;
+  int ctas_per_sm = ctas_env > 0 ? ctas_env : (tg.tile_bytes <= 24 * 1024 ? 3 : (tg.tile_bytes <= 40 * 1024 ? 2 : 1));
   tg.stages = stages_env > 0 ? stages_env : (sizeof(T) == 2 ? 3 : 4);
   if (tg.stages > kMaxStages) tg.stages = kMaxStages;
-  while (tg.stages > 1 && static_cast<size_t>(tg.stages) * tg.tile_bytes * ctas_per_sm > 216 * 1024) --tg.stages;
+  while (tg.stages > 1 && static_cast<size_t>(tg.stages) * tg.tile_bytes * ctas_per_sm > smem_budget) --tg.stages;
+  while (ctas_per_sm > 1 && static_cast<size_t>(tg.stages) * tg.tile_bytes * ctas_per_sm > smem_budget) --ctas_per_sm;
   const size_t smem = static_cast<size_t>(tg.stages) * tg.tile_bytes;
+  if (smem > 220 * 1024) return 0;
   static size_t configured = 0;
   if (smem > configured) {
-    RTM_CUDA(cudaFuncSetAttribute(decode_tma_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    RTM_CUDA(cudaFuncSetAttribute(decode_tma_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    RTM_CUDA(cudaFuncSetAttribute(decode_tma_kernel<T, true, kTileW>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    RTM_CUDA(cudaFuncSetAttribute(decode_tma_kernel<T, false, kTileW>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     configured = smem;
   }
   const int grid = min(tg.total_tiles, rtm::sm_count() * ctas_per_sm);
   {
     rtm::ProfileScope prof(RTM_K_DECODE, stream);
     if (g.num_classes == 80)
-      decode_tma_kernel<T, true><<<grid, kTmaThreads, smem, stream>>>(maps[0], maps[1], maps[2], tg, prm,
-                                                                     logit_gate_for(prm.conf_thres), ws);
+      decode_tma_kernel<T, true, kTileW><<<grid, tma_threads(kTileW), smem, stream>>>(maps[0], maps[1], maps[2], tg, prm,
+                                                                                     logit_gate_for(prm.conf_thres), ws);
     else
-      decode_tma_kernel<T, false><<<grid, kTmaThreads, smem, stream>>>(maps[0], maps[1], maps[2], tg, prm,
-                                                                      logit_gate_for(prm.conf_thres), ws);
+      decode_tma_kernel<T, false, kTileW><<<grid, tma_threads(kTileW), smem, stream>>>(maps[0], maps[1], maps[2], tg, prm,
+                                                                                      logit_gate_for(prm.conf_thres), ws);
   }
   RTM_LAUNCH_CHECK("decode_tma_kernel");
   return 1;
+}
+
+template <typename T>
+int try_launch_decode_tma(const void* p3, const void* p4, const void* p5, const HeadGeom& g, int B,
+                          const rtm_nms_params& prm, const Workspace& ws, cudaStream_t stream) {
+  if (!want_tma()) return 0;
+  // anchors per tile (RTM_TMA_TILEW = 32 | 64 | 80 | 128 overrides): 80 when it divides every level
+  // (640 x 640: 6400 / 1600 / 400; measured fastest, profiles/), else 64 / 32 with a masked tail
+  static const int tile_env = env_int("RTM_TMA_TILEW", 0);
+  bool div80 = true;
+  for (int l = 0; l < 3; ++l) div80 = div80 && g.lv[l].hw % 80 == 0;
+  const int tile_w = tile_env > 0 ? tile_env : (div80 ? 80 : (sizeof(T) == 2 ? 64 : 32));
+  switch (tile_w) {
+    case 32:
+      return launch_decode_tma_w<T, 32>(p3, p4, p5, g, B, prm, ws, stream);
+    case 64:
+      return launch_decode_tma_w<T, 64>(p3, p4, p5, g, B, prm, ws, stream);
+    case 80:
+      for (int l = 0; l < 3; ++l)
+        if (g.lv[l].hw % 80 != 0) return 0;
+      return launch_decode_tma_w<T, 80>(p3, p4, p5, g, B, prm, ws, stream);
+    case 128:
+      return launch_decode_tma_w<T, 128>(p3, p4, p5, g, B, prm, ws, stream);
+    default:
+      return 0;
+  }
 }
 
 template <typename T>

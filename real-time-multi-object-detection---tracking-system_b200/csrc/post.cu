@@ -28,19 +28,40 @@ struct PostArgs {
   rtm::TrackArgs trk;
   rtm::ZoneArgs zone;
   int has_zones;
+  int work_bytes;  // shared memory the three stages alias; the prefetch areas follow it
 };
 
-template <int kBatch>
 __global__ void __launch_bounds__(kPostThreads, 1) post_kernel(const __grid_constant__ PostArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_keep[rtm::kMaxDetCap];
   __shared__ int s_scan[33];
+  // the inputs of the later stages that do not depend on this frame's detections are fetched
+  // first, behind the NMS: the head of the track table, the zone table and its polygons
+  rtm::TrackPrefetch* tpf = reinterpret_cast<rtm::TrackPrefetch*>(smem_raw + a.work_bytes);
+  rtm::ZonePrefetch* zpf = reinterpret_cast<rtm::ZonePrefetch*>(tpf + 1);
   const int b = blockIdx.x;
-  rtm::nms_stream<kPostThreads, kBatch>(a.ws, a.prm, a.iou_gate, a.out, b, smem_raw, s_keep, s_scan);  // ends with a barrier
-  rtm::track_stream<kPostThreads>(a.trk, b, smem_raw);
+  RTM_TL(0);
+  rtm::track_prefetch<kPostThreads>(a.trk.tin, b, tpf);
+  if (a.has_zones) rtm::zone_prefetch<kPostThreads>(a.zone, b, zpf);
+  rtm::nms_stream<kPostThreads>(a.ws, a.prm, a.iou_gate, a.out, b, smem_raw, s_keep, s_scan);  // ends with a barrier
+  RTM_TL(10);
+  rtm::track_stream<kPostThreads>(a.trk, b, smem_raw, tpf);
   __syncthreads();
-  if (a.has_zones) rtm::zone_stream<kPostThreads>(a.zone, b, smem_raw, s_scan);
+  RTM_TL(20);
+  if (a.has_zones) rtm::zone_stream<kPostThreads>(a.zone, b, smem_raw, s_scan, zpf);
+  RTM_TL(30);
 }
+
+#ifdef RTM_TIMELINE
+}  // namespace
+extern "C" int rtm_debug_timeline(void* device_buffer) {  // (B, 32) u64, or null to stop
+  unsigned long long* p = static_cast<unsigned long long*>(device_buffer);
+  RTM_CUDA(cudaMemcpyToSymbol(rtm::g_timeline, &p, sizeof(p)));
+  return RTM_OK;
+}
+namespace {
+#endif
+
 
 bool fuse_enabled() {
   static int v = -1;
@@ -61,10 +82,11 @@ extern "C" int rtm_post_backbone_step(const rtm_step_io* io, const rtm_nms_param
   cudaStream_t s = static_cast<cudaStream_t>(stream);
 
   const size_t track_smem = rtm::track_smem_bytes(io->det_stride, io->table_in->capacity);
-  const int max_vertices = 2048;
-  size_t smem = rtm::kNmsSmemBytes;
-  if (track_smem > smem) smem = track_smem;
-  if (io->zones && static_cast<size_t>(max_vertices) * 8 > smem) smem = static_cast<size_t>(max_vertices) * 8;
+  size_t work = rtm::kNmsSmemBytes;
+  if (track_smem > work) work = track_smem;
+  if (io->zones && rtm::zone_smem_bytes(io->event_stride) > work) work = rtm::zone_smem_bytes(io->event_stride);
+  work = (work + 127) / 128 * 128;
+  const size_t smem = work + sizeof(rtm::TrackPrefetch) + sizeof(rtm::ZonePrefetch);
 
   if (!fuse_enabled() || smem > 200 * 1024) {
     // unfused fallback: the three stand-alone entry points back to back
@@ -112,24 +134,16 @@ extern "C" int rtm_post_backbone_step(const rtm_step_io* io, const rtm_nms_param
   if (a.has_zones)
     a.zone = rtm::ZoneArgs{*io->zones, *io->table_out, io->src_row, *io->state_in, *io->state_out, io->now,
                            io->now_per_stream, io->frame_id, io->events, io->event_stride, io->event_count,
-                           io->status, max_vertices};
+                           io->status};
+  a.work_bytes = static_cast<int>(work);
   static size_t configured = 0;
   if (smem > configured) {
-    RTM_CUDA(cudaFuncSetAttribute(post_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    RTM_CUDA(cudaFuncSetAttribute(post_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    RTM_CUDA(cudaFuncSetAttribute(post_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    RTM_CUDA(cudaFuncSetAttribute(post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     configured = smem;
-  }
-  static int batch = -1;  // survivors settled per barrier round of the NMS scan (tuning knob)
-  if (batch < 0) {
-    const char* e = getenv("RTM_NMS_BATCH");
-    batch = e ? atoi(e) : 1;
   }
   {
     rtm::ProfileScope prof(RTM_K_POST, s);
-    if (batch == 4) post_kernel<4><<<B, kPostThreads, smem, s>>>(a);
-    else if (batch == 2) post_kernel<2><<<B, kPostThreads, smem, s>>>(a);
-    else post_kernel<1><<<B, kPostThreads, smem, s>>>(a);
+    post_kernel<<<B, kPostThreads, smem, s>>>(a);
   }
   RTM_LAUNCH_CHECK("post_kernel");
   return RTM_OK;

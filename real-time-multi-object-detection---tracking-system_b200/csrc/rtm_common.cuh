@@ -57,6 +57,22 @@ struct ProfileScope {
 };
 
 // ---- device helpers -------------------------------------------------------------------
+// Diagnosis builds (-DRTM_TIMELINE, tools/post_timeline.py): thread 0 of every CTA stamps
+// %globaltimer at the stage boundaries of the post kernel.  Compiled out of the product library.
+#ifdef RTM_TIMELINE
+static __device__ unsigned long long* g_timeline = nullptr;
+__device__ __forceinline__ void timeline_mark(int i) {
+  if (threadIdx.x == 0 && g_timeline) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_timeline[blockIdx.x * 32 + i] = t;
+  }
+}
+#define RTM_TL(i) ::rtm::timeline_mark(i)
+#else
+#define RTM_TL(i) ((void)0)
+#endif
+
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;
 

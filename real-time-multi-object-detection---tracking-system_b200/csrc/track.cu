@@ -5,9 +5,9 @@
 // unmatched high-score detections, ageing, pruning.  One CTA per stream.
 //
 //   * detections of the stream are staged in shared memory (box, area, high/low lists);
-//   * each thread owns track rows (row r = tid + k*blockDim) and walks the detection tile,
-//     keeping the first arg-max of its IoU row in registers - the T x N IoU matrix is never
-//     materialised (tracker.py:150-161 builds it; only its row arg-max is ever read);
+//   * a warp takes a track row at a time: its lanes split the detection tile, each keeping the
+//     first arg-max of its columns in registers, then combine by shuffle - the T x N IoU matrix
+//     is never materialised (tracker.py:150-161 builds it; only its row arg-max is ever read);
 //   * the row-order greedy loop of tracker.py:186-191 is evaluated in its order-free form:
 //     an admissible row (max IoU >= thresh) bids for its arg-max column with atomicMin(row);
 //     the smallest row wins, every other bidder stays unmatched (no second choice);
@@ -26,13 +26,16 @@ using rtm::track_smem_bytes;
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) track_step_kernel(const TrackArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  rtm::track_stream<THREADS>(a, blockIdx.x, smem_raw);
+  __shared__ rtm::TrackPrefetch pf;
+  rtm::track_prefetch<THREADS>(a.tin, blockIdx.x, &pf);
+  __syncthreads();
+  rtm::track_stream<THREADS>(a, blockIdx.x, smem_raw, &pf);
 }
 
 template <int THREADS>
 int launch_track(const TrackArgs& a, cudaStream_t stream) {
   const size_t smem = track_smem_bytes(a.det_stride, a.tin.capacity);
-  RTM_REQUIRE(smem <= 227 * 1024, "rtm_track_step: det_stride %d / capacity %d need %zu B of shared memory (> 227 KB)",
+  RTM_REQUIRE(smem + sizeof(rtm::TrackPrefetch) <= 226 * 1024, "rtm_track_step: det_stride %d / capacity %d need %zu B of shared memory (> 227 KB)",
               a.det_stride, a.tin.capacity, smem);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {

@@ -41,32 +41,84 @@ __device__ __forceinline__ float box_area(const float4 b) {
   return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
 }
 
+// The head of a stream's input table, staged in shared memory ahead of use: the fused kernel
+// issues these loads before the NMS stage so that their latency is off the critical path.
+constexpr int kTrackPrefRows = 512;
+struct TrackPrefetch {
+  float4 box[kTrackPrefRows];
+  int32_t track_id[kTrackPrefRows];
+  float confidence[kTrackPrefRows];
+  int32_t class_id[kTrackPrefRows];
+  int32_t age[kTrackPrefRows];
+  int32_t tsu[kTrackPrefRows];
+  int32_t count, next_id;
+};
+
+// All threads call it; the caller provides a block barrier before track_stream reads `pf`.
+template <int THREADS>
+__device__ __forceinline__ void track_prefetch(const rtm_track_table& tin, const int b, TrackPrefetch* pf) {
+  const int tid = threadIdx.x;
+  const size_t row0 = static_cast<size_t>(b) * tin.capacity;
+  const int T = min(tin.count[b], tin.capacity);
+  const float4* in_box = reinterpret_cast<const float4*>(tin.xyxy) + row0;
+  for (int t = tid; t < min(T, kTrackPrefRows); t += THREADS) {
+    pf->box[t] = in_box[t];
+    pf->track_id[t] = tin.track_id[row0 + t];
+    pf->confidence[t] = tin.confidence[row0 + t];
+    pf->class_id[t] = tin.class_id[row0 + t];
+    pf->age[t] = tin.age[row0 + t];
+    pf->tsu[t] = tin.time_since_update[row0 + t];
+  }
+  if (tid == 0) {
+    pf->count = T;
+    pf->next_id = tin.next_id[b];
+  }
+}
+
 // One association stage: rows = tracks with s_match[t] < 0, columns = s_list[0..m).
 // On return s_match[t] holds (det index | flag) for the rows that won their column.
+// A group of G lanes (G = 4 .. 32, a power of two chosen from the number of columns) takes a row at
+// a time: its lanes split the columns (each keeps the first arg-max of its ascending subsequence),
+// then combine - larger IoU wins, equal IoU resolves to the lower column, which is np.argmax over
+// the whole row (tracker.py:187).
 template <int THREADS>
-__device__ __forceinline__ void associate(const float4* __restrict__ trk_box, int T,
+__device__ __forceinline__ void associate(const TrackPrefetch* pf, const float4* __restrict__ g_box, int T,
                                           const float4* s_box, const float* s_area,
                                           const int* s_list, int m, int* s_win, int* s_match,
                                           float thresh, int flag) {
   const int tid = threadIdx.x;
   for (int j = tid; j < m; j += THREADS) s_win[j] = INT_MAX;
   __syncthreads();
-  for (int t = tid; t < T; t += THREADS) {
-    if (s_match[t] >= 0) continue;
-    const float4 a = trk_box[t];
-    const float area_a = box_area(a);
-    int d0 = s_list[0];
-    float best = pair_iou(a, area_a, s_box[d0], s_area[d0]);
-    int bj = 0;
-    for (int j = 1; j < m; ++j) {
-      const int d = s_list[j];
-      const float v = pair_iou(a, area_a, s_box[d], s_area[d]);
-      if (v > best) {  // strict: first arg-max, np.argmax semantics (tracker.py:187)
-        best = v;
-        bj = j;
+  int G = 4;
+  while (G < 32 && G < m) G <<= 1;
+  const int sub = tid & (G - 1), groups = THREADS / G;
+  // every lane of a warp runs the same number of rounds (shuffles need the whole warp)
+  for (int t0 = 0; t0 < T; t0 += groups) {
+    const int t = t0 + tid / G;
+    const bool open = t < T && s_match[t] < 0;
+    float best = -1.f;
+    int bj = INT_MAX;
+    if (open) {
+      const float4 a = t < kTrackPrefRows ? pf->box[t] : g_box[t];
+      const float area_a = box_area(a);
+      for (int j = sub; j < m; j += G) {
+        const int d = s_list[j];
+        const float v = pair_iou(a, area_a, s_box[d], s_area[d]);
+        if (v > best) {  // strict: first arg-max of the lane's columns
+          best = v;
+          bj = j;
+        }
       }
     }
-    if (best >= thresh) {  // tracker.py:188, float32 compare
+    for (int d = G >> 1; d > 0; d >>= 1) {
+      const float ov = __shfl_xor_sync(kFull, best, d);
+      const int oj = __shfl_xor_sync(kFull, bj, d);
+      if (ov > best || (ov == best && oj < bj)) {
+        best = ov;
+        bj = oj;
+      }
+    }
+    if (open && sub == 0 && best >= thresh) {  // tracker.py:188, float32 compare
       atomicMin(&s_win[bj], t);
       s_match[t] = -2 - bj;  // bidding for column bj
     }
@@ -85,7 +137,8 @@ __device__ __forceinline__ void associate(const float4* __restrict__ trk_box, in
 // One stream.  `smem_raw`: track_smem_bytes(det_stride, capacity) bytes of shared memory,
 // 16-byte aligned.  All THREADS threads of the block must call it (block-uniform control flow).
 template <int THREADS>
-__device__ __forceinline__ void track_stream(const TrackArgs& a, const int b, unsigned char* smem_raw) {
+__device__ __forceinline__ void track_stream(const TrackArgs& a, const int b, unsigned char* smem_raw,
+                                             const TrackPrefetch* pf) {
   const int tid = threadIdx.x;
   const int cap = a.tin.capacity, S = a.det_stride;
 
@@ -95,7 +148,9 @@ __device__ __forceinline__ void track_stream(const TrackArgs& a, const int b, un
   int* s_lo = s_hi + S;                                 // S  ... low det; later: birth list
   int* s_win = s_lo + S;                                // S  column winners of a stage
   int* s_born = s_win + S;                              // S  1 if high column j is unmatched
-  int* s_match = s_born + S;                            // cap
+  float* s_conf = reinterpret_cast<float*>(s_born + S);  // S
+  int* s_cls = reinterpret_cast<int*>(s_conf + S);       // S
+  int* s_match = s_cls + S;                             // cap
   int* s_scan = s_match + cap;                          // 33
 
   const size_t row0 = static_cast<size_t>(b) * cap;
@@ -104,8 +159,8 @@ __device__ __forceinline__ void track_stream(const TrackArgs& a, const int b, un
   float4* out_box = reinterpret_cast<float4*>(a.tout.xyxy) + row0;
   const float4* det_box = reinterpret_cast<const float4*>(a.det_xyxy) + det0;
 
-  const int T = min(a.tin.count[b], cap);
-  const int next_id = a.tin.next_id[b];
+  const int T = pf->count;
+  const int next_id = pf->next_id;
   int n = a.det_count[b];
   int st = 0;
   if (n > S) {
@@ -117,12 +172,13 @@ __device__ __forceinline__ void track_stream(const TrackArgs& a, const int b, un
   if (n == 0) {
     // tracker.py:70-73: age only, nothing is pruned on an empty frame
     for (int t = tid; t < T; t += THREADS) {
-      a.tout.track_id[row0 + t] = a.tin.track_id[row0 + t];
-      out_box[t] = in_box[t];
-      a.tout.confidence[row0 + t] = a.tin.confidence[row0 + t];
-      a.tout.class_id[row0 + t] = a.tin.class_id[row0 + t];
-      a.tout.age[row0 + t] = a.tin.age[row0 + t];
-      a.tout.time_since_update[row0 + t] = a.tin.time_since_update[row0 + t] + 1;
+      const bool p = t < kTrackPrefRows;
+      a.tout.track_id[row0 + t] = p ? pf->track_id[t] : a.tin.track_id[row0 + t];
+      out_box[t] = p ? pf->box[t] : in_box[t];
+      a.tout.confidence[row0 + t] = p ? pf->confidence[t] : a.tin.confidence[row0 + t];
+      a.tout.class_id[row0 + t] = p ? pf->class_id[t] : a.tin.class_id[row0 + t];
+      a.tout.age[row0 + t] = p ? pf->age[t] : a.tin.age[row0 + t];
+      a.tout.time_since_update[row0 + t] = (p ? pf->tsu[t] : a.tin.time_since_update[row0 + t]) + 1;
       if (a.src_row) a.src_row[row0 + t] = t;
     }
     if (tid == 0) {
@@ -143,7 +199,10 @@ __device__ __forceinline__ void track_stream(const TrackArgs& a, const int b, un
       const float4 bx = det_box[d];
       s_box[d] = bx;
       s_area[d] = box_area(bx);
-      hi = a.det_conf[det0 + d] >= a.track_thresh;
+      const float cf = a.det_conf[det0 + d];
+      s_conf[d] = cf;
+      s_cls[d] = a.det_cls[det0 + d];
+      hi = cf >= a.track_thresh;
       if (a.det_track_id) a.det_track_id[det0 + d] = 0;
       if (a.det_kind) a.det_kind[det0 + d] = RTM_DET_NONE;
     }
@@ -158,19 +217,21 @@ __device__ __forceinline__ void track_stream(const TrackArgs& a, const int b, un
   for (int t = tid; t < T; t += THREADS) s_match[t] = -1;
   for (int j = tid; j < H; j += THREADS) s_born[j] = 1;
   __syncthreads();
+  RTM_TL(11);
 
   // ---- stage 1: all retained tracks x high detections (tracker.py:91-104) ---------------
   if (T > 0 && H > 0) {
-    associate<THREADS>(in_box, T, s_box, s_area, s_hi, H, s_win, s_match, a.match_thresh, 0);
+    associate<THREADS>(pf, in_box, T, s_box, s_area, s_hi, H, s_win, s_match, a.match_thresh, 0);
     for (int j = tid; j < H; j += THREADS) s_born[j] = (s_win[j] == INT_MAX);
     __syncthreads();
   }
+  RTM_TL(12);
   // ---- stage 2: still-unmatched tracks x low detections, same threshold (tracker.py:109-123)
   if (T > 0 && L > 0) {
-    associate<THREADS>(in_box, T, s_box, s_area, s_lo, L, s_win, s_match, a.match_thresh,
-                       kStage2Flag);
+    associate<THREADS>(pf, in_box, T, s_box, s_area, s_lo, L, s_win, s_match, a.match_thresh, kStage2Flag);
   }
 
+  RTM_TL(13);
   // ---- births: unmatched high detections in ascending order (tracker.py:126-135) --------
   int NB = 0;
   int* s_birth = s_lo;  // low list is dead from here on
@@ -184,6 +245,7 @@ __device__ __forceinline__ void track_stream(const TrackArgs& a, const int b, un
   }
   __syncthreads();
 
+  RTM_TL(14);
   // ---- update, age, prune, compact (tracker.py:99-104, 138-139, 144-147) ---------------
   const bool birth_survives = 1 <= a.track_buffer;
   int kept = 0;
@@ -195,22 +257,23 @@ __device__ __forceinline__ void track_stream(const TrackArgs& a, const int b, un
     float conf = 0.f;
     float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
     if (v < T) {
-      id = a.tin.track_id[row0 + v];
+      const bool p = v < kTrackPrefRows;
+      id = p ? pf->track_id[v] : a.tin.track_id[row0 + v];
       const int m = s_match[v];
       if (m >= 0) {
         det = m & ~kStage2Flag;
         kind = (m & kStage2Flag) ? RTM_DET_STAGE2 : RTM_DET_STAGE1;
         box = s_box[det];
-        conf = a.det_conf[det0 + det];
-        cls = a.det_cls[det0 + det];
-        age = a.tin.age[row0 + v] + 1;
+        conf = s_conf[det];
+        cls = s_cls[det];
+        age = (p ? pf->age[v] : a.tin.age[row0 + v]) + 1;
         tsu = 1;
       } else {
-        box = in_box[v];
-        conf = a.tin.confidence[row0 + v];
-        cls = a.tin.class_id[row0 + v];
-        age = a.tin.age[row0 + v];
-        tsu = a.tin.time_since_update[row0 + v] + 1;
+        box = p ? pf->box[v] : in_box[v];
+        conf = p ? pf->confidence[v] : a.tin.confidence[row0 + v];
+        cls = p ? pf->class_id[v] : a.tin.class_id[row0 + v];
+        age = p ? pf->age[v] : a.tin.age[row0 + v];
+        tsu = (p ? pf->tsu[v] : a.tin.time_since_update[row0 + v]) + 1;
       }
       keep = tsu <= a.track_buffer;
     } else if (v < V) {
@@ -218,8 +281,8 @@ __device__ __forceinline__ void track_stream(const TrackArgs& a, const int b, un
       kind = RTM_DET_BIRTH;
       id = next_id + (v - T);
       box = s_box[det];
-      conf = a.det_conf[det0 + det];
-      cls = a.det_cls[det0 + det];
+      conf = s_conf[det];
+      cls = s_cls[det];
       age = 1;
       tsu = 1;
       keep = birth_survives;
@@ -253,7 +316,7 @@ __device__ __forceinline__ void track_stream(const TrackArgs& a, const int b, un
 }
 
 inline size_t track_smem_bytes(int det_stride, int capacity) {
-  return static_cast<size_t>(det_stride) * (16 + 4 + 4 * 4 + 4) + static_cast<size_t>(capacity) * 4 + 40 * 4;
+  return static_cast<size_t>(det_stride) * (16 + 4 + 4 * 4 + 4 + 4 + 4) + static_cast<size_t>(capacity) * 4 + 40 * 4;
 }
 
 }  // namespace rtm

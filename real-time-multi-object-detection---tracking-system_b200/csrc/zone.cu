@@ -9,12 +9,11 @@
 //   outside -> the dwell timer of that zone name is dropped (:122-125);
 //   tracks not passed to the call lose all dwell timers, cooldowns persist (:128-130).
 //
-// One CTA per stream.  The polygons of the stream are staged in shared memory; one thread
-// per track row walks the zones IN ORDER (zones sharing a name share a state column, so the
-// order inside a track matters and is kept).  The 32 lanes of a warp therefore test 32
-// tracks against the same polygon edge at a time (uniform shared-memory broadcasts); fired
-// (row, zone) pairs are ranked with warp ballots + a block scan so the event list comes out
-// in the reference's (track order, zone order) without atomics.
+// One CTA per stream.  The zone table and polygons of the stream are staged in shared memory; one
+// thread per (track row, state column) walks the column's zones IN ORDER (zones sharing a name
+// share a state column, so their order matters and is kept; different columns never interact).
+// Fired (row, zone) pairs are ranked with a block scan so the event list comes out in the
+// reference's (track order, zone order).
 #include "zone_body.cuh"
 
 namespace {
@@ -25,7 +24,10 @@ using rtm::ZoneArgs;
 __global__ void __launch_bounds__(kZoneThreads) zone_step_kernel(const ZoneArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_scan[33];
-  rtm::zone_stream<kZoneThreads>(a, blockIdx.x, smem_raw, s_scan);
+  __shared__ rtm::ZonePrefetch zp;
+  rtm::zone_prefetch<kZoneThreads>(a, blockIdx.x, &zp);
+  __syncthreads();
+  rtm::zone_stream<kZoneThreads>(a, blockIdx.x, smem_raw, s_scan, &zp);
 }
 
 }  // namespace
@@ -44,8 +46,14 @@ extern "C" int rtm_zone_step(const rtm_zone_set* zones, const rtm_track_table* t
   RTM_REQUIRE(!(src_row && state_in->first_seen == state_out->first_seen),
               "rtm_zone_step: in-place state needs src_row == NULL (identity)");
   ZoneArgs a{*zones, *tracks, src_row, *state_in, *state_out, now, now_per_stream, frame_id,
-             events, event_stride, event_count, status, 2048};
-  const size_t smem = static_cast<size_t>(a.max_vertices) * sizeof(int2);
+             events, event_stride, event_count, status};
+  const size_t smem = rtm::zone_smem_bytes(event_stride);
+  RTM_REQUIRE(smem + sizeof(rtm::ZonePrefetch) <= 226 * 1024, "rtm_zone_step: %zu B of shared memory needed", smem);
+  static size_t configured = 0;
+  if (smem > 24 * 1024 && smem > configured) {
+    RTM_CUDA(cudaFuncSetAttribute(zone_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured = smem;
+  }
   {
     rtm::ProfileScope prof(RTM_K_ZONE, static_cast<cudaStream_t>(stream));
     zone_step_kernel<<<tracks->num_streams, kZoneThreads, smem, static_cast<cudaStream_t>(stream)>>>(a);

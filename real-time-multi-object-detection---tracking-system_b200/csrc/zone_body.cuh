@@ -22,7 +22,6 @@ struct ZoneArgs {
   int32_t event_stride;
   int32_t* event_count;
   int32_t* status;
-  int32_t max_vertices;  // shared-memory polygon tile (vertices); larger streams read global
 };
 
 // OpenCV pointPolygonTest, measureDist = false, integer contour and point.
@@ -48,39 +47,71 @@ __device__ __forceinline__ int point_in_polygon(const int2* __restrict__ poly, i
   return (counter & 1) ? 1 : -1;
 }
 
-// One stream.  `smem_raw`: a.max_vertices * 8 bytes of shared memory; `s_scan`: 33 ints.
-// All THREADS threads of the block must call it.
+// The stream's zone table and polygons, staged in shared memory ahead of use (the fused kernel
+// issues these loads before the NMS stage).  kZonePrefVertices vertices are staged; streams with
+// more read their polygons from global memory.
+constexpr int kZonePrefVertices = 2048;
+struct ZonePrefetch {
+  int2 poly[kZonePrefVertices];
+  double dwell[kMaxZonesPerStream], cool[kMaxZonesPerStream];
+  int off[kMaxZonesPerStream + 1], col[kMaxZonesPerStream];
+  int nz, v0, staged;
+};
+
+// All threads call it; contains one block barrier; the caller provides another before zone_stream.
 template <int THREADS>
-__device__ __forceinline__ void zone_stream(const ZoneArgs& a, const int b, unsigned char* smem_raw, int* s_scan) {
+__device__ __forceinline__ void zone_prefetch(const ZoneArgs& a, const int b, ZonePrefetch* zp) {
   const int tid = threadIdx.x;
-  constexpr int kZoneThreads = THREADS;
-  // per-stream zone table staged once (one global round trip instead of several per zone test)
-  __shared__ int s_zoff[kMaxZonesPerStream + 1];
-  __shared__ int s_zcol[kMaxZonesPerStream];
-  __shared__ double s_zdwell[kMaxZonesPerStream];
-  __shared__ double s_zcool[kMaxZonesPerStream];
-  const int cap = a.trk.capacity, C = a.zs.num_columns;
   const int z0 = a.zs.zone_offsets[b], z1 = a.zs.zone_offsets[b + 1];
   const int nz = min(z1 - z0, kMaxZonesPerStream);
   if (tid == 0 && z1 - z0 > kMaxZonesPerStream && a.status) atomicOr(&a.status[b], RTM_STATUS_ZONE_LIMIT);
   const int v0 = a.zs.poly_offsets[z0];
-  if (tid <= nz) s_zoff[tid] = a.zs.poly_offsets[z0 + tid] - v0;
-  if (tid < nz) {
-    s_zcol[tid] = a.zs.column[z0 + tid];
-    s_zdwell[tid] = a.zs.dwell_sec[z0 + tid];
-    s_zcool[tid] = a.zs.cooldown_sec[z0 + tid];
+  for (int z = tid; z <= nz; z += THREADS) zp->off[z] = a.zs.poly_offsets[z0 + z] - v0;
+  for (int z = tid; z < nz; z += THREADS) {
+    zp->col[z] = a.zs.column[z0 + z];
+    zp->dwell[z] = a.zs.dwell_sec[z0 + z];
+    zp->cool[z] = a.zs.cooldown_sec[z0 + z];
   }
   __syncthreads();
-  const int nv = s_zoff[nz];
-
-  // stage the stream's polygons (falls back to global memory when they do not fit)
-  int2* s_poly = reinterpret_cast<int2*>(smem_raw);
+  const int nv = zp->off[nz];
+  const bool staged = nv <= kZonePrefVertices;
   const int2* g_poly = reinterpret_cast<const int2*>(a.zs.poly_xy);
-  const bool staged = nv <= a.max_vertices;
   if (staged)
-    for (int i = tid; i < nv; i += kZoneThreads) s_poly[i] = g_poly[v0 + i];
+    for (int i = tid; i < nv; i += THREADS) zp->poly[i] = g_poly[v0 + i];
+  if (tid == 0) {
+    zp->nz = nz;
+    zp->v0 = v0;
+    zp->staged = staged;
+  }
+}
+
+constexpr int kZoneStepEvents = 4096;  // events one stream can emit in one step (shared-memory staging)
+
+struct ZoneFired {  // a fired (row, zone) pair waiting to be ranked
+  int32_t row, zone;
+  double dwell;
+};
+
+// One stream.  `smem_raw`: zone_smem_bytes(event_stride) bytes of shared memory, `s_scan`: 33 ints.
+// All THREADS threads of the block must call it.
+//
+// Work is spread over (track row, state column) pairs: zones of a stream that share a name share
+// a column and are evaluated in order by the pair's thread (their order matters: the reference
+// keys its dicts by name); different columns never interact.  Fired (row, zone) pairs are staged
+// in shared memory and ranked, so events come out in the reference's (track order, zone order).
+template <int THREADS>
+__device__ __forceinline__ void zone_stream(const ZoneArgs& a, const int b, unsigned char* smem_raw, int* s_scan,
+                                            const ZonePrefetch* zp) {
+  const int tid = threadIdx.x;
+  const int cap = a.trk.capacity, C = a.zs.num_columns;
+  const int nz = zp->nz;
+  const int2* poly = zp->staged ? zp->poly : reinterpret_cast<const int2*>(a.zs.poly_xy) + zp->v0;
+  ZoneFired* s_ev = reinterpret_cast<ZoneFired*>(smem_raw);
+  const int ev_cap = min(a.event_stride, kZoneStepEvents);
+  int* s_nev = s_scan;  // one counter
+  if (tid == 0) *s_nev = 0;
   __syncthreads();
-  const int2* poly = staged ? s_poly : g_poly + v0;
+  RTM_TL(21);
 
   const double now = a.now_per_stream ? a.now_per_stream[b] : a.now;
   const double kNaN = __longlong_as_double(0x7ff8000000000000LL);
@@ -90,111 +121,78 @@ __device__ __forceinline__ void zone_stream(const ZoneArgs& a, const int b, unsi
   const float4* boxes = reinterpret_cast<const float4*>(a.trk.xyxy) + row0;
   rtm_zone_event* ev_out = a.events + static_cast<size_t>(b) * a.event_stride;
 
-  int ev_base = 0;
-  bool overflow = false;
-  for (int r0 = 0; r0 < T; r0 += kZoneThreads) {
-    const int r = r0 + tid;
-    const bool live = r < T;
-    unsigned long long fired = 0ull;
-    double dwell_of[kMaxZonesPerStream];
-    int cx = 0, cy = 0;
-    float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (live) {
-      const int src = a.src_row ? a.src_row[row0 + r] : r;
-      const bool active = a.trk.time_since_update[row0 + r] == 1;
-      if (active) box = boxes[r];
-      // the row's state, all columns loaded before anything is stored (independent loads in
-      // flight together); rows absent from this call lose their dwell timers, keep cooldowns
-      double fs[kMaxZonesPerStream], la[kMaxZonesPerStream];
-      for (int c = 0; c < C; ++c) {
-        fs[c] = kNaN;
-        la[c] = 0.0;
-        if (src >= 0) {
-          la[c] = a.sin.last_alert[st0 + static_cast<size_t>(c) * cap + src];
-          if (active) fs[c] = a.sin.first_seen[st0 + static_cast<size_t>(c) * cap + src];
-        }
-      }
-      if (active) {
-        cx = __float2int_rz(__fdiv_rn(__fadd_rn(box.x, box.z), 2.0f));
-        cy = __float2int_rz(__fdiv_rn(__fadd_rn(box.y, box.w), 2.0f));
-        for (int z = 0; z < nz; ++z) {
-          const int p0 = s_zoff[z], k = s_zoff[z + 1] - p0, c = s_zcol[z];
-          if (point_in_polygon(poly + p0, k, cx, cy) >= 0) {
-            if (fs[c] != fs[c]) fs[c] = now;  // not in the zone before: start the dwell timer
-            const double dwell = now - fs[c];
-            if (dwell >= s_zdwell[z] && now - la[c] >= s_zcool[z]) {
-              fired |= 1ull << z;
-              dwell_of[z] = dwell;
-              la[c] = now;
-            }
-          } else {
-            fs[c] = kNaN;
+  // ---- pass 1: (column, row) pairs, column-major so that state accesses coalesce over rows ----
+  const int pairs = T * C;
+  for (int q = tid; q < pairs; q += THREADS) {
+    const int c = q / T, r = q - c * T;
+    const int src = a.src_row ? a.src_row[row0 + r] : r;
+    const bool active = a.trk.time_since_update[row0 + r] == 1;
+    // rows absent from this call lose their dwell timers and keep their cooldowns (zone_engine.py:128-130)
+    double fs = kNaN, la = 0.0;
+    if (src >= 0) {
+      la = a.sin.last_alert[st0 + static_cast<size_t>(c) * cap + src];
+      if (active) fs = a.sin.first_seen[st0 + static_cast<size_t>(c) * cap + src];
+    }
+    if (active) {
+      const float4 box = boxes[r];
+      const int cx = __float2int_rz(__fdiv_rn(__fadd_rn(box.x, box.z), 2.0f));
+      const int cy = __float2int_rz(__fdiv_rn(__fadd_rn(box.y, box.w), 2.0f));
+      for (int z = 0; z < nz; ++z) {
+        if (zp->col[z] != c) continue;
+        const int p0 = zp->off[z], k = zp->off[z + 1] - p0;
+        if (point_in_polygon(poly + p0, k, cx, cy) >= 0) {
+          if (fs != fs) fs = now;  // not in the zone before: start the dwell timer
+          const double dwell = now - fs;
+          if (dwell >= zp->dwell[z] && now - la >= zp->cool[z]) {
+            la = now;
+            const int slot = atomicAdd(s_nev, 1);
+            if (slot < ev_cap) s_ev[slot] = ZoneFired{r, z, dwell};
           }
+        } else {
+          fs = kNaN;
         }
       }
-      for (int c = 0; c < C; ++c) {
-        a.sout.first_seen[st0 + static_cast<size_t>(c) * cap + r] = fs[c];
-        a.sout.last_alert[st0 + static_cast<size_t>(c) * cap + r] = la[c];
-      }
     }
-    // rank this round's events in (row, zone) order
-    int tot;
-    const int nfired = __popcll(fired);
-    // exclusive prefix of per-thread event counts: warp shuffle scan + block scan of warp sums
-    int incl = nfired;
-    const int lane = tid & 31, warp = tid >> 5;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int o = __shfl_up_sync(rtm::kFull, incl, d);
-      if (lane >= d) incl += o;
-    }
-    if (lane == 31) s_scan[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-      const int nwarp = kZoneThreads / 32;
-      const int v = lane < nwarp ? s_scan[lane] : 0;
-      int inc2 = v;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int o = __shfl_up_sync(rtm::kFull, inc2, d);
-        if (lane >= d) inc2 += o;
-      }
-      if (lane < nwarp) s_scan[lane] = inc2 - v;
-      if (lane == 31) s_scan[32] = inc2;
-    }
-    __syncthreads();
-    int pos = ev_base + s_scan[warp] + incl - nfired;
-    tot = s_scan[32];
-    __syncthreads();
-    while (fired) {
-      const int z = __ffsll(static_cast<long long>(fired)) - 1;
-      fired &= fired - 1;
-      if (pos < a.event_stride) {
-        rtm_zone_event e;
-        e.stream = b;
-        e.frame_id = a.frame_id;
-        e.track_id = a.trk.track_id[row0 + r];
-        e.zone = z;
-        e.class_id = a.trk.class_id[row0 + r];
-        e.cx = cx;
-        e.cy = cy;
-        e.row = r;
-        e.dwell = dwell_of[z];
-        e.now = now;
-        e.xyxy[0] = box.x;
-        e.xyxy[1] = box.y;
-        e.xyxy[2] = box.z;
-        e.xyxy[3] = box.w;
-        ev_out[pos] = e;
-      } else {
-        overflow = true;
-      }
-      ++pos;
-    }
-    ev_base += tot;
+    a.sout.first_seen[st0 + static_cast<size_t>(c) * cap + r] = fs;
+    a.sout.last_alert[st0 + static_cast<size_t>(c) * cap + r] = la;
   }
-  if (overflow && a.status) atomicOr(&a.status[b], RTM_STATUS_EVENT_OVERFLOW);
-  if (tid == 0) a.event_count[b] = min(ev_base, a.event_stride);
+  __syncthreads();
+
+  // ---- pass 2: rank the fired pairs by (row, zone) and write the event records ----
+  const int fired_total = *s_nev;
+  const int E = min(fired_total, ev_cap);
+  for (int e = tid; e < E; e += THREADS) {
+    const ZoneFired f = s_ev[e];
+    const int key = f.row * kMaxZonesPerStream + f.zone;
+    int pos = 0;
+    for (int j = 0; j < E; ++j) pos += (s_ev[j].row * kMaxZonesPerStream + s_ev[j].zone) < key;
+    const int r = f.row;
+    const float4 box = boxes[r];
+    rtm_zone_event ev;
+    ev.stream = b;
+    ev.frame_id = a.frame_id;
+    ev.track_id = a.trk.track_id[row0 + r];
+    ev.zone = f.zone;
+    ev.class_id = a.trk.class_id[row0 + r];
+    ev.cx = __float2int_rz(__fdiv_rn(__fadd_rn(box.x, box.z), 2.0f));
+    ev.cy = __float2int_rz(__fdiv_rn(__fadd_rn(box.y, box.w), 2.0f));
+    ev.row = r;
+    ev.dwell = f.dwell;
+    ev.now = now;
+    ev.xyxy[0] = box.x;
+    ev.xyxy[1] = box.y;
+    ev.xyxy[2] = box.z;
+    ev.xyxy[3] = box.w;
+    ev_out[pos] = ev;
+  }
+  if (tid == 0) {
+    a.event_count[b] = E;
+    if (fired_total > ev_cap && a.status) atomicOr(&a.status[b], RTM_STATUS_EVENT_OVERFLOW);
+  }
+}
+
+inline size_t zone_smem_bytes(int event_stride) {
+  return static_cast<size_t>(event_stride < kZoneStepEvents ? event_stride : kZoneStepEvents) * sizeof(ZoneFired);
 }
 
 }  // namespace rtm

@@ -33,7 +33,7 @@ def run_nms_pred(pkg, pred, conf=0.35, iou=0.45, classes=None, agnostic=False, m
     return {k: v.cpu().numpy() for k, v in out.items()}
 
 
-def random_pred(rng, B, A, nc=80, n_obj=25, dup=6, tie=False, bg=0.01):
+def random_pred(rng, B, A, nc=80, n_obj=25, dup=6, tie=False, bg=0.01, fixed_cls=None, size=(20, 200)):
     """(B, 4+nc, A) prediction tensor: low background, clusters of near-duplicate boxes."""
     pred = np.zeros((B, 4 + nc, A), np.float32)
     pred[:, 4:] = rng.uniform(0, bg, (B, nc, A))
@@ -41,8 +41,8 @@ def random_pred(rng, B, A, nc=80, n_obj=25, dup=6, tie=False, bg=0.01):
     pred[:, 2] = rng.uniform(4, 200, (B, A)); pred[:, 3] = rng.uniform(4, 200, (B, A))
     for b in range(B):
         for _ in range(n_obj):
-            c = int(rng.integers(0, nc))
-            base = np.array([rng.uniform(50, 590), rng.uniform(50, 590), rng.uniform(20, 200), rng.uniform(20, 200)])
+            c = int(rng.integers(0, nc)) if fixed_cls is None else int(rng.choice(fixed_cls))
+            base = np.array([rng.uniform(50, 590), rng.uniform(50, 590), rng.uniform(*size), rng.uniform(*size)])
             for a in rng.choice(A, dup, replace=False):
                 pred[b, :4, a] = base + rng.normal(0, 2.0, 4)
                 s = rng.uniform(0.2, 0.95)
@@ -69,7 +69,8 @@ def check_against_oracle(pkg, pred, **kw):
     return got
 
 
-@pytest.mark.parametrize("case", ["default", "ties", "agnostic", "noclassfilter", "maxdet", "iou08", "many"])
+@pytest.mark.parametrize("case", ["default", "ties", "agnostic", "noclassfilter", "maxdet", "iou08", "many", "crowd", "crowd_maxdet",
+                                  "two_big_classes", "all_classes", "huge_boxes", "huge_boxes_ties", "crowd_ties"])
 def test_nms_matches_torchvision_bit_exact(pkg, case):
     rng = np.random.default_rng(hash(case) % 2**32)
     kw = dict(conf=0.35, iou=0.45, classes=WANTED, agnostic=False, max_det=100)
@@ -88,6 +89,18 @@ def test_nms_matches_torchvision_bit_exact(pkg, case):
     if case == "many":                                                         # > 2048 candidates: global-memory path
         kw.update(classes=None, conf=0.05)
         pred_kw.update(B=2, n_obj=60, dup=50, bg=0.01)
+    if case in ("crowd", "crowd_maxdet", "crowd_ties"):                        # one class, segment far longer than a warp handles
+        kw.update(classes=None, max_det=300 if case == "crowd" else 9)
+        pred_kw.update(B=3, n_obj=150, dup=10, fixed_cls=[0], size=(15, 60), tie=case == "crowd_ties")
+    if case == "two_big_classes":                                              # long segments + short ones in one stream
+        kw.update(classes=None)
+        pred_kw.update(B=3, n_obj=120, dup=8, fixed_cls=[0] * 10 + [2] * 10 + [5, 7, 11, 40, 79], size=(15, 80))
+    if case == "all_classes":
+        kw.update(classes=None, max_det=100)
+        pred_kw.update(B=3, n_obj=300, dup=4, size=(15, 80))
+    if case in ("huge_boxes", "huge_boxes_ties"):                              # boxes wider than the class offset: classes interact
+        kw.update(classes=None, iou=0.3)
+        pred_kw.update(B=3, n_obj=60, dup=6, size=(3000, 12000), tie=case.endswith("ties"))
     pred = random_pred(rng, **pred_kw)
     if case == "many":
         pred[:, 4:, ::3] = np.maximum(pred[:, 4:, ::3], rng.uniform(0.0, 0.12, pred[:, 4:, ::3].shape).astype(np.float32) *
