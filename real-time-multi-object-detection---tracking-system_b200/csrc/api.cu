@@ -1,6 +1,7 @@
 // Library-level entry points: version, error string, device info, and the fused
 // post-backbone step (device-resident and host-fed variants).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -28,6 +29,16 @@ int sm_count() {
 }
 
 bool g_profile_on = false;
+
+// RTM_PDL=0 turns programmatic dependent launch of the step's two kernels off
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RTM_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 
 namespace {
 struct ProfileRecord {

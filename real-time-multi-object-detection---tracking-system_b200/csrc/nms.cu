@@ -37,6 +37,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <unordered_set>
+
 #include "nms_body.cuh"
 
 namespace {
@@ -68,7 +70,14 @@ int next_pow2(int v) {
   return p;
 }
 
-size_t workspace_layout(int B, int A, char* base, Workspace* ws) {
+// Workspace = header (one tile ticket counter per slot) + a ring of kCandSlots copies of the
+// candidate interchange arrays + one set of spill arrays.  Consecutive head scans take
+// consecutive slots, so the scan of step k+2 may already run while the post kernel of step k
+// still reads its own slot (programmatic dependent launch: see decode_tma_kernel and post.cu).
+constexpr int kCandSlots = 3;
+constexpr size_t kWorkspaceHeader = 128 * kCandSlots;
+
+size_t workspace_layout(int B, int A, char* base, Workspace* ws, int half = 0) {
   const int words = (A + 31) / 32, cap_p2 = next_pow2(A);
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -76,10 +85,14 @@ size_t workspace_layout(int B, int A, char* base, Workspace* ws) {
     off = align_up(off + bytes, 256);
     return o;
   };
-  const size_t o_mask = take(sizeof(uint32_t) * B * words);
-  const size_t o_box = take(sizeof(float4) * B * A);
-  const size_t o_score = take(sizeof(float) * B * A);
-  const size_t o_cls = take(sizeof(int32_t) * B * A);
+  const size_t o_head = take(kWorkspaceHeader);
+  size_t o_mask[kCandSlots], o_box[kCandSlots], o_score[kCandSlots], o_cls[kCandSlots];
+  for (int h = 0; h < kCandSlots; ++h) {
+    o_mask[h] = take(sizeof(uint32_t) * B * words);
+    o_box[h] = take(sizeof(float4) * B * A);
+    o_score[h] = take(sizeof(float) * B * A);
+    o_cls[h] = take(sizeof(int32_t) * B * A);
+  }
   const size_t o_keys = take(sizeof(uint64_t) * B * cap_p2);
   const size_t o_ubox = take(sizeof(float4) * B * A);
   const size_t o_sbox = take(sizeof(float4) * B * A);
@@ -87,10 +100,11 @@ size_t workspace_layout(int B, int A, char* base, Workspace* ws) {
   const size_t o_loc = take(sizeof(int32_t) * B * A);
   const size_t o_alive = take(sizeof(uint32_t) * B * 2 * words);
   if (ws) {
-    ws->mask = reinterpret_cast<uint32_t*>(base + o_mask);
-    ws->box = reinterpret_cast<float4*>(base + o_box);
-    ws->score = reinterpret_cast<float*>(base + o_score);
-    ws->cls = reinterpret_cast<int32_t*>(base + o_cls);
+    ws->tile_counter = reinterpret_cast<int*>(base + o_head) + 32 * half;  // 128 bytes apart
+    ws->mask = reinterpret_cast<uint32_t*>(base + o_mask[half]);
+    ws->box = reinterpret_cast<float4*>(base + o_box[half]);
+    ws->score = reinterpret_cast<float*>(base + o_score[half]);
+    ws->cls = reinterpret_cast<int32_t*>(base + o_cls[half]);
     ws->keys = reinterpret_cast<uint64_t*>(base + o_keys);
     ws->ubox = reinterpret_cast<float4*>(base + o_ubox);
     ws->sbox = reinterpret_cast<float4*>(base + o_sbox);
@@ -178,6 +192,7 @@ struct TmaGeom {
   int total_tiles;
   int stages;
   int tile_bytes;
+  int pdl_wait;  // experiment switch: wait for the prerequisite grid before exiting
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -292,12 +307,21 @@ __global__ void __launch_bounds__(tma_threads(kTileW)) decode_tma_kernel(const _
   extern __shared__ __align__(128) unsigned char tile_smem[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ int s_tile[kMaxStages];  // tile held by each stage, -1 = no more tiles
+  __shared__ int s_next[kMaxStages];  // ticket drawn for the stage's next fill (producer lane only)
   using P = Pair<T>;
   constexpr int kConsumerWarps = kTileW / kAnchorsPerWarp;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int stages = tg.stages;
   const int tps = tg.tiles_before[3], tb1 = tg.tiles_before[1], tb2 = tg.tiles_before[2];
+  // Programmatic dependent launch (no-ops for an ordinary launch).  The kernel behind this one on
+  // the stream - the step's post kernel - may be scheduled as soon as SMs free up; it waits for this
+  // grid to complete before it reads the candidate lists.  This grid in turn may have been started
+  // while the PREVIOUS step's post kernel was still running: nothing here reads what that kernel
+  // writes, but every thread waits for it before exiting, so that "this grid is complete" implies
+  // "the previous post kernel is complete" for the kernels ordered after this one.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -307,35 +331,63 @@ __global__ void __launch_bounds__(tma_threads(kTileW)) decode_tma_kernel(const _
   }
   __syncthreads();
 
-  const int first = blockIdx.x, step = gridDim.x;
-  const int my_tiles = first < tg.total_tiles ? (tg.total_tiles - first + step - 1) / step : 0;
-  // tile t = (stream b, tile r of the stream); advanced incrementally, no division per tile
-  const int step_b = step / tps, step_r = step - step_b * tps;
-  int b = first / tps, r = first - b * tps;
-
+  // Tiles are handed out by a ticket counter (tile t = stream t / tps, tile t % tps of that stream),
+  // so whichever CTAs are resident share the work evenly - also while the previous step's
+  // post kernel still occupies part of the GPU.
   if (warp == kConsumerWarps) {
     // ===== producer warp: one elected lane keeps the ring full =====
     if (lane == 0) {
-      int s = 0, fill = 0;
-      for (int it = 0; it < my_tiles; ++it) {
-        if (fill > 0) mbar_wait(&empty_bar[s], (fill - 1) & 1);
+      auto issue = [&](int s, int t) {
+        const int b = t / tps, r = t - b * tps;
         const int li = r >= tb2 ? 2 : (r >= tb1 ? 1 : 0);
         const int x = (r - (li == 2 ? tb2 : (li == 1 ? tb1 : 0))) * kTileW;
+        s_tile[s] = t;
         mbar_expect_tx(&full_bar[s], tg.tile_bytes);
         tma_load_tile(tile_smem + static_cast<size_t>(s) * tg.tile_bytes, li == 0 ? &map0 : (li == 1 ? &map1 : &map2),
                       &full_bar[s], x, b);
-        if (++s == stages) {
-          s = 0;
-          ++fill;
+      };
+      // first round of the ring: tiles blockIdx + k * grid, no ticket needed; the tickets of the
+      // second round are drawn meanwhile (all in flight together), later ones one ring cycle ahead
+      const int dyn0 = stages * static_cast<int>(gridDim.x);
+      bool done = false;
+      for (int k = 0; k < stages && !done; ++k) {
+        const int t = static_cast<int>(blockIdx.x) + k * static_cast<int>(gridDim.x);
+        if (t < tg.total_tiles) {
+          issue(k, t);
+        } else {
+          s_tile[k] = -1;
+          mbar_arrive(&full_bar[k]);
+          done = true;
         }
-        b += step_b;
-        r += step_r;
-        if (r >= tps) {
-          r -= tps;
-          ++b;
+      }
+      if (!done) {
+        int tk[kMaxStages];
+#pragma unroll
+        for (int k = 0; k < kMaxStages; ++k) tk[k] = k < stages ? atomicAdd(ws.tile_counter, 1) : 0;
+#pragma unroll
+        for (int k = 0; k < kMaxStages; ++k)
+          if (k < stages) s_next[k] = dyn0 + tk[k];
+        int s = 0, fill = 1, drawn = 0, drawn_for = -1;  // ticket in flight and the stage it is for
+        while (true) {
+          mbar_wait(&empty_bar[s], (fill - 1) & 1);
+          if (drawn_for >= 0) s_next[drawn_for] = dyn0 + drawn;  // arrived while the ring drained
+          const int t = s_next[s];
+          if (t >= tg.total_tiles) {
+            s_tile[s] = -1;
+            mbar_arrive(&full_bar[s]);
+            break;
+          }
+          issue(s, t);
+          drawn = atomicAdd(ws.tile_counter, 1);
+          drawn_for = s;
+          if (++s == stages) {
+            s = 0;
+            ++fill;
+          }
         }
       }
     }
+    if (tg.pdl_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
     return;
   }
 
@@ -351,14 +403,17 @@ __global__ void __launch_bounds__(tma_threads(kTileW)) decode_tma_kernel(const _
   uint8_t* mask_bytes = reinterpret_cast<uint8_t*>(ws.mask);
 
   int s = 0, phase = 0;
-  for (int it = 0; it < my_tiles; ++it) {
+  while (true) {
+    mbar_wait(&full_bar[s], phase);
+    const int t = *reinterpret_cast<volatile int*>(&s_tile[s]);
+    if (t < 0) break;
+    const int b = t / tps, r = t - b * tps;
     const int li = r >= tb2 ? 2 : (r >= tb1 ? 1 : 0);
     const int lv_w = li == 2 ? w2 : (li == 1 ? w1 : w0);
     const int lv_stride = li == 2 ? st2 : (li == 1 ? st1 : st0);
     const int lv_anchor0 = li == 2 ? a2 : (li == 1 ? a1 : 0);
     const int lv_hw = li == 2 ? hw2 : (li == 1 ? hw1 : hw0);
     const int pix = (r - (li == 2 ? tb2 : (li == 1 ? tb1 : 0))) * kTileW + col;
-    mbar_wait(&full_bar[s], phase);
     const T* tile = reinterpret_cast<const T*>(tile_smem + static_cast<size_t>(s) * tg.tile_bytes);
     const T* cls_col = tile + (kBoxCh + q) * kTileW + col;  // row of class q
 
@@ -434,13 +489,8 @@ __global__ void __launch_bounds__(tma_threads(kTileW)) decode_tma_kernel(const _
       s = 0;
       phase ^= 1;
     }
-    b += step_b;
-    r += step_r;
-    if (r >= tps) {
-      r -= tps;
-      ++b;
-    }
   }
+  if (tg.pdl_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------------------
@@ -549,6 +599,220 @@ __global__ void __launch_bounds__(THREADS) decode_ldg_kernel(const HeadPtrs<T> h
   }
   if (in_range)
     reinterpret_cast<uint8_t*>(ws.mask + static_cast<size_t>(b) * ws.words)[a0 >> 3] = static_cast<uint8_t>(mine);
+}
+
+// ---------------------------------------------------------------------------------------
+// decode_scan: streaming head scan without shared-memory staging.
+//
+// The class planes are the part of the head every anchor needs (80 of 144 channels); the 64 box
+// channels matter only where a class passes the confidence test.  So the class planes are streamed
+// once with 16-byte loads - four lanes share a group of 8 consecutive anchors, lane q taking
+// classes q, q+4, ... - all of a lane's loads in flight together, the running maximum kept packed;
+// and the box planes are read only for the 8-anchor groups that hold a candidate (their 16-byte
+// pieces: sector-granular).  On the bench workload that is 2/3 of the head bytes.
+// ---------------------------------------------------------------------------------------
+constexpr int kScanThreads = 128;
+
+template <typename T>
+struct Vec16;  // eight anchors of one channel row: one (16-bit) or two (float) 16-byte loads
+template <>
+struct Vec16<__nv_bfloat16> {
+  static constexpr int kLoads = 1;
+  using M = __nv_bfloat162;
+  static __device__ __forceinline__ M lowest() { return __float2bfloat162_rn(-INFINITY); }
+  static __device__ __forceinline__ void fold(M (&m)[4], const uint4 (&v)[1]) {
+    const M* p = reinterpret_cast<const M*>(&v[0]);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) m[e] = __hmax2(m[e], p[e]);
+  }
+  static __device__ __forceinline__ void unpack(const M (&m)[4], float (&f)[8]) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      f[2 * e] = __low2float(m[e]);
+      f[2 * e + 1] = __high2float(m[e]);
+    }
+  }
+};
+template <>
+struct Vec16<__half> {
+  static constexpr int kLoads = 1;
+  using M = __half2;
+  static __device__ __forceinline__ M lowest() { return __float2half2_rn(-INFINITY); }
+  static __device__ __forceinline__ void fold(M (&m)[4], const uint4 (&v)[1]) {
+    const M* p = reinterpret_cast<const M*>(&v[0]);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) m[e] = __hmax2(m[e], p[e]);
+  }
+  static __device__ __forceinline__ void unpack(const M (&m)[4], float (&f)[8]) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      f[2 * e] = __low2float(m[e]);
+      f[2 * e + 1] = __high2float(m[e]);
+    }
+  }
+};
+template <>
+struct Vec16<float> {
+  static constexpr int kLoads = 2;
+  using M = float2;
+  static __device__ __forceinline__ M lowest() { return make_float2(-INFINITY, -INFINITY); }
+  static __device__ __forceinline__ void fold(M (&m)[4], const uint4 (&v)[2]) {
+    const float* p = reinterpret_cast<const float*>(&v[0]);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) m[e] = make_float2(fmaxf(m[e].x, p[2 * e]), fmaxf(m[e].y, p[2 * e + 1]));
+  }
+  static __device__ __forceinline__ void unpack(const M (&m)[4], float (&f)[8]) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      f[2 * e] = m[e].x;
+      f[2 * e + 1] = m[e].y;
+    }
+  }
+};
+
+__device__ __forceinline__ uint4 ld_stream16(const void* p) {  // read-once data: do not keep it in L1
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
+template <typename T, int BATCH>
+__global__ void __launch_bounds__(kScanThreads) decode_scan_kernel(const HeadPtrs<T> heads, const HeadGeom g,
+                                                                   const rtm_nms_params prm, const float logit_gate,
+                                                                   const Workspace ws) {
+  using V = Vec16<T>;
+  constexpr int L = V::kLoads;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // see decode_tma_kernel
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31, gl = lane & 7, q = lane >> 3;
+  const int grp = (blockIdx.x * (kScanThreads / 32) + (threadIdx.x >> 5)) * 8 + gl;  // group of 8 consecutive anchors
+  const int a0 = grp * kVec;
+  const bool in_range = a0 < g.num_anchors;
+  int li = 0;
+  if (a0 >= g.lv[1].anchor0) li = 1;
+  if (a0 >= g.lv[2].anchor0) li = 2;
+  const Level lv = g.lv[li];
+  const int pix0 = a0 - lv.anchor0;
+  const int nc = g.num_classes;
+  const T* base = heads.p[li] + static_cast<size_t>(b) * (kBoxCh + nc) * lv.hw + pix0;
+  const size_t hw = lv.hw;
+
+  // ---- N1: this lane's classes (q, q + 4, ...) over its 8 anchors.  A batch of rows is loaded
+  //      (all loads in flight), folded into a packed maximum, and only if that maximum can pass the
+  //      confidence test is the batch looked at element by element - in registers - for the exact
+  //      float32 sigmoid and the FIRST arg-max (ascending classes, strict >) ----
+  float best[8];
+  int bcls[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    best[j] = -1.f;
+    bcls[j] = 0x7fffffff;
+  }
+  const int iters = (nc + 3) >> 2;
+  for (int i0 = 0; i0 < iters; i0 += BATCH) {
+    uint4 v[BATCH][L];
+#pragma unroll
+    for (int i = 0; i < BATCH; ++i) {
+      const int c = 4 * (i0 + i) + q;
+      const bool ok = in_range && c < nc;
+#pragma unroll
+      for (int l = 0; l < L; ++l)
+        v[i][l] = ok ? ld_stream16(reinterpret_cast<const char*>(base + (kBoxCh + c) * hw) + 16 * l) : make_uint4(0, 0, 0, 0);
+    }
+    typename V::M mx[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) mx[e] = V::lowest();
+#pragma unroll
+    for (int i = 0; i < BATCH; ++i)
+      if (in_range && 4 * (i0 + i) + q < nc) V::fold(mx, v[i]);
+    float am[8];
+    V::unpack(mx, am);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (am[j] > logit_gate) {  // rare
+#pragma unroll
+        for (int i = 0; i < BATCH; ++i) {
+          const int c = 4 * (i0 + i) + q;
+          const float x = to_float(reinterpret_cast<const T*>(&v[i][0])[j]);
+          if (c < nc && x > logit_gate) {
+            const float p = sigmoidf_rn(x);
+            if (p > best[j]) {
+              best[j] = p;
+              bcls[j] = c;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  unsigned cand = 0;  // candidate bits of the group's 8 anchors (identical in its four lanes)
+  unsigned pass = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (best[j] >= 0.f) pass |= 1u << j;
+  if (__any_sync(kFull, pass != 0)) {
+    // ---- combine the four class quarters of every anchor; class filter on the arg-max class ----
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (!__any_sync(kFull, (pass >> j) & 1u)) continue;
+      float sc = best[j];
+      int jc = bcls[j];
+#pragma unroll
+      for (int d = 8; d <= 16; d <<= 1) {
+        const float ob = __shfl_xor_sync(kFull, sc, d);
+        const int oc = __shfl_xor_sync(kFull, jc, d);
+        if (ob > sc || (ob == sc && oc < jc)) {
+          sc = ob;
+          jc = oc;
+        }
+      }
+      best[j] = sc;
+      bcls[j] = jc;
+      if (sc > prm.conf_thres && class_wanted(prm, jc & 255)) cand |= 1u << j;
+    }
+    // ---- D1 for the candidates: lane q decodes side q of its group's candidate anchors ----
+    if (__any_sync(kFull, cand != 0)) {
+      float dist[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dist[j] = 0.f;
+      if (cand) {
+        uint4 bx[kRegMax][L];
+#pragma unroll
+        for (int k = 0; k < kRegMax; ++k)
+#pragma unroll
+          for (int l = 0; l < L; ++l)
+            bx[k][l] = *reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(base + (q * kRegMax + k) * hw) + 16 * l);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if ((cand >> j) & 1u) {
+            float x[kRegMax];
+#pragma unroll
+            for (int k = 0; k < kRegMax; ++k) x[k] = to_float(reinterpret_cast<const T*>(&bx[k][0])[j]);
+            dist[j] = dfl_expectation(x);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (!__any_sync(kFull, (cand >> j) & 1u)) continue;
+        const float dl = dist[j];
+        const float dt = __shfl_down_sync(kFull, dist[j], 8), dr = __shfl_down_sync(kFull, dist[j], 16),
+                    db = __shfl_down_sync(kFull, dist[j], 24);
+        if (q == 0 && ((cand >> j) & 1u)) {
+          const int pix = pix0 + j;
+          const int y = pix / lv.w, x = pix - y * lv.w;
+          store_candidate(ws, b, a0 + j,
+                          dist_to_xyxy(dl, dt, dr, db, static_cast<float>(x) + 0.5f, static_cast<float>(y) + 0.5f,
+                                       static_cast<float>(lv.stride), nullptr),
+                          best[j], bcls[j]);
+        }
+      }
+    }
+  }
+  if (in_range && q == 0)
+    reinterpret_cast<uint8_t*>(ws.mask + static_cast<size_t>(b) * ws.words)[a0 >> 3] = static_cast<uint8_t>(cand);
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------------------
@@ -710,16 +974,6 @@ int env_int(const char* name, int dflt) {
   return e && *e ? atoi(e) : dflt;
 }
 
-// which head scan to use: RTM_DECODE_IMPL=tma (default when the shape allows) | ldg
-bool want_tma() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("RTM_DECODE_IMPL");
-    v = (e && strcmp(e, "ldg") == 0) ? 0 : 1;
-  }
-  return v == 1;
-}
-
 template <typename T>
 CUtensorMapDataType tensor_map_dtype();
 template <>
@@ -761,6 +1015,8 @@ int launch_decode_tma_w(const void* p3, const void* p4, const void* p5, const He
   for (int l = 0; l < 3; ++l) tg.tiles_before[l + 1] = tg.tiles_before[l] + (g.lv[l].hw + kTileW - 1) / kTileW;
   tg.total_tiles = tg.tiles_before[3] * B;
   tg.tile_bytes = ch * kTileW * static_cast<int>(sizeof(T));
+  static const int pdl_wait_env = env_int("RTM_PDL_WAIT", 0);
+  tg.pdl_wait = pdl_wait_env;
   if (tg.tile_bytes % 128 != 0) return 0;
   // ring depth and residency: as many tiles in flight per SM as fit (RTM_TMA_STAGES / RTM_TMA_CTAS override)
   static const int stages_env = env_int("RTM_TMA_STAGES", 0), ctas_env = env_int("RTM_TMA_CTAS", 0);
@@ -778,15 +1034,29 @@ int launch_decode_tma_w(const void* p3, const void* p4, const void* p5, const He
     RTM_CUDA(cudaFuncSetAttribute(decode_tma_kernel<T, false, kTileW>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     configured = smem;
   }
-  const int grid = min(tg.total_tiles, rtm::sm_count() * ctas_per_sm);
+  static const int grid_env = env_int("RTM_TMA_GRID", 0);  // experiments: any grid works with ticketed tiles
+  const int grid = min(tg.total_tiles, grid_env > 0 ? grid_env : rtm::sm_count() * ctas_per_sm);
   {
     rtm::ProfileScope prof(RTM_K_DECODE, stream);
+    // Programmatic dependent launch: when the kernel in front of this one on the stream is the
+    // previous step's post kernel (which releases its dependents as soon as it starts), the scan
+    // of this step runs beside it - it reads nothing that kernel writes (other workspace half).
+    // Off while per-kernel profiling is on, so that each kernel is timed alone.
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(tma_threads(kTileW));
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (rtm::pdl_enabled() && !rtm::g_profile_on) ? 1 : 0;
+    const float gate = logit_gate_for(prm.conf_thres);
     if (g.num_classes == 80)
-      decode_tma_kernel<T, true, kTileW><<<grid, tma_threads(kTileW), smem, stream>>>(maps[0], maps[1], maps[2], tg, prm,
-                                                                                     logit_gate_for(prm.conf_thres), ws);
+      RTM_CUDA(cudaLaunchKernelEx(&cfg, decode_tma_kernel<T, true, kTileW>, maps[0], maps[1], maps[2], tg, prm, gate, ws));
     else
-      decode_tma_kernel<T, false, kTileW><<<grid, tma_threads(kTileW), smem, stream>>>(maps[0], maps[1], maps[2], tg, prm,
-                                                                                      logit_gate_for(prm.conf_thres), ws);
+      RTM_CUDA(cudaLaunchKernelEx(&cfg, decode_tma_kernel<T, false, kTileW>, maps[0], maps[1], maps[2], tg, prm, gate, ws));
   }
   RTM_LAUNCH_CHECK("decode_tma_kernel");
   return 1;
@@ -795,7 +1065,6 @@ int launch_decode_tma_w(const void* p3, const void* p4, const void* p5, const He
 template <typename T>
 int try_launch_decode_tma(const void* p3, const void* p4, const void* p5, const HeadGeom& g, int B,
                           const rtm_nms_params& prm, const Workspace& ws, cudaStream_t stream) {
-  if (!want_tma()) return 0;
   // anchors per tile (RTM_TMA_TILEW = 32 | 64 | 80 | 128 overrides): 80 when it divides every level
   // (640 x 640: 6400 / 1600 / 400; measured fastest, profiles/), else 64 / 32 with a masked tail
   static const int tile_env = env_int("RTM_TMA_TILEW", 0);
@@ -818,22 +1087,59 @@ int try_launch_decode_tma(const void* p3, const void* p4, const void* p5, const 
   }
 }
 
+// which head scan to use: RTM_DECODE_IMPL = tma (default; falls back to scan where the tiling does
+// not apply) | scan | ldg
+int decode_impl() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RTM_DECODE_IMPL");
+    v = !e ? 1 : (strcmp(e, "scan") == 0 ? 0 : (strcmp(e, "ldg") == 0 ? 2 : 1));
+  }
+  return v;
+}
+
 template <typename T>
 int launch_decode(const void* p3, const void* p4, const void* p5, const HeadGeom& g, int B,
                   const rtm_nms_params& prm, const Workspace& ws, cudaStream_t stream) {
   HeadPtrs<T> heads{{static_cast<const T*>(p3), static_cast<const T*>(p4), static_cast<const T*>(p5)}};
   for (int l = 0; l < 3; ++l)
     RTM_REQUIRE((reinterpret_cast<uintptr_t>(heads.p[l]) & 15) == 0, "head level %d must be 16-byte aligned", l);
-  const int tma = try_launch_decode_tma<T>(p3, p4, p5, g, B, prm, ws, stream);
-  if (tma != 0) return tma < 0 ? tma : RTM_OK;
-  constexpr int THREADS = 128;
+  const int impl = decode_impl();
+  if (impl == 1) {
+    const int tma = try_launch_decode_tma<T>(p3, p4, p5, g, B, prm, ws, stream);
+    if (tma != 0) return tma < 0 ? tma : RTM_OK;
+  }
+  static const int dry = env_int("RTM_SCAN_DRY", 0);  // timing experiment: nothing passes the gate
+  const float gate = dry ? FLT_MAX : logit_gate_for(prm.conf_thres);
+  if (impl == 2) {
+    constexpr int THREADS = 128;
+    const int groups = g.num_anchors / kVec;
+    dim3 grid((groups + THREADS - 1) / THREADS, B);
+    {
+      rtm::ProfileScope prof(RTM_K_DECODE, stream);
+      decode_ldg_kernel<T, THREADS><<<grid, THREADS, 0, stream>>>(heads, g, prm, gate, ws);
+    }
+    RTM_LAUNCH_CHECK("decode_ldg_kernel");
+    return RTM_OK;
+  }
+  // streaming scan: a warp takes 8 groups of 8 anchors
   const int groups = g.num_anchors / kVec;
-  dim3 grid((groups + THREADS - 1) / THREADS, B);
+  const int warps = (groups + 7) / 8;
+  constexpr int BATCH = sizeof(T) == 2 ? 20 : 10;
   {
     rtm::ProfileScope prof(RTM_K_DECODE, stream);
-    decode_ldg_kernel<T, THREADS><<<grid, THREADS, 0, stream>>>(heads, g, prm, logit_gate_for(prm.conf_thres), ws);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((warps + kScanThreads / 32 - 1) / (kScanThreads / 32), B);
+    cfg.blockDim = dim3(kScanThreads);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (rtm::pdl_enabled() && !rtm::g_profile_on) ? 1 : 0;
+    RTM_CUDA(cudaLaunchKernelEx(&cfg, decode_scan_kernel<T, BATCH>, heads, g, prm, gate, ws));
   }
-  RTM_LAUNCH_CHECK("decode_ldg_kernel");
+  RTM_LAUNCH_CHECK("decode_scan_kernel");
   return RTM_OK;
 }
 
@@ -851,9 +1157,16 @@ int rtm::launch_decode_stage(const void* head_p3, const void* head_p4, const voi
   HeadGeom g;
   int rc = make_geom(img_h, img_w, params->num_classes, &g);
   if (rc) return rc;
-  const size_t need = workspace_layout(num_streams, g.num_anchors, static_cast<char*>(workspace), ws);
+  // consecutive scans take consecutive candidate-list slots of the workspace
+  static int half = 0;
+  half = (half + 1) % kCandSlots;
+  const size_t need = workspace_layout(num_streams, g.num_anchors, static_cast<char*>(workspace), ws, half);
   RTM_REQUIRE(workspace_bytes >= need, "workspace has %zu bytes, %zu needed", workspace_bytes, need);
   RTM_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
+  // the ticket counters must start at zero: clear the header the first time a workspace is seen
+  // (afterwards every NMS stage leaves the counter of the half it consumed at zero)
+  static std::unordered_set<const void*> seen;
+  if (seen.insert(workspace).second) RTM_CUDA(cudaMemsetAsync(workspace, 0, kWorkspaceHeader, s));
   switch (head_dtype) {
     case RTM_F32:
       return launch_decode<float>(head_p3, head_p4, head_p5, g, num_streams, *params, *ws, s);

@@ -36,6 +36,9 @@ struct Workspace {
   float* sarea;     // (B, A)
   int32_t* loc;     // (B, A)
   uint32_t* alive;  // (B, 2, words)
+  // tile ticket counter of the head scan that filled this candidate list; the NMS stage that
+  // consumes the list zeroes it again (the workspace starts zero-filled)
+  int* tile_counter;
   int num_anchors, words, cap_p2;
 };
 
@@ -672,6 +675,7 @@ __device__ __forceinline__ int nms_stream(const Workspace& ws, const rtm_nms_par
   const int tid = threadIdx.x;
   const int A = ws.num_anchors, W = ws.words;
   const uint32_t* mask = ws.mask + static_cast<size_t>(b) * W;
+  if (b == 0 && tid == 0) *ws.tile_counter = 0;  // the scan that filled this list is over: re-arm its tickets
   // ---- one pass over the stream's candidate mask: words stay in registers, ranks by block scan ----
   constexpr int kIters = (kMaxAnchors / 32 + THREADS - 1) / THREADS;
   uint32_t mw[kIters];

@@ -40,6 +40,7 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 int sm_count();  // cached multiProcessorCount of the current device
+bool pdl_enabled();  // programmatic dependent launch of the step kernels (RTM_PDL=0 turns it off)
 
 // Brackets a kernel launch with CUDA events while rtm_profile_enable(1) is in effect.
 extern bool g_profile_on;
