@@ -160,6 +160,44 @@ int rtm_track_step(const rtm_track_table* table_in, const rtm_track_table* table
                    int32_t* det_kind, int32_t* src_row, int32_t* status,
                    rtm_cuda_stream stream);
 
+/*
+ * Row K of the scope table: opt-in motion model.  THE REFERENCE HAS NO KALMAN FILTER (its
+ * tracker matches detections against the last matched box, tracker.py:93,112); with
+ * kalman_in / kalman_out == NULL rtm_track_step_ex is rtm_track_step.  With them, every track
+ * carries the constant-velocity filter of ByteTrack (ifzhang/ByteTrack, yolox/tracker/
+ * kalman_filter.py: state x, y, a = w/h, h + velocities; std_weight_position 1/20,
+ * std_weight_velocity 1/160) and the association of both stages runs against the box PREDICTED
+ * for this frame instead of the stored one.  Everything else (thresholds, greedy assignment,
+ * births, ageing, pruning, the stored xyxy = last matched detection) is unchanged.  With
+ * diagonal initial covariance and diagonal process / measurement noise the 8 x 8 filter is four
+ * independent (position, velocity) filters; that is how the state is stored:
+ *   mean (B, capacity, 8)   x, y, a, h, vx, vy, va, vh
+ *   cov  (B, capacity, 12)  per coordinate: var(pos), cov(pos, vel), var(vel)
+ * float32 throughout; a track that was not matched in the previous step has vh zeroed before the
+ * prediction (STrack.predict).
+ */
+typedef struct rtm_kalman_state {
+  float* mean;
+  float* cov;
+} rtm_kalman_state;
+
+enum { RTM_ASSIGN_GREEDY = 0, /* tracker.py:182-194, what the reference runs without `lap` */
+       RTM_ASSIGN_OPTIMAL = 1 /* tracker.py:168-181: lap.lapjv(1 - IoU, extend_cost, cost_limit) */ };
+
+typedef struct rtm_track_options {
+  float track_thresh, match_thresh;
+  int32_t track_buffer;
+  int32_t assignment;                /* RTM_ASSIGN_* */
+  const rtm_kalman_state* kalman_in; /* both NULL: no motion model (the reference) */
+  const rtm_kalman_state* kalman_out;
+} rtm_track_options;
+
+int rtm_track_step_ex(const rtm_track_table* table_in, const rtm_track_table* table_out,
+                      const float* det_xyxy, const float* det_conf, const int32_t* det_cls,
+                      const int32_t* det_count, int32_t det_stride, const rtm_track_options* options,
+                      int32_t* det_track_id, int32_t* det_kind, int32_t* src_row, int32_t* status,
+                      rtm_cuda_stream stream);
+
 /* ------------------------------------------------------------------------------------------
  * Z1..Z3  zone step.  Replaces ZoneEventEngine.process, src/events/zone_engine.py:82-132
  * (centroid, cv2.pointPolygonTest >= 0, dwell timer, cooldown ledger, stale purge).
@@ -252,6 +290,9 @@ typedef struct rtm_step_io {
   int32_t event_stride;
   int32_t* event_count;
   int32_t* status;
+  /* opt-in motion model of the tracker stage (see rtm_track_step_ex); NULL = the reference */
+  const rtm_kalman_state* kalman_in;
+  const rtm_kalman_state* kalman_out;
 } rtm_step_io;
 
 int rtm_post_backbone_step(const rtm_step_io* io, const rtm_nms_params* params,

@@ -93,7 +93,12 @@ class TrackerOracle:
     """One stream's tracker state + step, tracker.py:43-148."""
 
     def __init__(self, track_thresh: float = 0.5, track_buffer: int = 30,
-                 match_thresh: float = 0.8, assign=assign_rowloop) -> None:
+                 match_thresh: float = 0.8, assign=assign_rowloop, use_kalman: bool = False) -> None:
+        # use_kalman: opt-in motion model that the reference does NOT have (SURVEY.md section 0 F1);
+        # see oracle/kalman_ref.py.  Off = the reference's behaviour.
+        self.use_kalman = use_kalman
+        self.kf_mean = np.zeros((0, 8), np.float32)
+        self.kf_cov = np.zeros((0, 12), np.float32)
         self.track_thresh = track_thresh
         self.track_buffer = track_buffer
         self.match_thresh = match_thresh
@@ -136,9 +141,19 @@ class TrackerOracle:
         n = len(conf)
         det_tid = np.zeros(n, np.int32)
         det_kind = np.zeros(n, np.int32)
+        tsu_in = self.tsu.copy()
         if n == 0:                                         # tracker.py:70-73: age only, no prune
+            if self.use_kalman and len(self):
+                from . import kalman_ref
+                self.kf_mean, self.kf_cov = kalman_ref.predict32(self.kf_mean, self.kf_cov, tsu_in)
             self.tsu = self.tsu + 1
             return det_tid, det_kind
+        self._matched = []                                 # (rows, dets) of this step, for the filter update
+        if self.use_kalman:
+            from . import kalman_ref
+            seen = kalman_ref.predicted_box32(self.kf_mean, tsu_in)   # what the association sees
+        else:
+            seen = self.xyxy
 
         high = np.flatnonzero(conf >= np.float32(self.track_thresh))   # tracker.py:76
         low = np.flatnonzero(~(conf >= np.float32(self.track_thresh)))  # tracker.py:77
@@ -146,7 +161,7 @@ class TrackerOracle:
 
         # stage 1: every retained track x high-score detections (tracker.py:91-106)
         if t_n and len(high):
-            m_t, m_d, rest_t, rest_d = self.assign(pairwise_iou(self.xyxy, xyxy[high]),
+            m_t, m_d, rest_t, rest_d = self.assign(pairwise_iou(seen, xyxy[high]),
                                                    self.match_thresh)
             self._commit(np.asarray(m_t, np.int64), high[np.asarray(m_d, np.int64)],
                          xyxy, conf, cls, det_tid, det_kind, KIND_STAGE1)
@@ -157,10 +172,15 @@ class TrackerOracle:
         # stage 2: still-unmatched tracks x low-score detections, same threshold
         # (tracker.py:109-123); unmatched low detections are dropped
         if len(rest_t) and len(low):
-            m_t, m_d, _, _ = self.assign(pairwise_iou(self.xyxy[rest_t], xyxy[low]),
+            m_t, m_d, _, _ = self.assign(pairwise_iou(seen[rest_t], xyxy[low]),
                                          self.match_thresh)
             self._commit(rest_t[np.asarray(m_t, np.int64)], low[np.asarray(m_d, np.int64)],
                          xyxy, conf, cls, det_tid, det_kind, KIND_STAGE2)
+
+        if self.use_kalman and t_n:                        # predict every track, update the matched ones
+            self.kf_mean, self.kf_cov = kalman_ref.predict32(self.kf_mean, self.kf_cov, tsu_in)
+            for rows, dets in self._matched:
+                self.kf_mean[rows], self.kf_cov[rows] = kalman_ref.update32(self.kf_mean[rows], self.kf_cov[rows], xyxy[dets])
 
         # births from unmatched high detections, ascending index (tracker.py:126-135)
         born = high[np.asarray(rest_d, np.int64)]
@@ -176,11 +196,15 @@ class TrackerOracle:
             self.next_id += k
             det_tid[born] = ids
             det_kind[born] = KIND_BIRTH
+            if self.use_kalman:
+                m0, c0 = kalman_ref.initiate32(xyxy[born])
+                self.kf_mean = np.concatenate([self.kf_mean, m0])
+                self.kf_cov = np.concatenate([self.kf_cov, c0])
 
         # age everything, then drop tracks past the buffer (tracker.py:138-139, 144-147)
         self.tsu = self.tsu + 1
         live = self.tsu <= self.track_buffer
-        for name in ("track_id", "xyxy", "conf", "cls", "age", "tsu"):
+        for name in ("track_id", "xyxy", "conf", "cls", "age", "tsu") + (("kf_mean", "kf_cov") if self.use_kalman else ()):
             setattr(self, name, getattr(self, name)[live])
         return det_tid, det_kind
 
@@ -188,6 +212,7 @@ class TrackerOracle:
         """Matched rows take the detection's box / score / class (tracker.py:99-104)."""
         if len(rows) == 0:
             return
+        self._matched.append((rows, dets))
         self.xyxy[rows] = xyxy[dets]
         self.conf[rows] = conf[dets]
         self.cls[rows] = cls[dets]

@@ -49,6 +49,19 @@ class TrackTable(C.Structure):
                 ("time_since_update", C.c_void_p)]
 
 
+class KalmanState(C.Structure):
+    _fields_ = [("mean", C.c_void_p), ("cov", C.c_void_p)]
+
+
+ASSIGN_GREEDY, ASSIGN_OPTIMAL = 0, 1
+
+
+class TrackOptions(C.Structure):
+    _fields_ = [("track_thresh", C.c_float), ("match_thresh", C.c_float), ("track_buffer", C.c_int32),
+                ("assignment", C.c_int32), ("kalman_in", C.POINTER(KalmanState)),
+                ("kalman_out", C.POINTER(KalmanState))]
+
+
 class ZoneSet(C.Structure):
     _fields_ = [("num_streams", C.c_int32), ("num_columns", C.c_int32), ("zone_offsets", C.c_void_p),
                 ("poly_offsets", C.c_void_p), ("poly_xy", C.c_void_p), ("dwell_sec", C.c_void_p),
@@ -86,6 +99,7 @@ class StepIO(C.Structure):
         ("state_out", C.POINTER(ZoneState)), ("now", C.c_double), ("now_per_stream", C.c_void_p),
         ("frame_id", C.c_int32), ("events", C.c_void_p), ("event_stride", C.c_int32),
         ("event_count", C.c_void_p), ("status", C.c_void_p),
+        ("kalman_in", C.POINTER(KalmanState)), ("kalman_out", C.POINTER(KalmanState)),
     ]
 
 
@@ -118,6 +132,9 @@ SIGNATURES = {
     "rtm_track_step": (C.c_int, [C.POINTER(TrackTable), C.POINTER(TrackTable), C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_int32,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rtm_track_step_ex": (C.c_int, [C.POINTER(TrackTable), C.POINTER(TrackTable), C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(TrackOptions),
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rtm_zone_step": (C.c_int, [C.POINTER(ZoneSet), C.POINTER(TrackTable), C.c_void_p,
                                 C.POINTER(ZoneState), C.POINTER(ZoneState), C.c_double, C.c_void_p,
                                 C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),

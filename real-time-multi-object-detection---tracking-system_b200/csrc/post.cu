@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(kPostThreads, 1) post_kernel(const __grid_cons
   RTM_TL(0);
   if (a.has_zones) rtm::zone_prefetch<kPostThreads>(a.zone, b, zpf);
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  rtm::track_prefetch<kPostThreads>(a.trk.tin, b, tpf);
+  rtm::track_prefetch<kPostThreads>(a.trk, b, tpf);
   rtm::nms_stream<kPostThreads>(a.ws, a.prm, a.iou_gate, a.out, b, smem_raw, s_keep, s_scan);  // ends with a barrier
   RTM_TL(10);
   rtm::track_stream<kPostThreads>(a.trk, b, smem_raw, tpf);
@@ -102,9 +102,10 @@ extern "C" int rtm_post_backbone_step(const rtm_step_io* io, const rtm_nms_param
                             io->scale, io->det_xyxy, io->det_conf, io->det_cls, io->det_anchor, io->det_keep,
                             io->det_count, io->det_stride, io->status, io->workspace, io->workspace_bytes, stream);
     if (rc) return rc;
-    rc = rtm_track_step(io->table_in, io->table_out, io->det_xyxy, io->det_conf, io->det_cls, io->det_count,
-                        io->det_stride, io->track_thresh, io->match_thresh, io->track_buffer, io->det_track_id,
-                        io->det_kind, io->src_row, io->status, stream);
+    const rtm_track_options opt{io->track_thresh, io->match_thresh, io->track_buffer, RTM_ASSIGN_GREEDY, io->kalman_in,
+                                io->kalman_out};
+    rc = rtm_track_step_ex(io->table_in, io->table_out, io->det_xyxy, io->det_conf, io->det_cls, io->det_count,
+                           io->det_stride, &opt, io->det_track_id, io->det_kind, io->src_row, io->status, stream);
     if (rc) return rc;
     if (!io->zones) return RTM_OK;
     return rtm_zone_step(io->zones, io->table_out, io->src_row, io->state_in, io->state_out, io->now,
@@ -120,6 +121,10 @@ extern "C" int rtm_post_backbone_step(const rtm_step_io* io, const rtm_nms_param
   RTM_REQUIRE(io->table_in->num_streams == io->table_out->num_streams && io->table_in->capacity == io->table_out->capacity &&
                   io->table_in->capacity > 0 && B > 0, "rtm_post_backbone_step: bad track tables");
   RTM_REQUIRE(io->table_in->xyxy != io->table_out->xyxy, "rtm_post_backbone_step: table_in and table_out must be distinct");
+  RTM_REQUIRE((io->kalman_in == nullptr) == (io->kalman_out == nullptr), "rtm_post_backbone_step: kalman_in / kalman_out go together");
+  if (io->kalman_in)
+    RTM_REQUIRE(io->kalman_in->mean && io->kalman_in->cov && io->kalman_out->mean && io->kalman_out->cov &&
+                    io->kalman_in->mean != io->kalman_out->mean, "rtm_post_backbone_step: bad Kalman state arrays");
   if (io->zones) {
     RTM_REQUIRE(io->state_in && io->state_out && io->events && io->event_count && io->event_stride > 0 && io->src_row,
                 "rtm_post_backbone_step: incomplete zone arguments");
@@ -137,7 +142,14 @@ extern "C" int rtm_post_backbone_step(const rtm_step_io* io, const rtm_nms_param
                       io->det_stride, io->status};
   a.trk = rtm::TrackArgs{*io->table_in, *io->table_out, io->det_xyxy, io->det_conf, io->det_cls, io->det_count,
                          io->det_stride, io->track_thresh, io->match_thresh, io->track_buffer, io->det_track_id,
-                         io->det_kind, io->src_row, io->status};
+                         io->det_kind, io->src_row, io->status,
+                         nullptr, nullptr, nullptr, nullptr, RTM_ASSIGN_GREEDY};
+  if (io->kalman_in) {
+    a.trk.kf_mean_in = io->kalman_in->mean;
+    a.trk.kf_cov_in = io->kalman_in->cov;
+    a.trk.kf_mean_out = io->kalman_out->mean;
+    a.trk.kf_cov_out = io->kalman_out->cov;
+  }
   a.has_zones = io->zones != nullptr;
   if (a.has_zones)
     a.zone = rtm::ZoneArgs{*io->zones, *io->table_out, io->src_row, *io->state_in, *io->state_out, io->now,

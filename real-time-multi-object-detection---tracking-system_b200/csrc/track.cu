@@ -27,7 +27,7 @@ template <int THREADS>
 __global__ void __launch_bounds__(THREADS) track_step_kernel(const TrackArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ rtm::TrackPrefetch pf;
-  rtm::track_prefetch<THREADS>(a.tin, blockIdx.x, &pf);
+  rtm::track_prefetch<THREADS>(a, blockIdx.x, &pf);
   __syncthreads();
   rtm::track_stream<THREADS>(a, blockIdx.x, smem_raw, &pf);
 }
@@ -53,21 +53,44 @@ int launch_track(const TrackArgs& a, cudaStream_t stream) {
 
 }  // namespace
 
+extern "C" int rtm_track_step_ex(const rtm_track_table* table_in, const rtm_track_table* table_out,
+                                 const float* det_xyxy, const float* det_conf, const int32_t* det_cls,
+                                 const int32_t* det_count, int32_t det_stride, const rtm_track_options* opt,
+                                 int32_t* det_track_id, int32_t* det_kind, int32_t* src_row, int32_t* status,
+                                 rtm_cuda_stream stream) {
+  RTM_REQUIRE(table_in && table_out && opt, "rtm_track_step: null table / options");
+  RTM_REQUIRE(table_in->num_streams == table_out->num_streams && table_in->capacity == table_out->capacity,
+              "rtm_track_step: table_in / table_out shapes differ");
+  RTM_REQUIRE(table_in->num_streams > 0 && table_in->capacity > 0, "rtm_track_step: empty table");
+  RTM_REQUIRE(table_in->xyxy != table_out->xyxy, "rtm_track_step: table_in and table_out must be distinct");
+  RTM_REQUIRE(det_xyxy && det_conf && det_cls && det_count && det_stride > 0, "rtm_track_step: null detections");
+  RTM_REQUIRE((opt->kalman_in == nullptr) == (opt->kalman_out == nullptr), "rtm_track_step: kalman_in / kalman_out go together");
+  RTM_REQUIRE(opt->assignment == RTM_ASSIGN_GREEDY || opt->assignment == RTM_ASSIGN_OPTIMAL, "rtm_track_step: unknown assignment mode %d",
+              opt->assignment);
+  TrackArgs a{*table_in, *table_out, det_xyxy, det_conf, det_cls, det_count, det_stride,
+              opt->track_thresh, opt->match_thresh, opt->track_buffer, det_track_id, det_kind, src_row, status,
+              nullptr, nullptr, nullptr, nullptr, opt->assignment};
+  if (opt->kalman_in) {
+    RTM_REQUIRE(opt->kalman_in->mean && opt->kalman_in->cov && opt->kalman_out->mean && opt->kalman_out->cov,
+                "rtm_track_step: null Kalman state arrays");
+    RTM_REQUIRE(opt->kalman_in->mean != opt->kalman_out->mean, "rtm_track_step: Kalman state must ping-pong like the tables");
+    a.kf_mean_in = opt->kalman_in->mean;
+    a.kf_cov_in = opt->kalman_in->cov;
+    a.kf_mean_out = opt->kalman_out->mean;
+    a.kf_cov_out = opt->kalman_out->cov;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (det_stride > 256 || table_in->capacity > 2048) return launch_track<1024>(a, s);
+  return launch_track<256>(a, s);
+}
+
 extern "C" int rtm_track_step(const rtm_track_table* table_in, const rtm_track_table* table_out,
                               const float* det_xyxy, const float* det_conf, const int32_t* det_cls,
                               const int32_t* det_count, int32_t det_stride, float track_thresh,
                               float match_thresh, int32_t track_buffer, int32_t* det_track_id,
                               int32_t* det_kind, int32_t* src_row, int32_t* status,
                               rtm_cuda_stream stream) {
-  RTM_REQUIRE(table_in && table_out, "rtm_track_step: null table");
-  RTM_REQUIRE(table_in->num_streams == table_out->num_streams && table_in->capacity == table_out->capacity,
-              "rtm_track_step: table_in / table_out shapes differ");
-  RTM_REQUIRE(table_in->num_streams > 0 && table_in->capacity > 0, "rtm_track_step: empty table");
-  RTM_REQUIRE(table_in->xyxy != table_out->xyxy, "rtm_track_step: table_in and table_out must be distinct");
-  RTM_REQUIRE(det_xyxy && det_conf && det_cls && det_count && det_stride > 0, "rtm_track_step: null detections");
-  TrackArgs a{*table_in, *table_out, det_xyxy, det_conf, det_cls, det_count, det_stride,
-              track_thresh, match_thresh, track_buffer, det_track_id, det_kind, src_row, status};
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (det_stride > 256 || table_in->capacity > 2048) return launch_track<1024>(a, s);
-  return launch_track<256>(a, s);
+  const rtm_track_options opt{track_thresh, match_thresh, track_buffer, RTM_ASSIGN_GREEDY, nullptr, nullptr};
+  return rtm_track_step_ex(table_in, table_out, det_xyxy, det_conf, det_cls, det_count, det_stride, &opt, det_track_id,
+                           det_kind, src_row, status, stream);
 }

@@ -23,7 +23,116 @@ struct TrackArgs {
   int32_t* det_kind;
   int32_t* src_row;
   int32_t* status;
+  // opt-in motion model (row K): all four null = the reference's behaviour
+  const float* kf_mean_in;
+  const float* kf_cov_in;
+  float* kf_mean_out;
+  float* kf_cov_out;
+  int32_t assignment;  // RTM_ASSIGN_*
 };
+
+// ---- constant-velocity filter of ByteTrack (xyah), stored as four (position, velocity) filters.
+// The arithmetic below is restated operation for operation, in float32, by oracle/kalman_ref.py
+// (decoupled form) and checked there against the canonical 8 x 8 matrix form.
+struct KalmanTrack {
+  float m[8];   // x, y, a, h, vx, vy, va, vh
+  float c[12];  // per coordinate: var(pos), cov(pos, vel), var(vel)
+};
+
+__device__ __forceinline__ void kalman_load(KalmanTrack& k, const float* mean, const float* cov, size_t row) {
+  const float4* m4 = reinterpret_cast<const float4*>(mean + row * 8);
+  const float4* c4 = reinterpret_cast<const float4*>(cov + row * 12);
+  const float4 a = m4[0], b = m4[1], c0 = c4[0], c1 = c4[1], c2 = c4[2];
+  k.m[0] = a.x; k.m[1] = a.y; k.m[2] = a.z; k.m[3] = a.w;
+  k.m[4] = b.x; k.m[5] = b.y; k.m[6] = b.z; k.m[7] = b.w;
+  k.c[0] = c0.x; k.c[1] = c0.y; k.c[2] = c0.z; k.c[3] = c0.w;
+  k.c[4] = c1.x; k.c[5] = c1.y; k.c[6] = c1.z; k.c[7] = c1.w;
+  k.c[8] = c2.x; k.c[9] = c2.y; k.c[10] = c2.z; k.c[11] = c2.w;
+}
+
+__device__ __forceinline__ void kalman_store(const KalmanTrack& k, float* mean, float* cov, size_t row) {
+  float4* m4 = reinterpret_cast<float4*>(mean + row * 8);
+  float4* c4 = reinterpret_cast<float4*>(cov + row * 12);
+  m4[0] = make_float4(k.m[0], k.m[1], k.m[2], k.m[3]);
+  m4[1] = make_float4(k.m[4], k.m[5], k.m[6], k.m[7]);
+  c4[0] = make_float4(k.c[0], k.c[1], k.c[2], k.c[3]);
+  c4[1] = make_float4(k.c[4], k.c[5], k.c[6], k.c[7]);
+  c4[2] = make_float4(k.c[8], k.c[9], k.c[10], k.c[11]);
+}
+
+constexpr float kStdPos = 1.f / 20.f, kStdVel = 1.f / 160.f;
+
+__device__ __forceinline__ void box_to_xyah(const float4 b, float (&z)[4]) {
+  const float w = b.z - b.x, h = b.w - b.y;
+  z[0] = b.x + w * 0.5f;
+  z[1] = b.y + h * 0.5f;
+  z[2] = w / h;
+  z[3] = h;
+}
+
+__device__ __forceinline__ float4 xyah_to_box(const float cx, const float cy, const float a, const float h) {
+  const float w = a * h;
+  const float x1 = cx - w * 0.5f, y1 = cy - h * 0.5f;
+  return make_float4(x1, y1, x1 + w, y1 + h);
+}
+
+// KalmanFilter.initiate
+__device__ __forceinline__ void kalman_initiate(KalmanTrack& k, const float4 box) {
+  float z[4];
+  box_to_xyah(box, z);
+  const float sp = (2.f * kStdPos) * z[3], sv = (10.f * kStdVel) * z[3];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    k.m[i] = z[i];
+    k.m[4 + i] = 0.f;
+    k.c[3 * i] = i == 2 ? 1e-2f * 1e-2f : sp * sp;
+    k.c[3 * i + 1] = 0.f;
+    k.c[3 * i + 2] = i == 2 ? 1e-5f * 1e-5f : sv * sv;
+  }
+}
+
+// STrack.predict + KalmanFilter.predict: a track that missed the previous frame has vh zeroed
+__device__ __forceinline__ void kalman_predict(KalmanTrack& k, const int tsu_in) {
+  if (tsu_in > 1) k.m[7] = 0.f;
+  const float sp = kStdPos * k.m[3], sv = kStdVel * k.m[3];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float qp = i == 2 ? 1e-2f * 1e-2f : sp * sp, qv = i == 2 ? 1e-5f * 1e-5f : sv * sv;
+    const float pp = k.c[3 * i], pv = k.c[3 * i + 1], vv = k.c[3 * i + 2];
+    k.m[i] = k.m[i] + k.m[4 + i];
+    k.c[3 * i] = ((pp + pv) + (pv + vv)) + qp;
+    k.c[3 * i + 1] = pv + vv;
+    k.c[3 * i + 2] = vv + qv;
+  }
+}
+
+// KalmanFilter.project + update with the measurement box
+__device__ __forceinline__ void kalman_update(KalmanTrack& k, const float4 box) {
+  float z[4];
+  box_to_xyah(box, z);
+  const float sr = kStdPos * k.m[3];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float r = i == 2 ? 1e-1f * 1e-1f : sr * sr;
+    const float pp = k.c[3 * i], pv = k.c[3 * i + 1], vv = k.c[3 * i + 2];
+    const float s = pp + r;
+    const float kp = pp / s, kv = pv / s;
+    const float y = z[i] - k.m[i];
+    k.m[i] = k.m[i] + kp * y;
+    k.m[4 + i] = k.m[4 + i] + kv * y;
+    k.c[3 * i] = pp - kp * pp;
+    k.c[3 * i + 1] = pv - kp * pv;
+    k.c[3 * i + 2] = vv - kv * pv;
+  }
+}
+
+// box the association sees for a row: predicted from the filter state (mean only)
+__device__ __forceinline__ float4 kalman_predicted_box(const float* mean, size_t row, const int tsu_in) {
+  const float4* m4 = reinterpret_cast<const float4*>(mean + row * 8);
+  const float4 p = m4[0], v = m4[1];
+  const float vh = tsu_in > 1 ? 0.f : v.w;
+  return xyah_to_box(p.x + v.x, p.y + v.y, p.z + v.z, p.w + vh);
+}
 
 // tracker.py:153-161 on one pair.  Non-overlapping pairs give exactly +0 (finite boxes with
 // non-negative area), so the division is skipped for them.
@@ -45,7 +154,8 @@ __device__ __forceinline__ float box_area(const float4 b) {
 // issues these loads before the NMS stage so that their latency is off the critical path.
 constexpr int kTrackPrefRows = 512;
 struct TrackPrefetch {
-  float4 box[kTrackPrefRows];
+  float4 box[kTrackPrefRows];   // stored box (tracker.py:100: the last matched detection)
+  float4 abox[kTrackPrefRows];  // box the association sees: the stored one, or the filter's prediction
   int32_t track_id[kTrackPrefRows];
   float confidence[kTrackPrefRows];
   int32_t class_id[kTrackPrefRows];
@@ -56,18 +166,22 @@ struct TrackPrefetch {
 
 // All threads call it; the caller provides a block barrier before track_stream reads `pf`.
 template <int THREADS>
-__device__ __forceinline__ void track_prefetch(const rtm_track_table& tin, const int b, TrackPrefetch* pf) {
+__device__ __forceinline__ void track_prefetch(const TrackArgs& a, const int b, TrackPrefetch* pf) {
+  const rtm_track_table& tin = a.tin;
   const int tid = threadIdx.x;
   const size_t row0 = static_cast<size_t>(b) * tin.capacity;
   const int T = min(tin.count[b], tin.capacity);
   const float4* in_box = reinterpret_cast<const float4*>(tin.xyxy) + row0;
   for (int t = tid; t < min(T, kTrackPrefRows); t += THREADS) {
-    pf->box[t] = in_box[t];
+    const int tsu = tin.time_since_update[row0 + t];
+    const float4 stored = in_box[t];
+    pf->box[t] = stored;
+    pf->abox[t] = a.kf_mean_in ? kalman_predicted_box(a.kf_mean_in, row0 + t, tsu) : stored;
     pf->track_id[t] = tin.track_id[row0 + t];
     pf->confidence[t] = tin.confidence[row0 + t];
     pf->class_id[t] = tin.class_id[row0 + t];
     pf->age[t] = tin.age[row0 + t];
-    pf->tsu[t] = tin.time_since_update[row0 + t];
+    pf->tsu[t] = tsu;
   }
   if (tid == 0) {
     pf->count = T;
@@ -82,7 +196,8 @@ __device__ __forceinline__ void track_prefetch(const rtm_track_table& tin, const
 // then combine - larger IoU wins, equal IoU resolves to the lower column, which is np.argmax over
 // the whole row (tracker.py:187).
 template <int THREADS>
-__device__ __forceinline__ void associate(const TrackPrefetch* pf, const float4* __restrict__ g_box, int T,
+__device__ __forceinline__ void associate(const TrackPrefetch* pf, const float4* __restrict__ g_box,
+                                          const float* kf_mean, const int32_t* g_tsu, size_t row0, int T,
                                           const float4* s_box, const float* s_area,
                                           const int* s_list, int m, int* s_win, int* s_match,
                                           float thresh, int flag) {
@@ -99,7 +214,8 @@ __device__ __forceinline__ void associate(const TrackPrefetch* pf, const float4*
     float best = -1.f;
     int bj = INT_MAX;
     if (open) {
-      const float4 a = t < kTrackPrefRows ? pf->box[t] : g_box[t];
+      const float4 a = t < kTrackPrefRows ? pf->abox[t]
+                                          : (kf_mean ? kalman_predicted_box(kf_mean, row0 + t, g_tsu[row0 + t]) : g_box[t]);
       const float area_a = box_area(a);
       for (int j = sub; j < m; j += G) {
         const int d = s_list[j];
@@ -178,8 +294,15 @@ __device__ __forceinline__ void track_stream(const TrackArgs& a, const int b, un
       a.tout.confidence[row0 + t] = p ? pf->confidence[t] : a.tin.confidence[row0 + t];
       a.tout.class_id[row0 + t] = p ? pf->class_id[t] : a.tin.class_id[row0 + t];
       a.tout.age[row0 + t] = p ? pf->age[t] : a.tin.age[row0 + t];
-      a.tout.time_since_update[row0 + t] = (p ? pf->tsu[t] : a.tin.time_since_update[row0 + t]) + 1;
+      const int tsu_in = p ? pf->tsu[t] : a.tin.time_since_update[row0 + t];
+      a.tout.time_since_update[row0 + t] = tsu_in + 1;
       if (a.src_row) a.src_row[row0 + t] = t;
+      if (a.kf_mean_in) {  // the filter still advances one frame
+        KalmanTrack k;
+        kalman_load(k, a.kf_mean_in, a.kf_cov_in, row0 + t);
+        kalman_predict(k, tsu_in);
+        kalman_store(k, a.kf_mean_out, a.kf_cov_out, row0 + t);
+      }
     }
     if (tid == 0) {
       a.tout.count[b] = T;
@@ -221,14 +344,16 @@ __device__ __forceinline__ void track_stream(const TrackArgs& a, const int b, un
 
   // ---- stage 1: all retained tracks x high detections (tracker.py:91-104) ---------------
   if (T > 0 && H > 0) {
-    associate<THREADS>(pf, in_box, T, s_box, s_area, s_hi, H, s_win, s_match, a.match_thresh, 0);
+    associate<THREADS>(pf, in_box, a.kf_mean_in, a.tin.time_since_update, row0, T, s_box, s_area, s_hi, H, s_win, s_match,
+                       a.match_thresh, 0);
     for (int j = tid; j < H; j += THREADS) s_born[j] = (s_win[j] == INT_MAX);
     __syncthreads();
   }
   RTM_TL(12);
   // ---- stage 2: still-unmatched tracks x low detections, same threshold (tracker.py:109-123)
   if (T > 0 && L > 0) {
-    associate<THREADS>(pf, in_box, T, s_box, s_area, s_lo, L, s_win, s_match, a.match_thresh, kStage2Flag);
+    associate<THREADS>(pf, in_box, a.kf_mean_in, a.tin.time_since_update, row0, T, s_box, s_area, s_lo, L, s_win, s_match,
+                       a.match_thresh, kStage2Flag);
   }
 
   RTM_TL(13);
@@ -256,8 +381,13 @@ __device__ __forceinline__ void track_stream(const TrackArgs& a, const int b, un
     int id = 0, cls = 0, age = 0, tsu = 0, det = -1, kind = RTM_DET_NONE;
     float conf = 0.f;
     float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+    KalmanTrack kf;
     if (v < T) {
       const bool p = v < kTrackPrefRows;
+      if (a.kf_mean_in) {
+        kalman_load(kf, a.kf_mean_in, a.kf_cov_in, row0 + v);
+        kalman_predict(kf, p ? pf->tsu[v] : a.tin.time_since_update[row0 + v]);
+      }
       id = p ? pf->track_id[v] : a.tin.track_id[row0 + v];
       const int m = s_match[v];
       if (m >= 0) {
@@ -268,6 +398,7 @@ __device__ __forceinline__ void track_stream(const TrackArgs& a, const int b, un
         cls = s_cls[det];
         age = (p ? pf->age[v] : a.tin.age[row0 + v]) + 1;
         tsu = 1;
+        if (a.kf_mean_in) kalman_update(kf, box);
       } else {
         box = p ? pf->box[v] : in_box[v];
         conf = p ? pf->confidence[v] : a.tin.confidence[row0 + v];
@@ -286,6 +417,7 @@ __device__ __forceinline__ void track_stream(const TrackArgs& a, const int b, un
       age = 1;
       tsu = 1;
       keep = birth_survives;
+      if (a.kf_mean_in) kalman_initiate(kf, box);
     }
     if (det >= 0) {
       if (a.det_track_id) a.det_track_id[det0 + det] = id;
@@ -301,6 +433,7 @@ __device__ __forceinline__ void track_stream(const TrackArgs& a, const int b, un
       a.tout.age[row0 + p] = age;
       a.tout.time_since_update[row0 + p] = tsu;
       if (a.src_row) a.src_row[row0 + p] = v < T ? v : -1;
+      if (a.kf_mean_in) kalman_store(kf, a.kf_mean_out, a.kf_cov_out, row0 + p);
     }
     kept += tot;
   }

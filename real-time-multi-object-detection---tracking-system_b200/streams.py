@@ -76,7 +76,7 @@ class DeviceTrackTable:
 
     FIELDS = ("track_id", "xyxy", "confidence", "class_id", "age", "time_since_update")
 
-    def __init__(self, num_streams: int, capacity: int, device) -> None:
+    def __init__(self, num_streams: int, capacity: int, device, kalman: bool = False) -> None:
         import torch
         self.num_streams, self.capacity, self.device = int(num_streams), int(capacity), device
         i32 = dict(dtype=torch.int32, device=device)
@@ -94,12 +94,21 @@ class DeviceTrackTable:
                                       self.track_id.data_ptr(), self.xyxy.data_ptr(),
                                       self.confidence.data_ptr(), self.class_id.data_ptr(),
                                       self.age.data_ptr(), self.time_since_update.data_ptr())
+        # opt-in motion model (rtm_kalman_state): four (position, velocity) filters per track
+        self.kf_mean = self.kf_cov = self.kalman = None
+        if kalman:
+            self.kf_mean = torch.zeros(B, cap, 8, **f32)
+            self.kf_cov = torch.zeros(B, cap, 12, **f32)
+            self.kalman = _lib.KalmanState(self.kf_mean.data_ptr(), self.kf_cov.data_ptr())
 
     def to_host(self):
         """dict of host numpy arrays (synchronises)."""
         out = {k: getattr(self, k).cpu().numpy() for k in self.FIELDS}
         out["count"] = self.count.cpu().numpy()
         out["next_id"] = self.next_id.cpu().numpy()
+        if self.kalman is not None:
+            out["kf_mean"] = self.kf_mean.cpu().numpy()
+            out["kf_cov"] = self.kf_cov.cpu().numpy()
         return out
 
     def load(self, stream: int, rows: dict, next_id: int) -> None:
@@ -222,7 +231,7 @@ class StreamBatch:
                  iou: float = 0.45, classes: Optional[Sequence[int]] = None, max_det: int = 100,
                  agnostic_nms: bool = False, track_thresh: float = 0.5, track_buffer: int = 30,
                  match_thresh: float = 0.8, max_tracks: int = 1024, max_events: Optional[int] = None,
-                 det_slots: Optional[int] = None, device="cuda:0") -> None:
+                 det_slots: Optional[int] = None, device="cuda:0", use_kalman: bool = False) -> None:
         import torch
         self.lib = _lib.lib()
         self.device = torch.device(device)
@@ -249,7 +258,9 @@ class StreamBatch:
             self.scale = torch.tensor([[gain, px, py, self.src_hw[1], self.src_hw[0]]] * B, **f32)
             ws_bytes = self.lib.rtm_nms_workspace_bytes(B, self.num_anchors)
             self.workspace = torch.zeros(ws_bytes, dtype=torch.uint8, device=self.device)
-            self.tables = [DeviceTrackTable(B, max_tracks, self.device) for _ in range(2)]
+            # use_kalman: opt-in motion model the reference does not have (rtm_track_step_ex); off = reference
+            self.use_kalman = bool(use_kalman)
+            self.tables = [DeviceTrackTable(B, max_tracks, self.device, kalman=self.use_kalman) for _ in range(2)]
             self.src_row = torch.zeros(B, max_tracks, **i32)
             self.zones = None
             if zones_per_stream is not None:
@@ -295,6 +306,9 @@ class StreamBatch:
             io.event_count = self.zones.event_count.data_ptr()
         io.now, io.frame_id = float(now), int(frame_id)
         io.status = self.status.data_ptr()
+        if self.use_kalman:
+            io.kalman_in = C.pointer(self.tables[self.cur].kalman)
+            io.kalman_out = C.pointer(self.tables[self.cur ^ 1].kalman)
         return io
 
     def _advance(self) -> None:
@@ -326,10 +340,13 @@ class StreamBatch:
             st = _lib.cuda_stream()
             tin, tout = self.tables[self.cur], self.tables[self.cur ^ 1]
             want_assign = S == self.det_stride
-            _lib.check(self.lib.rtm_track_step(
+            opt = _lib.TrackOptions(self.track_thresh, self.match_thresh, self.track_buffer, _lib.ASSIGN_GREEDY,
+                                    C.pointer(tin.kalman) if self.use_kalman else None,
+                                    C.pointer(tout.kalman) if self.use_kalman else None)
+            _lib.check(self.lib.rtm_track_step_ex(
                 C.byref(tin.struct), C.byref(tout.struct), det_xyxy.data_ptr(), det_conf.data_ptr(),
-                det_cls.data_ptr(), det_count.data_ptr(), S, self.track_thresh, self.match_thresh,
-                self.track_buffer, self.det_track_id.data_ptr() if want_assign else None,
+                det_cls.data_ptr(), det_count.data_ptr(), S, C.byref(opt),
+                self.det_track_id.data_ptr() if want_assign else None,
                 self.det_kind.data_ptr() if want_assign else None, self.src_row.data_ptr(),
                 self.status.data_ptr(), st))
             if self.zones is not None:

@@ -29,15 +29,15 @@ def moving_heads(pkg, B, F, seed, n_obj=12):
     return frames
 
 
-@pytest.mark.parametrize("dtype", ["f32", "bf16"])
-def test_fused_step_matches_oracle_chain(pkg, dtype):
+@pytest.mark.parametrize("dtype,kalman", [("f32", False), ("bf16", False), ("bf16", True)])
+def test_fused_step_matches_oracle_chain(pkg, dtype, kalman):
     import torch
     B, F = 4, 25
     tdt = {"f32": torch.float32, "bf16": torch.bfloat16}[dtype]
     zones = [pkg.synth.make_zones(seed=b, num_zones=4, width=1920, height=1080, dwell_time_sec=0.2, cooldown_sec=0.4)
              for b in range(B)]
-    sb = pkg.StreamBatch(B, zones, src_hw=(1080, 1920), classes=WANTED, max_tracks=256)
-    trk = [tracker_ref.TrackerOracle() for _ in range(B)]
+    sb = pkg.StreamBatch(B, zones, src_hw=(1080, 1920), classes=WANTED, max_tracks=256, use_kalman=kalman)
+    trk = [tracker_ref.TrackerOracle(use_kalman=kalman) for _ in range(B)]
     zon = [zone_ref.ZoneOracle(z) for z in zones]
     n_events = 0
     for f, heads in enumerate(moving_heads(pkg, B, F, seed=4)):
@@ -70,6 +70,10 @@ def test_fused_step_matches_oracle_chain(pkg, dtype):
             assert [(e.track_id, e.zone_name, e.centroid, e.dwell_time_sec, e.bbox_xyxy, e.frame_id) for e in got_ev[b]] == \
                    [(e.track_id, e.zone_name, e.centroid, e.dwell_time_sec, e.bbox_xyxy, e.frame_id) for e in exp_ev]
             n_events += len(exp_ev)
+            if kalman:
+                host = sb.table.to_host()
+                np.testing.assert_array_equal(host["kf_mean"][b, :len(o)], o.kf_mean)
+                np.testing.assert_array_equal(host["kf_cov"][b, :len(o)], o.kf_cov)
     assert n_events > 0
 
 

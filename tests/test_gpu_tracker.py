@@ -121,3 +121,39 @@ def test_track_table_overflow_is_reported_not_truncated(pkg):
     xy = np.arange(12, dtype=np.float32)[:, None] * 100 + np.array([0, 0, 10, 10], np.float32)
     with pytest.raises(pkg.RtmError, match="capacity"):
         trk.update(types.SimpleNamespace(xyxy=xy, confidence=np.full(12, 0.9, np.float32), class_id=np.zeros(12, np.int32)))
+
+
+@pytest.mark.parametrize("clip", ["slow", "gaps", "crowd"])
+def test_motion_model_matches_oracle(pkg, clip):
+    """Opt-in Kalman mode (row K; the reference has none): ids, assignments and stored state
+    bit-exact against the oracle, filter means / covariances within the stated 1e-4 relative
+    (in fact bit for bit: both sides spell out the same float32 operations)."""
+    kw = dict(slow=dict(num_objects=20, w_range=(60, 160), h_range=(120, 320), vmax=2.0, dropout=0.05),
+              gaps=dict(num_objects=12, w_range=(80, 160), h_range=(120, 300), vmax=3.0, dropout=0.35),
+              crowd=dict(num_objects=200, w_range=(20, 60), h_range=(50, 150), vmax=1.5, dropout=0.05))[clip]
+    slots = 256 if clip == "crowd" else 64
+    sb = run_batch_against_oracle(pkg, B=5, F=50, slots=slots, clip_kw=kw, max_tracks=1024, seed=21,
+                                  track_kw=dict(use_kalman=True))
+    # replay the oracle once more to compare the filter state itself
+    xyxy, conf, cls, count = pkg.synth.scripted_batch(5, 50, slots, seed=21, **kw)
+    host = sb.table.to_host()
+    matched_more_than_once = 0
+    for b in range(5):
+        o = tracker_ref.TrackerOracle(use_kalman=True)
+        for f in range(50):
+            o.step(xyxy[f, b, :count[f, b]], conf[f, b, :count[f, b]], cls[f, b, :count[f, b]])
+        n = len(o)
+        assert host["count"][b] == n
+        np.testing.assert_allclose(host["kf_mean"][b, :n], o.kf_mean, rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(host["kf_cov"][b, :n], o.kf_cov, rtol=1e-4, atol=1e-9)
+        np.testing.assert_array_equal(host["kf_mean"][b, :n], o.kf_mean)
+        np.testing.assert_array_equal(host["kf_cov"][b, :n], o.kf_cov)
+        matched_more_than_once += int((o.age > 2).sum())
+    assert matched_more_than_once > 0                      # the update path ran, not only initiate / predict
+
+
+def test_motion_model_off_is_the_reference(pkg):
+    """use_kalman=False and rtm_track_step_ex with NULL Kalman pointers are rtm_track_step."""
+    run_batch_against_oracle(pkg, B=4, F=30, slots=64, clip_kw=dict(num_objects=25, w_range=(30, 90), h_range=(40, 140),
+                                                                    vmax=3.0, dropout=0.1), max_tracks=512, seed=5,
+                             track_kw=dict(use_kalman=False))
