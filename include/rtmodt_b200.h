@@ -49,7 +49,10 @@ enum {
   RTM_STATUS_DET_OVERFLOW = 2,   /* det_count[b] > det_stride                          */
   RTM_STATUS_CAND_OVERFLOW = 4,  /* NMS candidates exceed the workspace capacity       */
   RTM_STATUS_EVENT_OVERFLOW = 8, /* events of one step exceed event_stride             */
-  RTM_STATUS_ZONE_LIMIT = 16     /* a stream has more than 64 zones                    */
+  RTM_STATUS_ZONE_LIMIT = 16,    /* a stream has more than 64 zones                    */
+  RTM_STATUS_ASSIGN_LIMIT = 32   /* RTM_ASSIGN_OPTIMAL: more than 4096 admissible pairs in a
+                                    stage, or a conflict component with more than 32 rows or
+                                    columns                                              */
 };
 
 /* per-detection outcome of one tracker step (rtm_track_step: det_kind) */
@@ -190,6 +193,9 @@ typedef struct rtm_track_options {
   int32_t assignment;                /* RTM_ASSIGN_* */
   const rtm_kalman_state* kalman_in; /* both NULL: no motion model (the reference) */
   const rtm_kalman_state* kalman_out;
+  double cost_limit;                 /* RTM_ASSIGN_OPTIMAL: lap's cost_limit, `1 - match_thresh` evaluated in
+                                        double as tracker.py:170 does; a pair is admissible iff
+                                        (double)float32(1 - IoU) < cost_limit                         */
 } rtm_track_options;
 
 int rtm_track_step_ex(const rtm_track_table* table_in, const rtm_track_table* table_out,

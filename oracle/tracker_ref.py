@@ -89,6 +89,36 @@ def assign_columnwin(iou: np.ndarray, thresh: float):
     return rows.tolist(), cols.tolist(), np.flatnonzero(~hit).tolist(), np.flatnonzero(~taken).tolist()
 
 
+def assign_lapjv_emulated(iou: np.ndarray, thresh: float):
+    """The branch the reference takes when ``lap`` is installed (tracker.py:168-181):
+    ``lap.lapjv(1 - iou, extend_cost=True, cost_limit=1 - thresh)``.
+
+    PARITY UNPINNED: ``lap>=0.4.0`` (requirements.txt:22) is not installed here and no reference
+    test fixes its output.  Restated from its published behaviour: with ``cost_limit`` lap solves
+    the square problem ``[[C, L/2], [L/2, 0]]`` of size T + N (L = cost_limit, C in float64) and
+    reports row i as unmatched when its column is one of the T padding columns.  Solved here with
+    ``scipy.optimize.linear_sum_assignment``; equal to lapjv wherever the optimum is unique (ties are
+    broken solver by solver).
+    """
+    from scipy.optimize import linear_sum_assignment
+    t_n, d_n = iou.shape
+    if t_n == 0 or d_n == 0:
+        return [], [], list(range(t_n)), list(range(d_n))
+    limit = 1 - thresh                                     # tracker.py:170, Python float
+    cost = (np.float32(1) - np.asarray(iou, np.float32)).astype(np.float64)   # tracker.py:167, then lap's cast
+    ext = np.full((t_n + d_n, t_n + d_n), limit / 2.0)
+    ext[t_n:, d_n:] = 0.0
+    ext[:t_n, :d_n] = cost
+    r_ind, c_ind = linear_sum_assignment(ext)
+    rows = [int(r) for r, c in zip(r_ind, c_ind) if r < t_n and c < d_n]
+    cols = [int(c) for r, c in zip(r_ind, c_ind) if r < t_n and c < d_n]
+    hit = np.zeros(t_n, bool)
+    hit[rows] = True
+    taken = np.zeros(d_n, bool)
+    taken[cols] = True
+    return rows, cols, np.flatnonzero(~hit).tolist(), np.flatnonzero(~taken).tolist()
+
+
 class TrackerOracle:
     """One stream's tracker state + step, tracker.py:43-148."""
 

@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("RTM_LIB_PATH") or os.path.join(HERE, "librtmodt_b200.
 
 RTM_F32, RTM_F16, RTM_BF16 = 0, 1, 2
 STATUS_TRACK_OVERFLOW, STATUS_DET_OVERFLOW, STATUS_CAND_OVERFLOW = 1, 2, 4
-STATUS_EVENT_OVERFLOW, STATUS_ZONE_LIMIT = 8, 16
+STATUS_EVENT_OVERFLOW, STATUS_ZONE_LIMIT, STATUS_ASSIGN_LIMIT = 8, 16, 32
 DET_NONE, DET_STAGE1, DET_STAGE2, DET_BIRTH = 0, 1, 2, 3
 MAX_ZONES_PER_STREAM = 64
 
@@ -25,6 +25,8 @@ _STATUS_TEXT = {
     STATUS_CAND_OVERFLOW: "NMS candidates exceed the workspace capacity",
     STATUS_EVENT_OVERFLOW: "zone events of one step exceed the event buffer (raise max_events)",
     STATUS_ZONE_LIMIT: f"a stream has more than {MAX_ZONES_PER_STREAM} zones",
+    STATUS_ASSIGN_LIMIT: "optimal assignment: more than 4096 admissible pairs in a stage or a conflict component "
+                         "with more than 32 rows / columns",
 }
 
 i32p = C.POINTER(C.c_int32)
@@ -59,7 +61,19 @@ ASSIGN_GREEDY, ASSIGN_OPTIMAL = 0, 1
 class TrackOptions(C.Structure):
     _fields_ = [("track_thresh", C.c_float), ("match_thresh", C.c_float), ("track_buffer", C.c_int32),
                 ("assignment", C.c_int32), ("kalman_in", C.POINTER(KalmanState)),
-                ("kalman_out", C.POINTER(KalmanState))]
+                ("kalman_out", C.POINTER(KalmanState)), ("cost_limit", C.c_double)]
+
+
+def track_options(track_thresh, match_thresh, track_buffer, assignment="greedy", kalman_in=None, kalman_out=None):
+    """rtm_track_options; ``assignment`` = "greedy" (what the reference runs without lap, tracker.py:182-194)
+    or "lapjv" (its lap.lapjv branch, tracker.py:168-181: cost_limit = 1 - match_thresh in double)."""
+    if assignment not in ("greedy", "lapjv"):
+        raise ValueError(f"assignment must be 'greedy' or 'lapjv', not {assignment!r}")
+    return TrackOptions(float(track_thresh), float(match_thresh), int(track_buffer),
+                        ASSIGN_OPTIMAL if assignment == "lapjv" else ASSIGN_GREEDY,
+                        C.pointer(kalman_in) if kalman_in is not None else None,
+                        C.pointer(kalman_out) if kalman_out is not None else None,
+                        1 - float(match_thresh))
 
 
 class ZoneSet(C.Structure):

@@ -103,7 +103,7 @@ extern "C" int rtm_post_backbone_step(const rtm_step_io* io, const rtm_nms_param
                             io->det_count, io->det_stride, io->status, io->workspace, io->workspace_bytes, stream);
     if (rc) return rc;
     const rtm_track_options opt{io->track_thresh, io->match_thresh, io->track_buffer, RTM_ASSIGN_GREEDY, io->kalman_in,
-                                io->kalman_out};
+                                io->kalman_out, 0.0};
     rc = rtm_track_step_ex(io->table_in, io->table_out, io->det_xyxy, io->det_conf, io->det_cls, io->det_count,
                            io->det_stride, &opt, io->det_track_id, io->det_kind, io->src_row, io->status, stream);
     if (rc) return rc;
@@ -143,7 +143,7 @@ extern "C" int rtm_post_backbone_step(const rtm_step_io* io, const rtm_nms_param
   a.trk = rtm::TrackArgs{*io->table_in, *io->table_out, io->det_xyxy, io->det_conf, io->det_cls, io->det_count,
                          io->det_stride, io->track_thresh, io->match_thresh, io->track_buffer, io->det_track_id,
                          io->det_kind, io->src_row, io->status,
-                         nullptr, nullptr, nullptr, nullptr, RTM_ASSIGN_GREEDY};
+                         nullptr, nullptr, nullptr, nullptr, RTM_ASSIGN_GREEDY, 0.0};
   if (io->kalman_in) {
     a.trk.kf_mean_in = io->kalman_in->mean;
     a.trk.kf_cov_in = io->kalman_in->cov;

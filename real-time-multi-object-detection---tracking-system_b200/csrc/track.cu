@@ -29,16 +29,16 @@ __global__ void __launch_bounds__(THREADS) track_step_kernel(const TrackArgs a) 
   __shared__ rtm::TrackPrefetch pf;
   rtm::track_prefetch<THREADS>(a, blockIdx.x, &pf);
   __syncthreads();
-  rtm::track_stream<THREADS>(a, blockIdx.x, smem_raw, &pf);
+  rtm::track_stream<THREADS, true>(a, blockIdx.x, smem_raw, &pf);
 }
 
 template <int THREADS>
 int launch_track(const TrackArgs& a, cudaStream_t stream) {
-  const size_t smem = track_smem_bytes(a.det_stride, a.tin.capacity);
+  const size_t smem = track_smem_bytes(a.det_stride, a.tin.capacity, a.assignment == RTM_ASSIGN_OPTIMAL);
   RTM_REQUIRE(smem + sizeof(rtm::TrackPrefetch) <= 226 * 1024, "rtm_track_step: det_stride %d / capacity %d need %zu B of shared memory (> 227 KB)",
               a.det_stride, a.tin.capacity, smem);
   static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  if (smem + sizeof(rtm::TrackPrefetch) > 40 * 1024 && smem > configured) {  // static + dynamic beyond the default limit
     RTM_CUDA(cudaFuncSetAttribute(track_step_kernel<THREADS>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     configured = smem;
@@ -69,7 +69,7 @@ extern "C" int rtm_track_step_ex(const rtm_track_table* table_in, const rtm_trac
               opt->assignment);
   TrackArgs a{*table_in, *table_out, det_xyxy, det_conf, det_cls, det_count, det_stride,
               opt->track_thresh, opt->match_thresh, opt->track_buffer, det_track_id, det_kind, src_row, status,
-              nullptr, nullptr, nullptr, nullptr, opt->assignment};
+              nullptr, nullptr, nullptr, nullptr, opt->assignment, opt->cost_limit};
   if (opt->kalman_in) {
     RTM_REQUIRE(opt->kalman_in->mean && opt->kalman_in->cov && opt->kalman_out->mean && opt->kalman_out->cov,
                 "rtm_track_step: null Kalman state arrays");
@@ -90,7 +90,7 @@ extern "C" int rtm_track_step(const rtm_track_table* table_in, const rtm_track_t
                               float match_thresh, int32_t track_buffer, int32_t* det_track_id,
                               int32_t* det_kind, int32_t* src_row, int32_t* status,
                               rtm_cuda_stream stream) {
-  const rtm_track_options opt{track_thresh, match_thresh, track_buffer, RTM_ASSIGN_GREEDY, nullptr, nullptr};
+  const rtm_track_options opt{track_thresh, match_thresh, track_buffer, RTM_ASSIGN_GREEDY, nullptr, nullptr, 0.0};
   return rtm_track_step_ex(table_in, table_out, det_xyxy, det_conf, det_cls, det_count, det_stride, &opt, det_track_id,
                            det_kind, src_row, status, stream);
 }

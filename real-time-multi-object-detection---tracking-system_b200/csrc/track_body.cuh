@@ -29,6 +29,7 @@ struct TrackArgs {
   float* kf_mean_out;
   float* kf_cov_out;
   int32_t assignment;  // RTM_ASSIGN_*
+  double cost_limit;   // RTM_ASSIGN_OPTIMAL: lap's cost_limit = 1 - match_thresh (tracker.py:170), in double
 };
 
 // ---- constant-velocity filter of ByteTrack (xyah), stored as four (position, velocity) filters.
@@ -250,9 +251,223 @@ __device__ __forceinline__ void associate(const TrackPrefetch* pf, const float4*
   __syncthreads();
 }
 
+// ---------------------------------------------------------------------------------------
+// Optimal assignment (RTM_ASSIGN_OPTIMAL): what the reference computes when `lap` is installed,
+// lap.lapjv(1 - IoU, extend_cost=True, cost_limit=1 - thresh) (tracker.py:168-181).  lap solves
+// the (T + N) x (T + N) problem [[C, L/2], [L/2, 0]] (L = cost_limit): a pair is worth matching
+// iff its cost is below L, so the optimum is the minimum-cost matching on the ADMISSIBLE pairs
+// (cost < L, i.e. IoU > thresh - a sparse graph) where every unmatched row or column pays L/2.
+//   1. admissible pairs are collected in parallel (same row scan as the greedy stage);
+//   2. a pair whose row and column have no other admissible pair is matched at once - in ordinary
+//      scenes that settles everything;
+//   3. what is left falls into small connected components; each is solved exactly with the
+//      Hungarian method (potentials + shortest augmenting paths, float64) on its own extended
+//      matrix, serially - the components of a stream are few and tiny.
+// Limits (reported through the status word, never silently exceeded): kAssignMaxEdges admissible
+// pairs per stage, kAssignMaxSide rows or columns per component.
+// ---------------------------------------------------------------------------------------
+constexpr int kAssignMaxEdges = 4096;
+constexpr int kAssignMaxSide = 32;
+
+struct AssignScratch {
+  int n_edges;
+  int limit_hit;
+  unsigned short edge_row[kAssignMaxEdges], edge_col[kAssignMaxEdges];
+  float edge_cost[kAssignMaxEdges];  // 1 - IoU in float32 (what the reference hands to lap), < 0 = settled
+  // working set of the component solver (thread 0 only)
+  float cost[kAssignMaxSide * kAssignMaxSide];
+  int rows[kAssignMaxSide], cols[kAssignMaxSide], match[kAssignMaxSide];
+  double u[2 * kAssignMaxSide + 1], v[2 * kAssignMaxSide + 1], minv[2 * kAssignMaxSide + 1];
+  int p[2 * kAssignMaxSide + 1], way[2 * kAssignMaxSide + 1];
+  unsigned char used[2 * kAssignMaxSide + 8];
+};
+
+// Hungarian method on the extended matrix of one component: r rows, c columns, cost[i * c + j]
+// (float32 values, +inf where the pair is not admissible), half = L / 2.  match[i] = column or -1.
+static __device__ __noinline__ void hungarian_component(AssignScratch* sc, const int r, const int c, const double half) {
+  const int n = r + c;
+  const double kInf = 1e300;
+  const float* cost = sc->cost;
+  double *u = sc->u, *v = sc->v, *minv = sc->minv;
+  int *p = sc->p, *way = sc->way, *match = sc->match;
+  unsigned char* used = sc->used;
+  auto entry = [&](int i, int j) -> double {  // 0-based
+    if (i < r && j < c) {
+      const float x = cost[i * c + j];
+      return x < 3.0e38f ? static_cast<double>(x) : kInf;
+    }
+    if (i >= r && j >= c) return 0.0;
+    return half;
+  };
+  for (int k = 0; k <= n; ++k) {
+    u[k] = v[k] = 0.0;
+    p[k] = 0;
+    way[k] = 0;
+  }
+  for (int i = 1; i <= n; ++i) {
+    p[0] = i;
+    int j0 = 0;
+    for (int k = 0; k <= n; ++k) {
+      minv[k] = kInf;
+      used[k] = 0;
+    }
+    do {
+      used[j0] = 1;
+      const int i0 = p[j0];
+      double delta = kInf;
+      int j1 = 0;
+      for (int j = 1; j <= n; ++j) {
+        if (used[j]) continue;
+        const double cur = entry(i0 - 1, j - 1) - u[i0] - v[j];
+        if (cur < minv[j]) {
+          minv[j] = cur;
+          way[j] = j0;
+        }
+        if (minv[j] < delta) {
+          delta = minv[j];
+          j1 = j;
+        }
+      }
+      for (int j = 0; j <= n; ++j) {
+        if (used[j]) {
+          u[p[j]] += delta;
+          v[j] -= delta;
+        } else {
+          minv[j] -= delta;
+        }
+      }
+      j0 = j1;
+    } while (p[j0] != 0);
+    do {
+      const int j1 = way[j0];
+      p[j0] = p[j1];
+      j0 = j1;
+    } while (j0);
+  }
+  for (int i = 0; i < r; ++i) match[i] = -1;
+  for (int j = 1; j <= c; ++j)
+    if (p[j] >= 1 && p[j] <= r) match[p[j] - 1] = j - 1;
+}
+
+template <int THREADS>
+__device__ __forceinline__ int associate_optimal(const TrackPrefetch* pf, const float4* __restrict__ g_box,
+                                                 const float* kf_mean, const int32_t* g_tsu, size_t row0, int T,
+                                                 const float4* s_box, const float* s_area, const int* s_list, int m,
+                                                 int* s_win, int* s_match, const double cost_limit, int flag,
+                                                 AssignScratch* sc, int* deg_row, int* deg_col) {
+  const int tid = threadIdx.x;
+  for (int j = tid; j < m; j += THREADS) {
+    s_win[j] = INT_MAX;
+    deg_col[j] = 0;
+  }
+  for (int t = tid; t < T; t += THREADS) deg_row[t] = 0;
+  if (tid == 0) {
+    sc->n_edges = 0;
+    sc->limit_hit = 0;
+  }
+  __syncthreads();
+  // ---- 1. admissible pairs ----
+  int G = 4;
+  while (G < 32 && G < m) G <<= 1;
+  const int sub = tid & (G - 1), groups = THREADS / G;
+  for (int t0 = 0; t0 < T; t0 += groups) {
+    const int t = t0 + tid / G;
+    if (t < T && s_match[t] < 0) {
+      const float4 a = t < kTrackPrefRows ? pf->abox[t]
+                                          : (kf_mean ? kalman_predicted_box(kf_mean, row0 + t, g_tsu[row0 + t]) : g_box[t]);
+      const float area_a = box_area(a);
+      for (int j = sub; j < m; j += G) {
+        const int d = s_list[j];
+        const float cst = __fsub_rn(1.f, pair_iou(a, area_a, s_box[d], s_area[d]));  // tracker.py:167, float32
+        if (static_cast<double>(cst) < cost_limit) {
+          const int e = atomicAdd(&sc->n_edges, 1);
+          if (e < kAssignMaxEdges) {
+            sc->edge_row[e] = static_cast<unsigned short>(t);
+            sc->edge_col[e] = static_cast<unsigned short>(j);
+            sc->edge_cost[e] = cst;
+          }
+          atomicAdd(&deg_row[t], 1);
+          atomicAdd(&deg_col[j], 1);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const int E = min(sc->n_edges, kAssignMaxEdges);
+  // ---- 2. pairs alone in their row and column ----
+  for (int e = tid; e < E; e += THREADS) {
+    const int t = sc->edge_row[e], j = sc->edge_col[e];
+    if (deg_row[t] == 1 && deg_col[j] == 1) {
+      s_match[t] = s_list[j] | flag;
+      s_win[j] = t;
+      sc->edge_cost[e] = -1.f;
+    }
+  }
+  __syncthreads();
+  // ---- 3. the rest, component by component (thread 0) ----
+  if (tid == 0) {
+    if (sc->n_edges > kAssignMaxEdges) sc->limit_hit = 1;
+    for (int e0 = 0; e0 < E; ++e0) {
+      if (sc->edge_cost[e0] < 0.f) continue;
+      int *rows = sc->rows, *cols = sc->cols, r = 0, c = 0;
+      float* cost = sc->cost;
+      bool too_big = false;
+      rows[r++] = sc->edge_row[e0];
+      cols[c++] = sc->edge_col[e0];
+      // flood: pull in every unsettled pair that shares a row or a column with the component
+      for (bool grown = true; grown && !too_big;) {
+        grown = false;
+        for (int e = e0; e < E && !too_big; ++e) {
+          if (sc->edge_cost[e] < 0.f) continue;
+          const int t = sc->edge_row[e], j = sc->edge_col[e];
+          bool has_r = false, has_c = false;
+          for (int k = 0; k < r; ++k) has_r |= rows[k] == t;
+          for (int k = 0; k < c; ++k) has_c |= cols[k] == j;
+          if (has_r == has_c) continue;  // neither (not ours) or both (already in)
+          if (!has_r) {
+            if (r == kAssignMaxSide) too_big = true;
+            else rows[r++] = t;
+          } else {
+            if (c == kAssignMaxSide) too_big = true;
+            else cols[c++] = j;
+          }
+          grown = true;
+        }
+      }
+      if (too_big) {
+        sc->limit_hit = 1;
+        break;
+      }
+      for (int k = 0; k < r * c; ++k) cost[k] = 3.4e38f;
+      for (int e = e0; e < E; ++e) {
+        if (sc->edge_cost[e] < 0.f) continue;
+        int li = -1, lj = -1;
+        for (int k = 0; k < r; ++k)
+          if (rows[k] == sc->edge_row[e]) li = k;
+        for (int k = 0; k < c; ++k)
+          if (cols[k] == sc->edge_col[e]) lj = k;
+        if (li >= 0 && lj >= 0) {
+          cost[li * c + lj] = sc->edge_cost[e];
+          sc->edge_cost[e] = -1.f;  // settled with this component
+        }
+      }
+      hungarian_component(sc, r, c, cost_limit * 0.5);
+      const int* match = sc->match;
+      for (int k = 0; k < r; ++k) {
+        if (match[k] >= 0 && cost[k * c + match[k]] < 3.0e38f) {
+          s_match[rows[k]] = s_list[cols[match[k]]] | flag;
+          s_win[cols[match[k]]] = rows[k];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  return sc->limit_hit;
+}
+
 // One stream.  `smem_raw`: track_smem_bytes(det_stride, capacity) bytes of shared memory,
 // 16-byte aligned.  All THREADS threads of the block must call it (block-uniform control flow).
-template <int THREADS>
+template <int THREADS, bool WITH_OPTIMAL = false>
 __device__ __forceinline__ void track_stream(const TrackArgs& a, const int b, unsigned char* smem_raw,
                                              const TrackPrefetch* pf) {
   const int tid = threadIdx.x;
@@ -267,7 +482,12 @@ __device__ __forceinline__ void track_stream(const TrackArgs& a, const int b, un
   float* s_conf = reinterpret_cast<float*>(s_born + S);  // S
   int* s_cls = reinterpret_cast<int*>(s_conf + S);       // S
   int* s_match = s_cls + S;                             // cap
-  int* s_scan = s_match + cap;                          // 33
+  int* s_scan = s_match + cap;                          // 33 (+ 7 spare)
+  // optimal-assignment scratch (only laid out by track_smem_bytes when that mode is on)
+  int* s_deg_row = s_scan + 40;                         // cap
+  int* s_deg_col = s_deg_row + cap;                     // S
+  AssignScratch* s_assign = reinterpret_cast<AssignScratch*>(s_deg_col + S);
+  const bool optimal = WITH_OPTIMAL && a.assignment == RTM_ASSIGN_OPTIMAL;
 
   const size_t row0 = static_cast<size_t>(b) * cap;
   const size_t det0 = static_cast<size_t>(b) * S;
@@ -344,16 +564,28 @@ __device__ __forceinline__ void track_stream(const TrackArgs& a, const int b, un
 
   // ---- stage 1: all retained tracks x high detections (tracker.py:91-104) ---------------
   if (T > 0 && H > 0) {
-    associate<THREADS>(pf, in_box, a.kf_mean_in, a.tin.time_since_update, row0, T, s_box, s_area, s_hi, H, s_win, s_match,
-                       a.match_thresh, 0);
+    if (WITH_OPTIMAL && optimal) {
+      if (associate_optimal<THREADS>(pf, in_box, a.kf_mean_in, a.tin.time_since_update, row0, T, s_box, s_area, s_hi, H, s_win,
+                                     s_match, a.cost_limit, 0, s_assign, s_deg_row, s_deg_col))
+        st |= RTM_STATUS_ASSIGN_LIMIT;
+    } else {
+      associate<THREADS>(pf, in_box, a.kf_mean_in, a.tin.time_since_update, row0, T, s_box, s_area, s_hi, H, s_win, s_match,
+                         a.match_thresh, 0);
+    }
     for (int j = tid; j < H; j += THREADS) s_born[j] = (s_win[j] == INT_MAX);
     __syncthreads();
   }
   RTM_TL(12);
   // ---- stage 2: still-unmatched tracks x low detections, same threshold (tracker.py:109-123)
   if (T > 0 && L > 0) {
-    associate<THREADS>(pf, in_box, a.kf_mean_in, a.tin.time_since_update, row0, T, s_box, s_area, s_lo, L, s_win, s_match,
-                       a.match_thresh, kStage2Flag);
+    if (WITH_OPTIMAL && optimal) {
+      if (associate_optimal<THREADS>(pf, in_box, a.kf_mean_in, a.tin.time_since_update, row0, T, s_box, s_area, s_lo, L, s_win,
+                                     s_match, a.cost_limit, kStage2Flag, s_assign, s_deg_row, s_deg_col))
+        st |= RTM_STATUS_ASSIGN_LIMIT;
+    } else {
+      associate<THREADS>(pf, in_box, a.kf_mean_in, a.tin.time_since_update, row0, T, s_box, s_area, s_lo, L, s_win, s_match,
+                         a.match_thresh, kStage2Flag);
+    }
   }
 
   RTM_TL(13);
@@ -448,7 +680,10 @@ __device__ __forceinline__ void track_stream(const TrackArgs& a, const int b, un
   }
 }
 
-inline size_t track_smem_bytes(int det_stride, int capacity) {
+inline size_t track_smem_bytes(int det_stride, int capacity, bool optimal = false) {
+  if (optimal)
+    return static_cast<size_t>(det_stride) * (16 + 4 + 4 * 4 + 4 + 4 + 4 + 4) + static_cast<size_t>(capacity) * 8 + 40 * 4 +
+           sizeof(AssignScratch) + 16;
   return static_cast<size_t>(det_stride) * (16 + 4 + 4 * 4 + 4 + 4 + 4) + static_cast<size_t>(capacity) * 4 + 40 * 4;
 }
 

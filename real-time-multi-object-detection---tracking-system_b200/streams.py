@@ -231,7 +231,8 @@ class StreamBatch:
                  iou: float = 0.45, classes: Optional[Sequence[int]] = None, max_det: int = 100,
                  agnostic_nms: bool = False, track_thresh: float = 0.5, track_buffer: int = 30,
                  match_thresh: float = 0.8, max_tracks: int = 1024, max_events: Optional[int] = None,
-                 det_slots: Optional[int] = None, device="cuda:0", use_kalman: bool = False) -> None:
+                 det_slots: Optional[int] = None, device="cuda:0", use_kalman: bool = False,
+                 assignment: str = "greedy") -> None:
         import torch
         self.lib = _lib.lib()
         self.device = torch.device(device)
@@ -260,6 +261,9 @@ class StreamBatch:
             self.workspace = torch.zeros(ws_bytes, dtype=torch.uint8, device=self.device)
             # use_kalman: opt-in motion model the reference does not have (rtm_track_step_ex); off = reference
             self.use_kalman = bool(use_kalman)
+            # assignment: "greedy" = what the reference runs without `lap` (and here); "lapjv" = its lap branch
+            self.assignment = assignment
+            _lib.track_options(0.5, 0.8, 30, assignment)          # validates the name
             self.tables = [DeviceTrackTable(B, max_tracks, self.device, kalman=self.use_kalman) for _ in range(2)]
             self.src_row = torch.zeros(B, max_tracks, **i32)
             self.zones = None
@@ -325,8 +329,28 @@ class StreamBatch:
         fid = self.frame_id if frame_id is None else frame_id
         with torch.cuda.device(self.device):
             io = self._io(heads, now, fid)
-            _lib.check(self.lib.rtm_post_backbone_step(C.byref(io), C.byref(self.params), _lib.cuda_stream()))
+            if self.assignment == "greedy":
+                _lib.check(self.lib.rtm_post_backbone_step(C.byref(io), C.byref(self.params), _lib.cuda_stream()))
+            else:
+                self._step_unfused(io)
         self._advance()
+
+    def _step_unfused(self, io) -> None:
+        """The three stages as separate entry points (the fused kernel only has the greedy assignment)."""
+        st = _lib.cuda_stream()
+        _lib.check(self.lib.rtm_decode_nms(io.head_p3, io.head_p4, io.head_p5, io.head_dtype, self.B, io.img_h, io.img_w,
+                                           C.byref(self.params), io.scale, io.det_xyxy, io.det_conf, io.det_cls,
+                                           io.det_anchor, io.det_keep, io.det_count, io.det_stride, io.status,
+                                           io.workspace, io.workspace_bytes, st))
+        tin, tout = self.tables[self.cur], self.tables[self.cur ^ 1]
+        opt = _lib.track_options(self.track_thresh, self.match_thresh, self.track_buffer, self.assignment,
+                                 tin.kalman if self.use_kalman else None, tout.kalman if self.use_kalman else None)
+        _lib.check(self.lib.rtm_track_step_ex(io.table_in, io.table_out, io.det_xyxy, io.det_conf, io.det_cls, io.det_count,
+                                              io.det_stride, C.byref(opt), io.det_track_id, io.det_kind, io.src_row,
+                                              io.status, st))
+        if self.zones is not None:
+            _lib.check(self.lib.rtm_zone_step(io.zones, io.table_out, io.src_row, io.state_in, io.state_out, io.now, None,
+                                              io.frame_id, io.events, io.event_stride, io.event_count, io.status, st))
 
     def track_only(self, det_xyxy, det_conf, det_cls, det_count, now: Optional[float] = None,
                    frame_id: Optional[int] = None) -> None:
@@ -340,9 +364,8 @@ class StreamBatch:
             st = _lib.cuda_stream()
             tin, tout = self.tables[self.cur], self.tables[self.cur ^ 1]
             want_assign = S == self.det_stride
-            opt = _lib.TrackOptions(self.track_thresh, self.match_thresh, self.track_buffer, _lib.ASSIGN_GREEDY,
-                                    C.pointer(tin.kalman) if self.use_kalman else None,
-                                    C.pointer(tout.kalman) if self.use_kalman else None)
+            opt = _lib.track_options(self.track_thresh, self.match_thresh, self.track_buffer, self.assignment,
+                                     tin.kalman if self.use_kalman else None, tout.kalman if self.use_kalman else None)
             _lib.check(self.lib.rtm_track_step_ex(
                 C.byref(tin.struct), C.byref(tout.struct), det_xyxy.data_ptr(), det_conf.data_ptr(),
                 det_cls.data_ptr(), det_count.data_ptr(), S, C.byref(opt),

@@ -46,12 +46,17 @@ class _ByteTrackCore:
     """Device-resident counterpart of the reference's ``_ByteTrackCore`` (tracker.py:43-194)."""
 
     def __init__(self, track_thresh: float = 0.5, track_buffer: int = 30, match_thresh: float = 0.8,
-                 max_tracks: int = 1024, max_dets: int = 256, device="cuda:0", use_kalman: bool = False) -> None:
+                 max_tracks: int = 1024, max_dets: int = 256, device="cuda:0", use_kalman: bool = False,
+                 assignment: str = "greedy") -> None:
         import torch
         self.track_thresh, self.track_buffer, self.match_thresh = track_thresh, track_buffer, match_thresh
         # opt-in: associate against the box a constant-velocity filter predicts (the reference has no
         # motion model; default off keeps its behaviour bit for bit)
         self.use_kalman = bool(use_kalman)
+        # "greedy": the branch of tracker.py:163-194 the reference takes when `lap` is missing (as here);
+        # "lapjv": its lap.lapjv branch, solved exactly on the GPU
+        self.assignment = assignment
+        _lib.track_options(track_thresh, match_thresh, track_buffer, assignment)
         self._lib = _lib.lib()
         self.device = torch.device(device)
         self.max_dets = int(max_dets)
@@ -89,9 +94,8 @@ class _ByteTrackCore:
                 self._det_cls[0, :n] = torch.as_tensor(np.ascontiguousarray(class_id, np.int32)).to(self.device)
             self._det_count.fill_(n)
             tin, tout = self._tables[self._cur], self._tables[self._cur ^ 1]
-            opt = _lib.TrackOptions(float(self.track_thresh), float(self.match_thresh), int(self.track_buffer),
-                                    _lib.ASSIGN_GREEDY, C.pointer(tin.kalman) if self.use_kalman else None,
-                                    C.pointer(tout.kalman) if self.use_kalman else None)
+            opt = _lib.track_options(self.track_thresh, self.match_thresh, self.track_buffer, self.assignment,
+                                     tin.kalman if self.use_kalman else None, tout.kalman if self.use_kalman else None)
             _lib.check(self._lib.rtm_track_step_ex(
                 C.byref(tin.struct), C.byref(tout.struct), self._det_xyxy.data_ptr(),
                 self._det_conf.data_ptr(), self._det_cls.data_ptr(), self._det_count.data_ptr(),
@@ -117,7 +121,7 @@ class MultiObjectTracker:
         self.algorithm = algorithm.lower()
         if self.algorithm == "bytetrack":
             bt_params = kwargs.get("bytetrack", kwargs)           # nested or flat, tracker.py:206
-            extra = {k: kwargs[k] for k in ("max_tracks", "max_dets", "device", "use_kalman") if k in kwargs}
+            extra = {k: kwargs[k] for k in ("max_tracks", "max_dets", "device", "use_kalman", "assignment") if k in kwargs}
             self._core = _ByteTrackCore(track_thresh=bt_params.get("track_thresh", 0.5),
                                         track_buffer=bt_params.get("track_buffer", 30),
                                         match_thresh=bt_params.get("match_thresh", 0.8), **extra)

@@ -31,12 +31,12 @@ def test_facade_replays_reference_golden(pkg, name):
         assert_state_equal(trk._core._tracks, trk._core._next_id, golden_state(g, f), int(g["next_id"][f]))
 
 
-def run_batch_against_oracle(pkg, B, F, slots, clip_kw, max_tracks, seed=100, track_kw=None, check_every=1):
+def run_batch_against_oracle(pkg, B, F, slots, clip_kw, max_tracks, seed=100, track_kw=None, check_every=1, oracle_kw=None):
     import torch
     track_kw = track_kw or {}
     xyxy, conf, cls, count = pkg.synth.scripted_batch(B, F, slots, seed=seed, **clip_kw)
     sb = pkg.StreamBatch(B, None, max_det=slots, max_tracks=max_tracks, **track_kw)
-    oracles = [tracker_ref.TrackerOracle(**track_kw) for _ in range(B)]
+    oracles = [tracker_ref.TrackerOracle(**(track_kw if oracle_kw is None else oracle_kw)) for _ in range(B)]
     dev = sb.device
     for f in range(F):
         sb.track_only(torch.from_numpy(xyxy[f]).to(dev), torch.from_numpy(conf[f]).to(dev),
@@ -157,3 +157,43 @@ def test_motion_model_off_is_the_reference(pkg):
     run_batch_against_oracle(pkg, B=4, F=30, slots=64, clip_kw=dict(num_objects=25, w_range=(30, 90), h_range=(40, 140),
                                                                     vmax=3.0, dropout=0.1), max_tracks=512, seed=5,
                              track_kw=dict(use_kalman=False))
+
+
+@pytest.mark.parametrize("clip", ["sparse", "crowd", "dense"])
+def test_optimal_assignment_matches_lapjv_emulation(pkg, clip):
+    """assignment="lapjv" (tracker.py:168-181, the branch taken when `lap` is installed) against the
+    scipy emulation of lap.lapjv(extend_cost, cost_limit): bit-exact state and assignments.  The clips
+    are dense enough for the optimal and the greedy assignment to differ."""
+    kw = dict(sparse=dict(num_objects=20, w_range=(60, 160), h_range=(120, 320), vmax=2.0, dropout=0.05),
+              crowd=dict(num_objects=250, w_range=(20, 60), h_range=(50, 150), vmax=1.5, dropout=0.05),
+              dense=pkg.synth.dense_crowd_kwargs(1000))[clip]
+    B, F, slots = (4, 40, 64) if clip == "sparse" else ((3, 20, 256) if clip == "crowd" else (2, 6, 1024))
+    run_batch_against_oracle(pkg, B=B, F=F, slots=slots, clip_kw=kw, max_tracks=4096, seed=31,
+                             track_kw=dict(assignment="lapjv"), oracle_kw=dict(assign=tracker_ref.assign_lapjv_emulated))
+    if clip == "crowd":
+        # the same clip under the greedy rule ends elsewhere: the test above is not vacuous
+        xyxy, conf, cls, count = pkg.synth.scripted_batch(B, F, slots, seed=31, **kw)
+        a, b = tracker_ref.TrackerOracle(), tracker_ref.TrackerOracle(assign=tracker_ref.assign_lapjv_emulated)
+        for f in range(F):
+            a.step(xyxy[f, 0, :count[f, 0]], conf[f, 0, :count[f, 0]], cls[f, 0, :count[f, 0]])
+            b.step(xyxy[f, 0, :count[f, 0]], conf[f, 0, :count[f, 0]], cls[f, 0, :count[f, 0]])
+        assert a.next_id != b.next_id or not np.array_equal(a.track_id, b.track_id) or not np.array_equal(a.xyxy, b.xyxy)
+
+
+def test_optimal_assignment_resolves_conflicts_the_greedy_rule_cannot(pkg):
+    """Two tracks whose best detection is the same one: greedy gives it to the first track and leaves
+    the second unmatched (no second choice); the optimal assignment matches both."""
+    import types
+    t0 = np.array([[0, 0, 100, 100], [4, 0, 104, 100]], np.float32)          # tracks A, B
+    d1 = np.array([[3, 0, 103, 100], [9, 0, 109, 100]], np.float32)          # X best for both; Y admissible for B only
+    conf, cls = np.full(2, 0.9, np.float32), np.zeros(2, np.int32)
+    for mode, assign in (("greedy", tracker_ref.assign_rowloop), ("lapjv", tracker_ref.assign_lapjv_emulated)):
+        trk = pkg.MultiObjectTracker(max_tracks=16, max_dets=8, assignment=mode)
+        orc = tracker_ref.TrackerOracle(assign=assign)
+        for boxes in (t0, d1):
+            trk.update(types.SimpleNamespace(xyxy=boxes, confidence=conf, class_id=cls))
+            exp_tid, exp_kind = orc.step(boxes, conf, cls)
+            tid, kind = trk._core.assignments()
+            np.testing.assert_array_equal(tid, exp_tid)
+            np.testing.assert_array_equal(kind, exp_kind)
+        assert trk._core._next_id == orc.next_id == (4 if mode == "greedy" else 3)
