@@ -67,6 +67,17 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu
+    --set full capture (profiles/traffic.json, written by tools/ncu_summary.py), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)[kernel]
+        return t["dram_bytes_read_per_launch"] + t["dram_bytes_write_per_launch"]
+    except Exception:
+        return None
+
+
 # ---------------------------------------------------------------------------
 # clocks
 # ---------------------------------------------------------------------------
@@ -374,8 +385,8 @@ def run_b200(args):
         dec_us = kernels["decode"]["avg_us"]
         alg_bytes = S * wl.bytes_per_stream_frame
         achieved = alg_bytes / (dec_us * 1e-6) / 1e9
-        roofline = {"bound": "hbm", "kernel": "decode_candidates_kernel", "achieved": achieved, "peak": hbm_peak,
-                    "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+        roofline = {"bound": "hbm", "kernel": "decode_tma_kernel", "achieved": achieved, "peak": hbm_peak,
+                    "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": ncu_traffic("decode_tma_kernel"), "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_us": dec_us,
                     "share_of_step": dec_us / sum(v["avg_us"] for v in kernels.values()),
                     "whole_step_frac": (alg_bytes * K / (ms_total / 1e3) / 1e9) / hbm_peak}

@@ -76,6 +76,15 @@ int rtm_letterbox(const uint8_t* frames, int32_t num_streams, int32_t src_h, int
                   int64_t row_stride, int64_t frame_stride, void* out, int32_t out_dtype,
                   int32_t out_h, int32_t out_w, rtm_cuda_stream stream);
 
+/* The same with the resize geometry given by the caller: the source is resized to new_w x new_h
+ * and placed at (left, top) of the out_w x out_h output, the rest is 114.  This is how the other
+ * LetterBox variants are expressed - auto=True (the minimum stride-32 rectangle ultralytics uses
+ * for .pt models: 1080p -> 384 x 640, 5040 anchors), scaleup=False, center=False. */
+int rtm_letterbox_ex(const uint8_t* frames, int32_t num_streams, int32_t src_h, int32_t src_w,
+                     int64_t row_stride, int64_t frame_stride, void* out, int32_t out_dtype,
+                     int32_t out_h, int32_t out_w, int32_t new_h, int32_t new_w, int32_t top,
+                     int32_t left, rtm_cuda_stream stream);
+
 /* ------------------------------------------------------------------------------------------
  * D1 + N1..N3  head decode, candidate filter, class-aware NMS, rescale.  Replaces
  * ultralytics Detect._inference / DFL / dist2bbox, ops.non_max_suppression (which calls

@@ -33,20 +33,25 @@ MAX_NMS = 30000
 # ---------------------------------------------------------------------------
 # P1 letterbox / preprocess
 # ---------------------------------------------------------------------------
-def letterbox_geometry(src_hw, new_shape=(640, 640)):
+def letterbox_geometry(src_hw, new_shape=(640, 640), auto=False, stride=32):
+    """LetterBox.__call__ geometry.  ``auto=True`` (what ultralytics uses for .pt models) pads only
+    to the next multiple of ``stride``: ``dw, dh = np.mod(dw, stride), np.mod(dh, stride)``."""
     h0, w0 = src_hw
     r = min(new_shape[0] / h0, new_shape[1] / w0)
     new_unpad = int(round(w0 * r)), int(round(h0 * r))          # (w, h)
-    dw, dh = (new_shape[1] - new_unpad[0]) / 2, (new_shape[0] - new_unpad[1]) / 2
+    dw, dh = new_shape[1] - new_unpad[0], new_shape[0] - new_unpad[1]
+    if auto:
+        dw, dh = dw % stride, dh % stride
+    dw, dh = dw / 2, dh / 2
     top, bottom = int(round(dh - 0.1)), int(round(dh + 0.1))
     left, right = int(round(dw - 0.1)), int(round(dw + 0.1))
     return new_unpad, (top, bottom, left, right)
 
 
-def letterbox(img: np.ndarray, new_shape=(640, 640)) -> np.ndarray:
+def letterbox(img: np.ndarray, new_shape=(640, 640), auto=False) -> np.ndarray:
     """u8 HWC BGR -> u8 HWC BGR letterboxed, via OpenCV exactly as ultralytics does."""
     import cv2
-    new_unpad, (top, bottom, left, right) = letterbox_geometry(img.shape[:2], new_shape)
+    new_unpad, (top, bottom, left, right) = letterbox_geometry(img.shape[:2], new_shape, auto)
     if img.shape[:2][::-1] != new_unpad:
         img = cv2.resize(img, new_unpad, interpolation=cv2.INTER_LINEAR)
     return cv2.copyMakeBorder(img, top, bottom, left, right, cv2.BORDER_CONSTANT, value=(114, 114, 114))

@@ -133,6 +133,9 @@ SIGNATURES = {
     "rtm_device_info": (C.c_int, [i32p, i32p, i32p]),
     "rtm_letterbox": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64,
                                 C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "rtm_letterbox_ex": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64,
+                                   C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                   C.c_int32, C.c_void_p]),
     "rtm_nms_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "rtm_decode_nms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                  C.c_int32, C.POINTER(NmsParams), C.c_void_p, C.c_void_p, C.c_void_p,

@@ -147,14 +147,19 @@ __global__ void __launch_bounds__(256) letterbox_kernel(const LetterboxArgs a) {
 
 }  // namespace
 
-extern "C" int rtm_letterbox(const uint8_t* frames, int32_t num_streams, int32_t src_h, int32_t src_w,
-                             int64_t row_stride, int64_t frame_stride, void* out, int32_t out_dtype,
-                             int32_t out_h, int32_t out_w, rtm_cuda_stream stream) {
+namespace {
+
+int launch_letterbox(const uint8_t* frames, int num_streams, int src_h, int src_w, int64_t row_stride, int64_t frame_stride,
+                     void* out, int out_dtype, int out_h, int out_w, int new_h, int new_w, int top, int left,
+                     rtm_cuda_stream stream) {
   RTM_REQUIRE(frames && out, "rtm_letterbox: null pointer");
   RTM_REQUIRE(num_streams > 0 && src_h > 0 && src_w > 0 && out_h > 0 && out_w > 0, "rtm_letterbox: bad shape");
   RTM_REQUIRE(out_w % kPix == 0, "rtm_letterbox: out_w %d must be a multiple of %d", out_w, kPix);
   RTM_REQUIRE(row_stride >= 3ll * src_w && frame_stride >= row_stride * src_h, "rtm_letterbox: strides too small");
   RTM_REQUIRE((reinterpret_cast<uintptr_t>(out) & 31) == 0, "rtm_letterbox: out must be 32-byte aligned");
+  RTM_REQUIRE(new_w >= 1 && new_h >= 1 && left >= 0 && top >= 0 && left + new_w <= out_w && top + new_h <= out_h,
+              "rtm_letterbox: resized image %dx%d at (%d, %d) does not fit the %dx%d output", new_w, new_h, left, top, out_w,
+              out_h);
   LetterboxArgs a;
   a.frames = frames;
   a.src_h = src_h;
@@ -164,14 +169,10 @@ extern "C" int rtm_letterbox(const uint8_t* frames, int32_t num_streams, int32_t
   a.out = out;
   a.out_h = out_h;
   a.out_w = out_w;
-  // LetterBox.__call__: r = min(H/h0, W/w0); new_unpad = round(w0*r), round(h0*r);
-  // dw, dh = (W - new_w)/2, (H - new_h)/2; top = round(dh - 0.1), left = round(dw - 0.1)
-  const double r = fmin(static_cast<double>(out_h) / src_h, static_cast<double>(out_w) / src_w);
-  a.new_w = static_cast<int>(nearbyint(src_w * r));  // Python round(): half to even
-  a.new_h = static_cast<int>(nearbyint(src_h * r));
-  RTM_REQUIRE(a.new_w >= 1 && a.new_h >= 1 && a.new_w <= out_w && a.new_h <= out_h, "rtm_letterbox: degenerate resize");
-  a.left = static_cast<int>(nearbyint((out_w - a.new_w) / 2.0 - 0.1));
-  a.top = static_cast<int>(nearbyint((out_h - a.new_h) / 2.0 - 0.1));
+  a.new_w = new_w;
+  a.new_h = new_h;
+  a.left = left;
+  a.top = top;
   a.resize = !(a.new_w == src_w && a.new_h == src_h);
   // cv::resize: inv_scale = dsize / ssize; scale = 1. / inv_scale
   a.scale_x = 1.0 / (static_cast<double>(a.new_w) / src_w);
@@ -195,4 +196,30 @@ extern "C" int rtm_letterbox(const uint8_t* frames, int32_t num_streams, int32_t
   }
   RTM_LAUNCH_CHECK("letterbox_kernel");
   return RTM_OK;
+}
+
+}  // namespace
+
+extern "C" int rtm_letterbox(const uint8_t* frames, int32_t num_streams, int32_t src_h, int32_t src_w,
+                             int64_t row_stride, int64_t frame_stride, void* out, int32_t out_dtype,
+                             int32_t out_h, int32_t out_w, rtm_cuda_stream stream) {
+  RTM_REQUIRE(src_h > 0 && src_w > 0 && out_h > 0 && out_w > 0, "rtm_letterbox: bad shape");
+  // LetterBox.__call__ (auto=False, scaleup=True, center=True): r = min(H/h0, W/w0);
+  // new_unpad = round(w0*r), round(h0*r); dw, dh = (W - new_w)/2, (H - new_h)/2;
+  // top = round(dh - 0.1), left = round(dw - 0.1)
+  const double r = fmin(static_cast<double>(out_h) / src_h, static_cast<double>(out_w) / src_w);
+  const int new_w = static_cast<int>(nearbyint(src_w * r));  // Python round(): half to even
+  const int new_h = static_cast<int>(nearbyint(src_h * r));
+  const int left = static_cast<int>(nearbyint((out_w - new_w) / 2.0 - 0.1));
+  const int top = static_cast<int>(nearbyint((out_h - new_h) / 2.0 - 0.1));
+  return launch_letterbox(frames, num_streams, src_h, src_w, row_stride, frame_stride, out, out_dtype, out_h, out_w, new_h,
+                          new_w, top, left, stream);
+}
+
+extern "C" int rtm_letterbox_ex(const uint8_t* frames, int32_t num_streams, int32_t src_h, int32_t src_w,
+                                int64_t row_stride, int64_t frame_stride, void* out, int32_t out_dtype,
+                                int32_t out_h, int32_t out_w, int32_t new_h, int32_t new_w, int32_t top, int32_t left,
+                                rtm_cuda_stream stream) {
+  return launch_letterbox(frames, num_streams, src_h, src_w, row_stride, frame_stride, out, out_dtype, out_h, out_w, new_h,
+                          new_w, top, left, stream);
 }

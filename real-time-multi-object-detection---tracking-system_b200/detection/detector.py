@@ -53,10 +53,13 @@ class Detector:
                  input_size: tuple = (640, 640), confidence: float = 0.35, iou: float = 0.45,
                  classes: Optional[list] = None, half: bool = True, device: str = "cuda:0",
                  max_det: int = 100, agnostic_nms: bool = False, *, model=None, names=None,
-                 num_classes: int = 80, warmup: bool = True) -> None:
+                 num_classes: int = 80, warmup: bool = True, auto: bool = False) -> None:
         import torch
         from .yolov8s import COCO_NAMES, YOLOv8s
         self.input_size = tuple(input_size)
+        # auto=True: LetterBox pads only to the next multiple of 32 (what ultralytics does for .pt models:
+        # 1080p -> 384 x 640, 5040 anchors); False: the square input the BASELINE configs fix (8400 anchors)
+        self.auto = bool(auto)
         self.confidence, self.iou, self.classes = confidence, iou, classes
         self.half = half and torch.cuda.is_available()
         self.device, self.max_det, self.agnostic_nms = device, max_det, agnostic_nms
@@ -90,11 +93,12 @@ class Detector:
         import torch
         key = (B, tuple(src_hw))
         if key not in self._bufs:
-            H, W = self.input_size[1], self.input_size[0]          # input_size is (w, h) like imgsz pairs
+            (H, W), geom = self._geometry(src_hw)
             A = sum((H // s) * (W // s) for s in (8, 16, 32))
             dev = self._dev
             gain, px, py = scale_params(src_hw, (H, W))
             self._bufs = {key: dict(
+                hw=(H, W), geom=geom,
                 frames=torch.empty((B, src_hw[0], src_hw[1], 3), dtype=torch.uint8, device=dev),
                 net_in=torch.empty((B, 3, H, W), dtype=self._dtype, device=dev),
                 scale=torch.tensor([[gain, px, py, src_hw[1], src_hw[0]]] * B, dtype=torch.float32, device=dev),
@@ -106,6 +110,20 @@ class Detector:
                 ws=torch.zeros(self._lib.rtm_nms_workspace_bytes(B, A), dtype=torch.uint8, device=dev))}
         return self._bufs[key]
 
+    def _geometry(self, src_hw):
+        """LetterBox.__call__ (scaleup=True, center=True): network input (H, W) and where the resized
+        source goes in it: (new_h, new_w, top, left)."""
+        h0, w0 = src_hw
+        Hf, Wf = self.input_size[1], self.input_size[0]            # input_size is (w, h) like imgsz pairs
+        r = min(Hf / h0, Wf / w0)
+        new_w, new_h = int(round(w0 * r)), int(round(h0 * r))
+        dw, dh = Wf - new_w, Hf - new_h
+        if self.auto:
+            dw, dh = dw % 32, dh % 32
+        H, W = new_h + dh, new_w + dw
+        top, left = int(round(dh / 2 - 0.1)), int(round(dw / 2 - 0.1))
+        return (H, W), (new_h, new_w, top, left)
+
     def detect(self, frame: np.ndarray) -> Detections:
         """Run inference on a single BGR frame and return ``Detections`` (detector.py:98-112)."""
         return self.detect_batch(frame[None])[0]
@@ -115,13 +133,14 @@ class Detector:
         import torch
         frames = np.ascontiguousarray(frames)
         B, h0, w0, _ = frames.shape
-        H, W = self.input_size[1], self.input_size[0]
         buf = self._buffers(B, (h0, w0))
+        (H, W), (new_h, new_w, top, left) = buf["hw"], buf["geom"]
         with torch.cuda.device(self._dev), torch.inference_mode():
             st = _lib.cuda_stream()
             buf["frames"].copy_(torch.from_numpy(frames), non_blocking=True)
-            _lib.check(self._lib.rtm_letterbox(buf["frames"].data_ptr(), B, h0, w0, w0 * 3, h0 * w0 * 3,
-                                               buf["net_in"].data_ptr(), _lib.dtype_code(self._dtype), H, W, st))
+            _lib.check(self._lib.rtm_letterbox_ex(buf["frames"].data_ptr(), B, h0, w0, w0 * 3, h0 * w0 * 3,
+                                                  buf["net_in"].data_ptr(), _lib.dtype_code(self._dtype), H, W,
+                                                  new_h, new_w, top, left, st))
             heads = [t.contiguous() for t in self.model(buf["net_in"])]
             _lib.check(self._lib.rtm_decode_nms(
                 heads[0].data_ptr(), heads[1].data_ptr(), heads[2].data_ptr(), _lib.dtype_code(heads[0].dtype),
