@@ -308,3 +308,56 @@ def test_detector_runs_the_yolov8s_stand_in(pkg, tmp_path):
         seq[-1].bias.data[:] = 0.5
     busy = det.detect(frame)
     assert 0 < len(busy) <= 100 and busy.xyxy.min() >= 0 and busy.xyxy[:, [0, 2]].max() <= 1920
+
+
+@pytest.mark.parametrize("src_hw", [(1080, 1920), (720, 1280), (500, 375), (333, 500)])
+def test_letterbox_auto_rectangle_matches_cv2_bit_exact(pkg, src_hw):
+    """LetterBox(auto=True), the variant ultralytics uses for .pt models: padding only to the next
+    multiple of 32 (1080p -> 384 x 640).  rtm_letterbox_ex takes the geometry from the caller."""
+    import torch
+    rng = np.random.default_rng(src_hw[0] + 3 * src_hw[1])
+    frames = rng.integers(0, 256, (2, *src_hw, 3), dtype=np.uint8)
+    (new_w, new_h), (top, bottom, left, right) = detect_ref.letterbox_geometry(src_hw, (640, 640), auto=True)
+    H, W = new_h + top + bottom, new_w + left + right
+    assert H % 32 == 0 and W % 32 == 0 and (H < 640 or W < 640 or src_hw[0] == src_hw[1])
+    dev = torch.device("cuda:0")
+    d_frames = torch.from_numpy(frames).to(dev)
+    out = torch.zeros(2, 3, H, W, dtype=torch.bfloat16, device=dev)
+    lib = pkg._lib.lib()
+    pkg._lib.check(lib.rtm_letterbox_ex(d_frames.data_ptr(), 2, src_hw[0], src_hw[1], src_hw[1] * 3, src_hw[0] * src_hw[1] * 3,
+                                        out.data_ptr(), pkg._lib.RTM_BF16, H, W, new_h, new_w, top, left, pkg._lib.cuda_stream()))
+    for b in range(2):
+        ref = detect_ref.preprocess(detect_ref.letterbox(frames[b], (640, 640), auto=True), "bf16")
+        assert tuple(ref.shape) == (3, H, W)
+        assert torch.equal(out[b].cpu(), ref)
+
+
+def test_detector_auto_rectangle_end_to_end(pkg):
+    """Detector(auto=True) on a 1080p frame: 384 x 640 network input, 5040 anchors, detections
+    rescaled with the rectangle's padding."""
+    import torch
+    rng = np.random.default_rng(2)
+    n_obj = 12
+    wh = np.stack([rng.uniform(40, 120, n_obj), rng.uniform(40, 120, n_obj)], 1)
+    c = np.stack([rng.uniform(80, 560, n_obj), rng.uniform(70, 310, n_obj)], 1)
+    boxes = np.concatenate([c - wh / 2, c + wh / 2], 1)
+    cls = rng.choice(np.asarray(WANTED), n_obj)
+    heads = [torch.from_numpy(t[None]) for t in pkg.synth.plant_head(rng, boxes, cls, imgsz=(384, 640), distractor_frac=0.0)]
+    assert [tuple(h.shape[2:]) for h in heads] == [(48, 80), (24, 40), (12, 20)]
+
+    class Planted(torch.nn.Module):
+        seen = None
+
+        def forward(self, x):
+            Planted.seen = x
+            return [h.to(x.device).to(x.dtype).contiguous() for h in heads]
+
+    frame = pkg.synth.synthetic_frame(rng, 1080, 1920)
+    det = pkg.Detector(None, model=Planted(), half=True, classes=WANTED, warmup=False, auto=True)
+    out = det.detect(frame)
+    assert tuple(Planted.seen.shape) == (1, 3, 384, 640)
+    assert torch.equal(Planted.seen[0].cpu(), detect_ref.preprocess(detect_ref.letterbox(frame, (640, 640), auto=True), "bf16"))
+    ref = detect_ref.detect_post([h.to(torch.bfloat16).float() for h in heads], (1080, 1920), imgsz=(384, 640), classes=WANTED)[0]
+    assert len(out) == len(ref["conf"]) > 5
+    np.testing.assert_array_equal(out.class_id, ref["cls"])
+    np.testing.assert_allclose(out.xyxy, ref["xyxy"], rtol=1e-4, atol=1e-2)
