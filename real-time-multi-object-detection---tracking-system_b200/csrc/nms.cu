@@ -193,6 +193,7 @@ struct TmaGeom {
   int stages;
   int tile_bytes;
   int pdl_wait;  // experiment switch: wait for the prerequisite grid before exiting
+  int static_rounds;  // ring rounds with the static schedule (tile = blockIdx + k * grid) before tickets take over
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -307,7 +308,7 @@ __global__ void __launch_bounds__(tma_threads(kTileW)) decode_tma_kernel(const _
   extern __shared__ __align__(128) unsigned char tile_smem[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
-  __shared__ int s_tile[kMaxStages];  // tile held by each stage, -1 = no more tiles
+  __shared__ int4 s_tile[kMaxStages];  // per stage: (stream, level, first anchor of the tile within the level, -) ; x < 0 = no more tiles
   __shared__ int s_next[kMaxStages];  // ticket drawn for the stage's next fill (producer lane only)
   using P = Pair<T>;
   constexpr int kConsumerWarps = kTileW / kAnchorsPerWarp;
@@ -341,45 +342,56 @@ __global__ void __launch_bounds__(tma_threads(kTileW)) decode_tma_kernel(const _
         const int b = t / tps, r = t - b * tps;
         const int li = r >= tb2 ? 2 : (r >= tb1 ? 1 : 0);
         const int x = (r - (li == 2 ? tb2 : (li == 1 ? tb1 : 0))) * kTileW;
-        s_tile[s] = t;
+        s_tile[s] = make_int4(b, li, x, 0);
         mbar_expect_tx(&full_bar[s], tg.tile_bytes);
         tma_load_tile(tile_smem + static_cast<size_t>(s) * tg.tile_bytes, li == 0 ? &map0 : (li == 1 ? &map1 : &map2),
                       &full_bar[s], x, b);
       };
       // first round of the ring: tiles blockIdx + k * grid, no ticket needed; the tickets of the
       // second round are drawn meanwhile (all in flight together), later ones one ring cycle ahead
-      const int dyn0 = stages * static_cast<int>(gridDim.x);
+      const int nstatic = stages * tg.static_rounds;
+      const int dyn0 = nstatic * static_cast<int>(gridDim.x);
       bool done = false;
       for (int k = 0; k < stages && !done; ++k) {
         const int t = static_cast<int>(blockIdx.x) + k * static_cast<int>(gridDim.x);
         if (t < tg.total_tiles) {
           issue(k, t);
         } else {
-          s_tile[k] = -1;
+          s_tile[k] = make_int4(-1, 0, 0, 0);
           mbar_arrive(&full_bar[k]);
           done = true;
         }
       }
       if (!done) {
+        // tiles stages .. nstatic-1 of this CTA are static too; tickets are drawn for the ones after
         int tk[kMaxStages];
 #pragma unroll
-        for (int k = 0; k < kMaxStages; ++k) tk[k] = k < stages ? atomicAdd(ws.tile_counter, 1) : 0;
+        for (int k = 0; k < kMaxStages; ++k)
+          tk[k] = (k < stages && stages + k >= nstatic) ? atomicAdd(ws.tile_counter, 1) : 0;
 #pragma unroll
         for (int k = 0; k < kMaxStages; ++k)
-          if (k < stages) s_next[k] = dyn0 + tk[k];
+          if (k < stages)
+            s_next[k] = stages + k < nstatic ? static_cast<int>(blockIdx.x) + (stages + k) * static_cast<int>(gridDim.x) : dyn0 + tk[k];
+        int issued = 2 * stages;  // tiles of this CTA that have a source by now
         int s = 0, fill = 1, drawn = 0, drawn_for = -1;  // ticket in flight and the stage it is for
         while (true) {
           mbar_wait(&empty_bar[s], (fill - 1) & 1);
           if (drawn_for >= 0) s_next[drawn_for] = dyn0 + drawn;  // arrived while the ring drained
           const int t = s_next[s];
           if (t >= tg.total_tiles) {
-            s_tile[s] = -1;
+            s_tile[s] = make_int4(-1, 0, 0, 0);
             mbar_arrive(&full_bar[s]);
             break;
           }
           issue(s, t);
-          drawn = atomicAdd(ws.tile_counter, 1);
-          drawn_for = s;
+          if (issued < nstatic) {
+            s_next[s] = static_cast<int>(blockIdx.x) + issued * static_cast<int>(gridDim.x);
+            drawn_for = -1;
+          } else {
+            drawn = atomicAdd(ws.tile_counter, 1);
+            drawn_for = s;
+          }
+          ++issued;
           if (++s == stages) {
             s = 0;
             ++fill;
@@ -405,15 +417,14 @@ __global__ void __launch_bounds__(tma_threads(kTileW)) decode_tma_kernel(const _
   int s = 0, phase = 0;
   while (true) {
     mbar_wait(&full_bar[s], phase);
-    const int t = *reinterpret_cast<volatile int*>(&s_tile[s]);
-    if (t < 0) break;
-    const int b = t / tps, r = t - b * tps;
-    const int li = r >= tb2 ? 2 : (r >= tb1 ? 1 : 0);
+    int b, li, x0;
+    asm volatile("ld.volatile.shared.v4.s32 {%0, %1, %2, _}, [%3];" : "=r"(b), "=r"(li), "=r"(x0) : "r"(smem_u32(&s_tile[s])));
+    if (b < 0) break;
     const int lv_w = li == 2 ? w2 : (li == 1 ? w1 : w0);
     const int lv_stride = li == 2 ? st2 : (li == 1 ? st1 : st0);
     const int lv_anchor0 = li == 2 ? a2 : (li == 1 ? a1 : 0);
     const int lv_hw = li == 2 ? hw2 : (li == 1 ? hw1 : hw0);
-    const int pix = (r - (li == 2 ? tb2 : (li == 1 ? tb1 : 0))) * kTileW + col;
+    const int pix = x0 + col;
     const T* tile = reinterpret_cast<const T*>(tile_smem + static_cast<size_t>(s) * tg.tile_bytes);
     const T* cls_col = tile + (kBoxCh + q) * kTileW + col;  // row of class q
 
@@ -670,6 +681,10 @@ struct Vec16<float> {
   }
 };
 
+// out of line on purpose: the exact path of decode_scan_kernel names it once per (anchor, class row)
+// of a batch, and is taken for a handful of them
+__device__ __noinline__ float sigmoidf_rn_call(float x) { return sigmoidf_rn(x); }
+
 __device__ __forceinline__ uint4 ld_stream16(const void* p) {  // read-once data: do not keep it in L1
   uint4 v;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
@@ -735,7 +750,7 @@ __global__ void __launch_bounds__(kScanThreads) decode_scan_kernel(const HeadPtr
           const int c = 4 * (i0 + i) + q;
           const float x = to_float(reinterpret_cast<const T*>(&v[i][0])[j]);
           if (c < nc && x > logit_gate) {
-            const float p = sigmoidf_rn(x);
+            const float p = sigmoidf_rn_call(x);
             if (p > best[j]) {
               best[j] = p;
               bcls[j] = c;
@@ -1015,8 +1030,9 @@ int launch_decode_tma_w(const void* p3, const void* p4, const void* p5, const He
   for (int l = 0; l < 3; ++l) tg.tiles_before[l + 1] = tg.tiles_before[l] + (g.lv[l].hw + kTileW - 1) / kTileW;
   tg.total_tiles = tg.tiles_before[3] * B;
   tg.tile_bytes = ch * kTileW * static_cast<int>(sizeof(T));
-  static const int pdl_wait_env = env_int("RTM_PDL_WAIT", 0);
+  static const int pdl_wait_env = env_int("RTM_PDL_WAIT", 0), static_env = env_int("RTM_TMA_STATIC_ROUNDS", 1);
   tg.pdl_wait = pdl_wait_env;
+  tg.static_rounds = static_env < 1 ? 1 : static_env;
   if (tg.tile_bytes % 128 != 0) return 0;
   // ring depth and residency: as many tiles in flight per SM as fit (RTM_TMA_STAGES / RTM_TMA_CTAS override)
   static const int stages_env = env_int("RTM_TMA_STAGES", 0), ctas_env = env_int("RTM_TMA_CTAS", 0);
