@@ -408,6 +408,7 @@ def run_b200(args):
                                              "steps": len(lat), "streams_per_step": S, "zone_events_emitted": ev_seen}
             if rank == 0:
                 extras["letterbox"] = letterbox_bench(pkg, lib, dev, S, hbm_peak)
+                extras["dense_crowd"] = dense_crowd_bench(pkg, dev)
 
         # ---- e2e: the same step fed from pinned HOST head tensors through the C ABI ----
         e2e = None
@@ -518,6 +519,66 @@ def e2e_bench(pkg, wl, sb, f0, K, W, total_streams, world, dev):
             "d2h_bytes_per_step": feeder.d2h_bytes, "ms_per_step": 1e3 * dt / K,
             "h2d_gbs": feeder.h2d_bytes * K / dt / 1e9,
             "api": "HostFeeder.step_pinned -> rtm_post_backbone_step_host (2 CUDA streams, H2D of step k+1 overlaps step k)"}
+
+
+def dense_crowd_bench(pkg, dev, streams=128, objects=1000, zones=16, distinct=4, frames=8, steps=48):
+    """BASELINE.json configs[4] as a side measurement: 128 streams x 1000 scripted objects (MOT20-like
+    motion) x 16 zone polygons (K in 4..12), tracker + zones only (the detector cannot emit 1000 boxes:
+    max_det = 100).  `distinct` different streams are generated and repeated to fill the batch (streams
+    are independent, so repetition changes nothing about the work); the clip runs forward then back.
+    The first frames of one stream are checked against the oracle."""
+    import numpy as np
+    import torch
+    from oracle import tracker_ref, zone_ref
+    slots = 1024
+    xyxy, conf, cls, count = pkg.synth.scripted_batch(distinct, frames, slots, seed=900, **pkg.synth.dense_crowd_kwargs(objects))
+    rep = streams // distinct
+    tile = lambda a: torch.from_numpy(np.ascontiguousarray(np.concatenate([a] * rep, axis=1))).to(dev)
+    d_xyxy, d_conf, d_cls, d_count = tile(xyxy), tile(conf), tile(cls), tile(count)
+    zcfg = [pkg.synth.make_zones(seed=b % distinct, num_zones=zones, width=1920, height=1080, kmin=4, kmax=12) for b in range(streams)]
+    order = list(range(frames)) + list(range(frames - 2, 0, -1))                 # forward, then back
+
+    def fresh():
+        return pkg.StreamBatch(streams, zcfg, src_hw=(1080, 1920), max_det=slots, max_tracks=4096, max_events=4096, device=dev)
+
+    # parity: stream 0, first frames, against the oracle
+    sb = fresh()
+    trk, zon = tracker_ref.TrackerOracle(), zone_ref.ZoneOracle(zcfg[0])
+    ok = True
+    for f in range(3):
+        now = T0 + f / FPS
+        sb.track_only(d_xyxy[f], d_conf[f], d_cls[f], d_count[f], now=now, frame_id=f)
+        n = int(count[f, 0])
+        trk.step(xyxy[f, 0, :n], conf[f, 0, :n], cls[f, 0, :n])
+        tracks, next_id = sb.read_tracks()
+        ok &= [t["track_id"] for t in tracks[0]] == trk.track_id.tolist() and int(next_id[0]) == trk.next_id
+        act = trk.active_rows()
+        exp = zon.process(zip(trk.track_id[act], trk.xyxy[act], trk.cls[act]), f, now)
+        got = sb.read_events()[0]
+        ok &= [(e.track_id, e.zone_name, e.centroid) for e in got] == [(e.track_id, e.zone_name, e.centroid) for e in exp]
+    sb.check_status()
+    # timing
+    sb = fresh()
+    k = 0
+    def go(n):
+        nonlocal k
+        for _ in range(n):
+            f = order[k % len(order)]
+            sb.track_only(d_xyxy[f], d_conf[f], d_cls[f], d_count[f], now=T0 + k / FPS, frame_id=k)
+            k += 1
+    go(8)
+    torch.cuda.synchronize(dev)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    go(steps)
+    b.record()
+    b.synchronize()
+    ms = a.elapsed_time(b) / steps
+    sb.check_status()
+    tracks, _ = sb.read_tracks()
+    return {"config": f"BASELINE.json configs[4]: {streams} streams x {objects} scripted objects, {zones} zones (K 4..12), tracker + zones "
+                      f"({distinct} distinct streams repeated)", "frames_per_s": streams / (ms * 1e-3), "ms_per_step": ms,
+            "live_tracks_per_stream": float(np.mean([len(t) for t in tracks])), "parity_ok": bool(ok), "steps": steps}
 
 
 def letterbox_bench(pkg, lib, dev, S, hbm_peak, iters=20):

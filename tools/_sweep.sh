@@ -1,7 +1,7 @@
-timeout 300 python -m pytest tests/test_gpu_pipeline.py tests/test_gpu_detect.py -x -q -m gpu 2>&1 | tail -1
-for i in 1 2; do
-python bench.py --steps 200 --warmup 20 --no-e2e --no-cpu --no-extras 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1])
-print(round(d['value']), round(d['ms_per_step']*1e3,1),'us/step', {k:round(v['avg_us'],1) for k,v in d['kernels'].items()}, d['parity']['ok'])"
-done
+python - <<'P'
+import sys, importlib, json
+sys.path.insert(0, '.')
+import torch, bench
+pkg = importlib.import_module("rtmodt_b200")
+print(json.dumps(bench.dense_crowd_bench(pkg, torch.device("cuda", 0))))
+P
