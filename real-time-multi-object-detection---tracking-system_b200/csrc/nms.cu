@@ -135,12 +135,13 @@ __device__ __forceinline__ float4 dist_to_xyxy(float l, float t, float r, float 
                                                float stride, float4* xywh) {
   const float x1 = __fsub_rn(ax, l), y1 = __fsub_rn(ay, t);
   const float x2 = __fadd_rn(ax, r), y2 = __fadd_rn(ay, b);
-  const float cx = __fmul_rn(__fdiv_rn(__fadd_rn(x1, x2), 2.f), stride);
-  const float cy = __fmul_rn(__fdiv_rn(__fadd_rn(y1, y2), 2.f), stride);
+  // x / 2 == x * 0.5f bit for bit (exact scaling by a power of two); the division sequence is ~10x the instructions
+  const float cx = __fmul_rn(__fmul_rn(__fadd_rn(x1, x2), 0.5f), stride);
+  const float cy = __fmul_rn(__fmul_rn(__fadd_rn(y1, y2), 0.5f), stride);
   const float w = __fmul_rn(__fsub_rn(x2, x1), stride);
   const float h = __fmul_rn(__fsub_rn(y2, y1), stride);
   if (xywh) *xywh = make_float4(cx, cy, w, h);
-  const float dw = __fdiv_rn(w, 2.f), dh = __fdiv_rn(h, 2.f);
+  const float dw = __fmul_rn(w, 0.5f), dh = __fmul_rn(h, 0.5f);
   return make_float4(__fsub_rn(cx, dw), __fsub_rn(cy, dh), __fadd_rn(cx, dw), __fadd_rn(cy, dh));
 }
 
@@ -193,6 +194,7 @@ struct TmaGeom {
   int stages;
   int tile_bytes;
   int pdl_wait;  // experiment switch: wait for the prerequisite grid before exiting
+  int evict_first;    // L2 evict-first hint on the tile loads
   int static_rounds;  // ring rounds with the static schedule (tile = blockIdx + k * grid) before tickets take over
 };
 
@@ -226,11 +228,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
     if (spin > (1u << 26)) __trap();
 }
-__device__ __forceinline__ void tma_load_tile(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int b) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(0), "r"(b)
-      : "memory");
+__device__ __forceinline__ void tma_load_tile(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int b,
+                                              const uint64_t policy) {
+  if (policy) {  // read-once data: L2 evict-first
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(0), "r"(b), "l"(policy)
+        : "memory");
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(0), "r"(b)
+        : "memory");
+  }
 }
 
 // two horizontally adjacent anchors of one channel row: one 4-byte (16-bit heads) or 8-byte load,
@@ -268,20 +278,42 @@ struct Pair<float> {
 // exact N1 of one anchor column for the lanes of its four class quarters: probability and index
 // of the FIRST class attaining the maximum float32 sigmoid; lanes whose quarter cannot pass
 // contribute (-1, INT_MAX).  `m` is the lane's maximum logit over its classes q, q+4, ...
-template <typename T, int kTileW>
+// The quarter's class values are read in one unrolled sweep (independent shared-memory loads) that
+// only notes which of them clear the gate - a handful at most; the sigmoid is evaluated for those,
+// in ascending class order with a strict comparison, which is torch's max(1) on the sigmoid tensor.
+template <typename T, bool NC80, int kTileW>
 __device__ __forceinline__ void anchor_best(const T* cls_col, const int q, const int iters, const int nc, const float m,
                                             const float logit_gate, float* best, int* bc) {
   float sc = -1.f;
   int j = 0x7fffffff;
   if (m > logit_gate) {
-    sc = sigmoidf_rn(m);
-    for (int i = 0; i < iters; ++i) {
+    unsigned bits = 0u;
+    if (NC80) {
+#pragma unroll
+      for (int i = 0; i < 20; ++i) bits |= (to_float(cls_col[(4 * i + q) * kTileW]) > logit_gate ? 1u : 0u) << i;
+    } else {
+      for (int i = 0; i < iters && i < 32; ++i)
+        if (4 * i + q < nc) bits |= (to_float(cls_col[(4 * i + q) * kTileW]) > logit_gate ? 1u : 0u) << i;
+    }
+    while (bits) {
+      const int i = __ffs(bits) - 1;
+      bits &= bits - 1;
+      const float p = sigmoidf_rn(to_float(cls_col[(4 * i + q) * kTileW]));
+      if (p > sc) {
+        sc = p;
+        j = 4 * i + q;
+      }
+    }
+    for (int i = 32; i < iters; ++i) {  // nc > 128: the classes the bitmask does not cover
       const int c = 4 * i + q;
       if (c < nc) {
         const float v = to_float(cls_col[c * kTileW]);
-        if (v > logit_gate && sigmoidf_rn(v) == sc) {
-          j = c;
-          break;
+        if (v > logit_gate) {
+          const float p = sigmoidf_rn(v);
+          if (p > sc) {
+            sc = p;
+            j = c;
+          }
         }
       }
     }
@@ -338,6 +370,8 @@ __global__ void __launch_bounds__(tma_threads(kTileW)) decode_tma_kernel(const _
   if (warp == kConsumerWarps) {
     // ===== producer warp: one elected lane keeps the ring full =====
     if (lane == 0) {
+      uint64_t policy = 0;
+      if (tg.evict_first) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
       auto issue = [&](int s, int t) {
         const int b = t / tps, r = t - b * tps;
         const int li = r >= tb2 ? 2 : (r >= tb1 ? 1 : 0);
@@ -345,7 +379,7 @@ __global__ void __launch_bounds__(tma_threads(kTileW)) decode_tma_kernel(const _
         s_tile[s] = make_int4(b, li, x, 0);
         mbar_expect_tx(&full_bar[s], tg.tile_bytes);
         tma_load_tile(tile_smem + static_cast<size_t>(s) * tg.tile_bytes, li == 0 ? &map0 : (li == 1 ? &map1 : &map2),
-                      &full_bar[s], x, b);
+                      &full_bar[s], x, b, policy);
       };
       // first round of the ring: tiles blockIdx + k * grid, no ticket needed; the tickets of the
       // second round are drawn meanwhile (all in flight together), later ones one ring cycle ahead
@@ -450,8 +484,8 @@ __global__ void __launch_bounds__(tma_threads(kTileW)) decode_tma_kernel(const _
       // ---- exact N1 for the anchors that can pass, then D1 for the survivors ----
       float best0, best1;
       int bc0, bc1;
-      anchor_best<T, kTileW>(tile + kBoxCh * kTileW + col, q, iters, nc, m0, logit_gate, &best0, &bc0);
-      anchor_best<T, kTileW>(tile + kBoxCh * kTileW + col + 1, q, iters, nc, m1, logit_gate, &best1, &bc1);
+      anchor_best<T, NC80, kTileW>(tile + kBoxCh * kTileW + col, q, iters, nc, m0, logit_gate, &best0, &bc0);
+      anchor_best<T, NC80, kTileW>(tile + kBoxCh * kTileW + col + 1, q, iters, nc, m1, logit_gate, &best1, &bc1);
       cand0 = best0 > prm.conf_thres && class_wanted(prm, bc0 & 255);
       cand1 = best1 > prm.conf_thres && class_wanted(prm, bc1 & 255);
       if (__any_sync(kFull, cand0 || cand1)) {
@@ -1019,9 +1053,14 @@ int launch_decode_tma_w(const void* p3, const void* p4, const void* p5, const He
     const cuuint32_t box[3] = {kTileW, static_cast<cuuint32_t>(ch), 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     if (ch > 256 || (strides[0] & 15) != 0) return 0;
+    static const int promo_env = env_int("RTM_TMA_L2PROMO", 3);  // 0 none, 1 64B, 2 128B, 3 256B
+    const CUtensorMapL2promotion promo = promo_env == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                         : promo_env == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                         : promo_env == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                                          : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
     const CUresult r = encode(&maps[l], tensor_map_dtype<T>(), 3, const_cast<void*>(ptrs[l]), dims, strides, box, estr,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return 0;
   }
   TmaGeom tg;
@@ -1033,6 +1072,8 @@ int launch_decode_tma_w(const void* p3, const void* p4, const void* p5, const He
   static const int pdl_wait_env = env_int("RTM_PDL_WAIT", 0), static_env = env_int("RTM_TMA_STATIC_ROUNDS", 1);
   tg.pdl_wait = pdl_wait_env;
   tg.static_rounds = static_env < 1 ? 1 : static_env;
+  static const int evict_env = env_int("RTM_TMA_EVICT_FIRST", 1);
+  tg.evict_first = evict_env;
   if (tg.tile_bytes % 128 != 0) return 0;
   // ring depth and residency: as many tiles in flight per SM as fit (RTM_TMA_STAGES / RTM_TMA_CTAS override)
   static const int stages_env = env_int("RTM_TMA_STAGES", 0), ctas_env = env_int("RTM_TMA_CTAS", 0);
@@ -1068,7 +1109,8 @@ int launch_decode_tma_w(const void* p3, const void* p4, const void* p5, const He
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = (rtm::pdl_enabled() && !rtm::g_profile_on) ? 1 : 0;
-    const float gate = logit_gate_for(prm.conf_thres);
+    static const int dry = env_int("RTM_SCAN_DRY", 0);  // timing experiment: nothing passes the gate
+    const float gate = dry ? FLT_MAX : logit_gate_for(prm.conf_thres);
     if (g.num_classes == 80)
       RTM_CUDA(cudaLaunchKernelEx(&cfg, decode_tma_kernel<T, true, kTileW>, maps[0], maps[1], maps[2], tg, prm, gate, ws));
     else

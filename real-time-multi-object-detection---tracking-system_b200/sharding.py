@@ -11,7 +11,7 @@ from __future__ import annotations
 
 from typing import Sequence
 
-COUNTERS = ("frames", "detections", "births", "events")
+COUNTERS = ("frames", "detections_last_step", "births", "events_last_step")
 
 
 def shard_streams(total_streams: int, world_size: int, rank: int) -> range:
