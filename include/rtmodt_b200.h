@@ -102,7 +102,12 @@ typedef struct rtm_nms_params {
   uint32_t class_mask[8]; /* bit c set = class c wanted (`classes=` argument; all ones = None) */
 } rtm_nms_params;
 
-/* bytes of scratch rtm_decode_nms / rtm_nms_pred need for num_streams streams of num_anchors */
+/* bytes of scratch rtm_decode_nms / rtm_nms_pred / rtm_post_backbone_step need for num_streams
+ * streams of num_anchors.  The workspace holds a ring of candidate lists (consecutive calls with the
+ * same workspace rotate through it, which is what allows the head scan of one step to overlap the
+ * post kernel of the step before) and a small header of tile counters.  Give every stream batch its
+ * own workspace, 256-byte aligned, and hand it over zero-filled (the library clears the header the
+ * first time it sees a workspace address; do not let other data live at that address in between). */
 size_t rtm_nms_workspace_bytes(int32_t num_streams, int32_t num_anchors);
 
 /*

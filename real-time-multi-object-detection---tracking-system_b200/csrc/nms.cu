@@ -37,7 +37,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include <unordered_set>
+#include <unordered_map>
 
 #include "nms_body.cuh"
 
@@ -1215,16 +1215,22 @@ int rtm::launch_decode_stage(const void* head_p3, const void* head_p4, const voi
   HeadGeom g;
   int rc = make_geom(img_h, img_w, params->num_classes, &g);
   if (rc) return rc;
-  // consecutive scans take consecutive candidate-list slots of the workspace
-  static int half = 0;
-  half = (half + 1) % kCandSlots;
+  // Consecutive scans of one workspace take consecutive candidate-list slots (kept per workspace, so
+  // that several stream batches, each with its own workspace and CUDA stream, can be interleaved).
+  // The ticket counters must start at zero: the header is cleared the first time a workspace is seen;
+  // afterwards every NMS stage leaves the counter of the slot it consumed at zero.
+  static std::unordered_map<const void*, int> next_slot;
+  auto it = next_slot.find(workspace);
+  if (it == next_slot.end()) {
+    RTM_REQUIRE(workspace_bytes >= kWorkspaceHeader, "workspace too small");
+    RTM_CUDA(cudaMemsetAsync(workspace, 0, kWorkspaceHeader, s));
+    it = next_slot.emplace(workspace, 0).first;
+  }
+  const int half = it->second;
+  it->second = (half + 1) % kCandSlots;
   const size_t need = workspace_layout(num_streams, g.num_anchors, static_cast<char*>(workspace), ws, half);
   RTM_REQUIRE(workspace_bytes >= need, "workspace has %zu bytes, %zu needed", workspace_bytes, need);
   RTM_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
-  // the ticket counters must start at zero: clear the header the first time a workspace is seen
-  // (afterwards every NMS stage leaves the counter of the half it consumed at zero)
-  static std::unordered_set<const void*> seen;
-  if (seen.insert(workspace).second) RTM_CUDA(cudaMemsetAsync(workspace, 0, kWorkspaceHeader, s));
   switch (head_dtype) {
     case RTM_F32:
       return launch_decode<float>(head_p3, head_p4, head_p5, g, num_streams, *params, *ws, s);

@@ -145,3 +145,40 @@ def test_back_to_back_steps_equal_synchronised_steps(pkg, S):
         assert ref["det_count"].sum() > 0 and ref["count"].sum() > 0
         for attempt in range(3):                   # overlap is timing dependent: look more than once
             same(ref, run(False, steps))
+
+
+def test_interleaved_stream_batches_do_not_disturb_each_other(pkg):
+    """Three stream batches (own workspaces) stepped round-robin without synchronisation end in the
+    state each reaches when it runs alone: the candidate-list slots rotate per workspace."""
+    import torch
+    from rtmodt_b200.workload import PostBackboneWorkload
+    dev = torch.device("cuda", 0)
+    S, F, steps = 8, 6, 40
+    wls = [PostBackboneWorkload(S, F, first_stream=100 * k, device=dev, dtype=torch.bfloat16) for k in range(3)]
+
+    def make(k):
+        return pkg.StreamBatch(S, wls[k].zones, src_hw=(1080, 1920), classes=WANTED, max_tracks=512, device=dev)
+
+    def final(sb):
+        torch.cuda.synchronize()
+        sb.check_status()
+        h = sb.table.to_host()
+        return h["count"].copy(), h["next_id"].copy(), [h["track_id"][b, :h["count"][b]].copy() for b in range(S)], \
+            [h["xyxy"][b, :h["count"][b]].copy() for b in range(S)]
+
+    alone = []
+    for k in range(3):
+        sb = make(k)
+        for f in range(steps):
+            sb.step(wls[k].heads[f % F], now=1.7e9 + f / 30.0, frame_id=f)
+            torch.cuda.synchronize()
+        alone.append(final(sb))
+    batches = [make(k) for k in range(3)]
+    for f in range(steps):
+        for k in range(3):
+            batches[k].step(wls[k].heads[f % F], now=1.7e9 + f / 30.0, frame_id=f)
+    for k in range(3):
+        got = final(batches[k])
+        assert np.array_equal(got[0], alone[k][0]) and np.array_equal(got[1], alone[k][1])
+        for a, b in zip(got[2] + got[3], alone[k][2] + alone[k][3]):
+            np.testing.assert_array_equal(a, b)
