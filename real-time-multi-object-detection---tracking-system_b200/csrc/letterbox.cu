@@ -18,6 +18,8 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "rtm_common.cuh"
 
@@ -86,6 +88,10 @@ struct alignas(sizeof(T) * kPix) OutPack {
 
 template <typename T>
 __global__ void __launch_bounds__(256) letterbox_kernel(const LetterboxArgs a) {
+  // u8 -> T(v / 255) for the 256 possible values, one IEEE division each instead of one per pixel
+  __shared__ T s_lut[256];
+  s_lut[threadIdx.x] = from_u8<T>(threadIdx.x);
+  __syncthreads();
   const int groups_per_row = a.out_w / kPix;
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= groups_per_row * a.out_h) return;
@@ -140,9 +146,81 @@ __global__ void __launch_bounds__(256) letterbox_kernel(const LetterboxArgs a) {
   for (int c = 0; c < 3; ++c) {
     OutPack<T> p;
 #pragma unroll
-    for (int e = 0; e < kPix; ++e) p.v[e] = from_u8<T>(px[c][e]);
+    for (int e = 0; e < kPix; ++e) p.v[e] = s_lut[px[c][e]];
     *reinterpret_cast<OutPack<T>*>(out + static_cast<long long>(c) * a.out_h * a.out_w) = p;
   }
+}
+
+// 3 : 1 decimation (1080p -> 640 x 360 inside 640 x 640, the BASELINE configuration): OpenCV's
+// fixed-point bilinear lands exactly on source pixel (3 rx + 1, 3 ry + 1) with unit weight, so the
+// resize is a strided gather.  A thread produces 16 consecutive output pixels: their 48 source bytes
+// lie in a 138-byte span that starts 3 bytes into a 16-byte aligned block (9 * 16 g + 3), fetched as
+// nine aligned 16-byte loads; every byte is then picked with a compile-time word index and shift.
+// The host checks the geometry (taps, alignment) before choosing this kernel.
+constexpr int kDecPix = 16;
+template <typename T>
+__global__ void __launch_bounds__(256) letterbox_decimate3_kernel(const LetterboxArgs a) {
+  __shared__ T s_lut[256];
+  s_lut[threadIdx.x] = from_u8<T>(threadIdx.x);
+  __syncthreads();
+  const int groups_per_row = a.out_w / kDecPix;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= groups_per_row * a.out_h) return;
+  const int b = blockIdx.y;
+  const int oy = g / groups_per_row;
+  const int ox0 = (g - oy * groups_per_row) * kDecPix;
+  const int ry = oy - a.top, rx0 = ox0 - a.left;
+  T* out = static_cast<T*>(a.out) + (static_cast<long long>(b) * 3 * a.out_h + oy) * a.out_w + ox0;
+  const long long plane = static_cast<long long>(a.out_h) * a.out_w;
+  using Pack = OutPack<T>;  // 8 values
+  if (ry < 0 || ry >= a.new_h || rx0 < 0 || rx0 >= a.new_w) {  // whole groups are inside or outside (host-checked)
+    Pack p;
+#pragma unroll
+    for (int e = 0; e < kPix; ++e) p.v[e] = s_lut[114];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      *reinterpret_cast<Pack*>(out + c * plane) = p;
+      *reinterpret_cast<Pack*>(out + c * plane + kPix) = p;
+    }
+    return;
+  }
+  const uint8_t* row = a.frames + static_cast<long long>(b) * a.frame_stride + static_cast<long long>(3 * ry + 1) * a.row_stride;
+  const uint4* src = reinterpret_cast<const uint4*>(row + 9 * rx0);  // 9 * 16 g: 16-byte aligned; first tap at byte 3
+  uint32_t w[36];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const uint4 v = __ldg(src + k);
+    w[4 * k] = v.x;
+    w[4 * k + 1] = v.y;
+    w[4 * k + 2] = v.z;
+    w[4 * k + 3] = v.w;
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {  // c: B, G, R in the source -> plane 2 - c
+    Pack lo, hi;
+#pragma unroll
+    for (int e = 0; e < kDecPix; ++e) {
+      const int o = 3 + 9 * e + c;  // byte offset inside the span: compile-time
+      const T val = s_lut[(w[o >> 2] >> ((o & 3) * 8)) & 0xffu];
+      if (e < kPix) lo.v[e] = val;
+      else hi.v[e - kPix] = val;
+    }
+    *reinterpret_cast<Pack*>(out + (2 - c) * plane) = lo;
+    *reinterpret_cast<Pack*>(out + (2 - c) * plane + kPix) = hi;
+  }
+}
+
+// host copy of linear_tap (same IEEE operations) to recognise the pure 3 : 1 decimation
+bool taps_are_decimate3(int dst, double scale, int ssize, bool horizontal) {
+  for (int d = 0; d < dst; ++d) {
+    float f = static_cast<float>((d + 0.5) * scale - 0.5);
+    int s = static_cast<int>(floorf(f));
+    f -= static_cast<float>(s);
+    if (horizontal && (s < 0 || s >= ssize - 1)) return false;
+    const int c1 = static_cast<int>(nearbyintf(f * 2048.f)), c0 = static_cast<int>(nearbyintf((1.f - f) * 2048.f));
+    if (s != 3 * d + 1 || c1 != 0 || c0 != 2048) return false;
+  }
+  return true;
 }
 
 }  // namespace
@@ -181,6 +259,30 @@ int launch_letterbox(const uint8_t* frames, int num_streams, int src_h, int src_
   dim3 grid((groups + 255) / 256, num_streams);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   rtm::ProfileScope prof(RTM_K_LETTERBOX, s);
+  // 3 : 1 decimation fast path (RTM_LETTERBOX_IMPL=direct turns it off)
+  static const bool allow_fast = !(getenv("RTM_LETTERBOX_IMPL") && strcmp(getenv("RTM_LETTERBOX_IMPL"), "direct") == 0);
+  if (allow_fast && a.resize && src_w == 3 * new_w && src_h == 3 * new_h && out_w % kDecPix == 0 && left % kDecPix == 0 &&
+      new_w % kDecPix == 0 && (reinterpret_cast<uintptr_t>(frames) & 15) == 0 && row_stride % 16 == 0 && frame_stride % 16 == 0 &&
+      row_stride >= 9ll * new_w && taps_are_decimate3(new_w, a.scale_x, src_w, true) &&
+      taps_are_decimate3(new_h, a.scale_y, src_h, false)) {
+    const int dgroups = (out_w / kDecPix) * out_h;
+    dim3 dgrid((dgroups + 255) / 256, num_streams);
+    switch (out_dtype) {
+      case RTM_F32:
+        letterbox_decimate3_kernel<float><<<dgrid, 256, 0, s>>>(a);
+        break;
+      case RTM_F16:
+        letterbox_decimate3_kernel<__half><<<dgrid, 256, 0, s>>>(a);
+        break;
+      case RTM_BF16:
+        letterbox_decimate3_kernel<__nv_bfloat16><<<dgrid, 256, 0, s>>>(a);
+        break;
+      default:
+        RTM_REQUIRE(false, "rtm_letterbox: unknown out_dtype %d", out_dtype);
+    }
+    RTM_LAUNCH_CHECK("letterbox_decimate3_kernel");
+    return RTM_OK;
+  }
   switch (out_dtype) {
     case RTM_F32:
       letterbox_kernel<float><<<grid, 256, 0, s>>>(a);
