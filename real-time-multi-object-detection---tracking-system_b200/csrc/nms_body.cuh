@@ -668,10 +668,17 @@ __device__ __forceinline__ int nms_run(const Workspace& ws, const rtm_nms_params
 // One stream.  `smem` = kNmsSmemBytes of dynamic shared memory, `s_keep` = kMaxDetCap ints,
 // `s_scan` = 33 ints.  All THREADS threads of the block must call it.  On return (after a
 // trailing __syncthreads) s_keep[0..kept) and the output slabs are written; returns kept.
-template <int THREADS>
+struct NoPrologue {
+  __device__ __forceinline__ void operator()() const {}
+};
+
+// `prologue` runs right after the stream's mask words have been requested and before anything waits
+// for them: the fused kernel hangs its table prefetches there, so that their load chains and the
+// mask load travel together.
+template <int THREADS, typename Prologue = NoPrologue>
 __device__ __forceinline__ int nms_stream(const Workspace& ws, const rtm_nms_params& prm, const float iou_gate,
                                           const NmsOut& out, const int b, unsigned char* smem, int* s_keep,
-                                          int* s_scan) {
+                                          int* s_scan, Prologue prologue = Prologue()) {
   const int tid = threadIdx.x;
   const int A = ws.num_anchors, W = ws.words;
   const uint32_t* mask = ws.mask + static_cast<size_t>(b) * W;
@@ -683,16 +690,18 @@ __device__ __forceinline__ int nms_stream(const Workspace& ws, const rtm_nms_par
   int n = 0;
 #pragma unroll
   for (int it = 0; it < kIters; ++it) {
-    mw[it] = 0u;
+    const int w = it * THREADS + tid;
+    mw[it] = w < W ? mask[w] : 0u;
+  }
+  prologue();
+#pragma unroll
+  for (int it = 0; it < kIters; ++it) {
     rb[it] = 0;
     if (it * THREADS < W) {  // block-uniform
       const int w = it * THREADS + tid;
-      uint32_t m = 0u;
-      if (w < W) {
-        m = mask[w];
-        const int valid = A - (w << 5);
-        if (valid < 32) m &= (1u << valid) - 1u;
-      }
+      uint32_t m = mw[it];
+      const int valid = A - (w << 5);
+      if (w < W && valid < 32) m &= (1u << valid) - 1u;
       int tot;
       rb[it] = n + block_exclusive_sum(__popc(m), s_scan, &tot);
       mw[it] = m;

@@ -48,10 +48,12 @@ __global__ void __launch_bounds__(kPostThreads, 1) post_kernel(const __grid_cons
   // waits for the scan to complete.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   RTM_TL(0);
-  if (a.has_zones) rtm::zone_prefetch<kPostThreads>(a.zone, b, zpf);
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  rtm::track_prefetch<kPostThreads>(a.trk, b, tpf);
-  rtm::nms_stream<kPostThreads>(a.ws, a.prm, a.iou_gate, a.out, b, smem_raw, s_keep, s_scan);  // ends with a barrier
+  auto prefetch = [&]() {
+    if (a.has_zones) rtm::zone_prefetch<kPostThreads>(a.zone, b, zpf);
+    rtm::track_prefetch<kPostThreads>(a.trk, b, tpf);
+  };
+  rtm::nms_stream<kPostThreads>(a.ws, a.prm, a.iou_gate, a.out, b, smem_raw, s_keep, s_scan, prefetch);  // ends with a barrier
   RTM_TL(10);
   rtm::track_stream<kPostThreads>(a.trk, b, smem_raw, tpf);
   __syncthreads();

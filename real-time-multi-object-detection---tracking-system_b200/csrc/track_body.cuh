@@ -205,8 +205,9 @@ __device__ __forceinline__ void associate(const TrackPrefetch* pf, const float4*
   const int tid = threadIdx.x;
   for (int j = tid; j < m; j += THREADS) s_win[j] = INT_MAX;
   __syncthreads();
-  int G = 4;
-  while (G < 32 && G < m) G <<= 1;
+  // lanes per row: few enough that the rows of a typical table (a few hundred) keep all groups busy,
+  // enough that a lane's share of the columns stays short
+  const int G = m <= 8 ? 4 : (m <= 64 ? 8 : (m <= 256 ? 16 : 32));
   const int sub = tid & (G - 1), groups = THREADS / G;
   // every lane of a warp runs the same number of rounds (shuffles need the whole warp)
   for (int t0 = 0; t0 < T; t0 += groups) {
@@ -367,8 +368,7 @@ __device__ __forceinline__ int associate_optimal(const TrackPrefetch* pf, const 
   }
   __syncthreads();
   // ---- 1. admissible pairs ----
-  int G = 4;
-  while (G < 32 && G < m) G <<= 1;
+  const int G = m <= 8 ? 4 : (m <= 64 ? 8 : (m <= 256 ? 16 : 32));
   const int sub = tid & (G - 1), groups = THREADS / G;
   for (int t0 = 0; t0 < T; t0 += groups) {
     const int t = t0 + tid / G;

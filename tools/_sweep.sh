@@ -1,12 +1,6 @@
-timeout 300 python -m pytest tests/test_gpu_detect.py -x -q -m gpu -k "letterbox or detector" 2>&1 | tail -2
-for impl in fast direct; do
-RTM_LETTERBOX_IMPL=$impl python - <<'P'
-import sys, importlib, json, os
-sys.path.insert(0, '.')
-import torch, bench
-pkg = importlib.import_module("rtmodt_b200")
-dev = torch.device("cuda", 0)
-r = bench.letterbox_bench(pkg, pkg._lib.lib(), dev, 64, 6549.4)
-print(os.environ.get("RTM_LETTERBOX_IMPL"), {k: (round(v, 3) if isinstance(v, float) else v) for k, v in r.items()})
-P
-done
+timeout 600 python -m pytest tests -x -q -m gpu 2>&1 | tail -2
+timeout 200 python tools/post_timeline.py 48 | grep -E "count|stage 1|stage 2|whole"
+python bench.py --steps 200 --warmup 20 --no-e2e --no-cpu 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1])
+print(round(d['value']), round(d['ms_per_step']*1e3,1),'us/step', {k:round(v['avg_us'],1) for k,v in d['kernels'].items()}, d['parity']['ok'], d['latency_ms_per_step'])"
