@@ -482,10 +482,54 @@ __global__ void __launch_bounds__(tma_threads(kTileW)) decode_tma_kernel(const _
     bool cand0 = false, cand1 = false;
     if (__any_sync(kFull, am > logit_gate)) {
       // ---- exact N1 for the anchors that can pass, then D1 for the survivors ----
-      float best0, best1;
-      int bc0, bc1;
-      anchor_best<T, NC80, kTileW>(tile + kBoxCh * kTileW + col, q, iters, nc, m0, logit_gate, &best0, &bc0);
-      anchor_best<T, NC80, kTileW>(tile + kBoxCh * kTileW + col + 1, q, iters, nc, m1, logit_gate, &best1, &bc1);
+      float best0 = -1.f, best1 = -1.f;
+      int bc0 = 0x7fffffff, bc1 = 0x7fffffff;
+      if (NC80) {
+        // both anchors of the lane in one sweep: a packed load yields the two class values of a row
+        if (m0 > logit_gate || m1 > logit_gate) {
+          unsigned bits0 = 0u, bits1 = 0u;
+#pragma unroll
+          for (int i = 0; i < 20; ++i) {
+            const typename P::V v = P::load(cls_col + 4 * i * kTileW);
+            bits0 |= (P::lo(v) > logit_gate ? 1u : 0u) << i;
+            bits1 |= (P::hi(v) > logit_gate ? 1u : 0u) << i;
+          }
+          while (bits0) {  // ascending classes, strict >: the first maximum (torch's max(1) on the sigmoid tensor)
+            const int i = __ffs(bits0) - 1;
+            bits0 &= bits0 - 1;
+            const float p = sigmoidf_rn(to_float(cls_col[4 * i * kTileW]));
+            if (p > best0) {
+              best0 = p;
+              bc0 = 4 * i + q;
+            }
+          }
+          while (bits1) {
+            const int i = __ffs(bits1) - 1;
+            bits1 &= bits1 - 1;
+            const float p = sigmoidf_rn(to_float(cls_col[4 * i * kTileW + 1]));
+            if (p > best1) {
+              best1 = p;
+              bc1 = 4 * i + q;
+            }
+          }
+        }
+#pragma unroll
+        for (int d = 8; d <= 16; d <<= 1) {
+          const float ob0 = __shfl_xor_sync(kFull, best0, d), ob1 = __shfl_xor_sync(kFull, best1, d);
+          const int oc0 = __shfl_xor_sync(kFull, bc0, d), oc1 = __shfl_xor_sync(kFull, bc1, d);
+          if (ob0 > best0 || (ob0 == best0 && oc0 < bc0)) {
+            best0 = ob0;
+            bc0 = oc0;
+          }
+          if (ob1 > best1 || (ob1 == best1 && oc1 < bc1)) {
+            best1 = ob1;
+            bc1 = oc1;
+          }
+        }
+      } else {
+        anchor_best<T, NC80, kTileW>(tile + kBoxCh * kTileW + col, q, iters, nc, m0, logit_gate, &best0, &bc0);
+        anchor_best<T, NC80, kTileW>(tile + kBoxCh * kTileW + col + 1, q, iters, nc, m1, logit_gate, &best1, &bc1);
+      }
       cand0 = best0 > prm.conf_thres && class_wanted(prm, bc0 & 255);
       cand1 = best1 > prm.conf_thres && class_wanted(prm, bc1 & 255);
       if (__any_sync(kFull, cand0 || cand1)) {
