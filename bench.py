@@ -409,6 +409,7 @@ def run_b200(args):
             if rank == 0:
                 extras["letterbox"] = letterbox_bench(pkg, lib, dev, S, hbm_peak)
                 extras["dense_crowd"] = dense_crowd_bench(pkg, dev)
+                extras["opt_in_modes"] = modes_bench(pkg, wl, dev, S, F)
 
         # ---- e2e: the same step fed from pinned HOST head tensors through the C ABI ----
         e2e = None
@@ -519,6 +520,28 @@ def e2e_bench(pkg, wl, sb, f0, K, W, total_streams, world, dev):
             "d2h_bytes_per_step": feeder.d2h_bytes, "ms_per_step": 1e3 * dt / K,
             "h2d_gbs": feeder.h2d_bytes * K / dt / 1e9,
             "api": "HostFeeder.step_pinned -> rtm_post_backbone_step_host (2 CUDA streams, H2D of step k+1 overlaps step k)"}
+
+
+def modes_bench(pkg, wl, dev, S, F, steps=100):
+    """The same workload with the tracker's opt-in modes (neither is the reference's default behaviour
+    here): use_kalman=True (fused path) and assignment="lapjv" (three launches per step)."""
+    import torch
+    out = {}
+    for name, kw in (("kalman", dict(use_kalman=True)), ("lapjv", dict(assignment="lapjv"))):
+        sb = pkg.StreamBatch(S, wl.zones, src_hw=(1080, 1920), classes=WANTED, max_tracks=512, device=dev, **kw)
+        for f in range(20):
+            sb.step(wl.heads[f % F], now=T0 + f / FPS, frame_id=f)
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for f in range(20, 20 + steps):
+            sb.step(wl.heads[f % F], now=T0 + f / FPS, frame_id=f)
+        b.record()
+        b.synchronize()
+        sb.check_status()
+        ms = a.elapsed_time(b) / steps
+        out[name] = {"frames_per_s": S / (ms * 1e-3), "ms_per_step": ms}
+    return out
 
 
 def dense_crowd_bench(pkg, dev, streams=128, objects=1000, zones=16, distinct=4, frames=8, steps=48):
