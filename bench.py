@@ -243,17 +243,20 @@ def _reference_worker(args):
     for f in range(warmup):
         one(f)
     # file-based barrier: all workers start the timed region together
+    # NB: the zone engine's clock is injected by replacing time.time (zone_engine.py:84 reads it), which is the
+    # process-wide function - wall time is therefore taken from the monotonic clock (system-wide on Linux, so
+    # the workers' readings are comparable)
     open(f"{barrier_path}.{streams[0]}", "w").close()
-    deadline = time.time() + 600
+    deadline = time.monotonic() + 600
     want = int(open(barrier_path).read())
     while len([n for n in os.listdir(os.path.dirname(barrier_path)) if n.startswith(os.path.basename(barrier_path) + ".")]) < want:
-        if time.time() > deadline:
+        if time.monotonic() > deadline:
             raise RuntimeError("reference arm: workers did not reach the barrier")
         time.sleep(0.005)
-    t0 = time.time()
+    t0 = time.monotonic()
     for f in range(warmup, warmup + steps):
         one(f)
-    t1 = time.time()
+    t1 = time.monotonic()
     return t0, t1, len(streams) * steps, dets, evs, ref is not None
 
 

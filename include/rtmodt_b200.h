@@ -313,6 +313,10 @@ typedef struct rtm_step_io {
   /* opt-in motion model of the tracker stage (see rtm_track_step_ex); NULL = the reference */
   const rtm_kalman_state* kalman_in;
   const rtm_kalman_state* kalman_out;
+  /* tracker assignment rule, RTM_ASSIGN_* (0 = greedy, what the reference runs without `lap`), and
+   * lap's cost_limit for RTM_ASSIGN_OPTIMAL (see rtm_track_options) */
+  int32_t assignment;
+  double cost_limit;
 } rtm_step_io;
 
 int rtm_post_backbone_step(const rtm_step_io* io, const rtm_nms_params* params,

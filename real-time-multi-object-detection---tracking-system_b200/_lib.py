@@ -114,6 +114,7 @@ class StepIO(C.Structure):
         ("frame_id", C.c_int32), ("events", C.c_void_p), ("event_stride", C.c_int32),
         ("event_count", C.c_void_p), ("status", C.c_void_p),
         ("kalman_in", C.POINTER(KalmanState)), ("kalman_out", C.POINTER(KalmanState)),
+        ("assignment", C.c_int32), ("cost_limit", C.c_double),
     ]
 
 

@@ -31,6 +31,7 @@ struct PostArgs {
   int work_bytes;  // shared memory the three stages alias; the prefetch areas follow it
 };
 
+template <bool WITH_OPTIMAL>
 __global__ void __launch_bounds__(kPostThreads, 1) post_kernel(const __grid_constant__ PostArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_keep[rtm::kMaxDetCap];
@@ -55,7 +56,7 @@ __global__ void __launch_bounds__(kPostThreads, 1) post_kernel(const __grid_cons
   };
   rtm::nms_stream<kPostThreads>(a.ws, a.prm, a.iou_gate, a.out, b, smem_raw, s_keep, s_scan, prefetch);  // ends with a barrier
   RTM_TL(10);
-  rtm::track_stream<kPostThreads>(a.trk, b, smem_raw, tpf);
+  rtm::track_stream<kPostThreads, WITH_OPTIMAL>(a.trk, b, smem_raw, tpf);
   __syncthreads();
   RTM_TL(20);
   if (a.has_zones) rtm::zone_stream<kPostThreads>(a.zone, b, smem_raw, s_scan, zpf);
@@ -91,7 +92,9 @@ extern "C" int rtm_post_backbone_step(const rtm_step_io* io, const rtm_nms_param
   const int B = io->table_in->num_streams;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
 
-  const size_t track_smem = rtm::track_smem_bytes(io->det_stride, io->table_in->capacity);
+  const bool optimal = io->assignment == RTM_ASSIGN_OPTIMAL;
+  RTM_REQUIRE(io->assignment == RTM_ASSIGN_GREEDY || optimal, "rtm_post_backbone_step: unknown assignment mode %d", io->assignment);
+  const size_t track_smem = rtm::track_smem_bytes(io->det_stride, io->table_in->capacity, optimal);
   size_t work = rtm::kNmsSmemBytes;
   if (track_smem > work) work = track_smem;
   if (io->zones && rtm::zone_smem_bytes(io->event_stride) > work) work = rtm::zone_smem_bytes(io->event_stride);
@@ -104,8 +107,8 @@ extern "C" int rtm_post_backbone_step(const rtm_step_io* io, const rtm_nms_param
                             io->scale, io->det_xyxy, io->det_conf, io->det_cls, io->det_anchor, io->det_keep,
                             io->det_count, io->det_stride, io->status, io->workspace, io->workspace_bytes, stream);
     if (rc) return rc;
-    const rtm_track_options opt{io->track_thresh, io->match_thresh, io->track_buffer, RTM_ASSIGN_GREEDY, io->kalman_in,
-                                io->kalman_out, 0.0};
+    const rtm_track_options opt{io->track_thresh, io->match_thresh, io->track_buffer, io->assignment, io->kalman_in,
+                                io->kalman_out, io->cost_limit};
     rc = rtm_track_step_ex(io->table_in, io->table_out, io->det_xyxy, io->det_conf, io->det_cls, io->det_count,
                            io->det_stride, &opt, io->det_track_id, io->det_kind, io->src_row, io->status, stream);
     if (rc) return rc;
@@ -145,7 +148,7 @@ extern "C" int rtm_post_backbone_step(const rtm_step_io* io, const rtm_nms_param
   a.trk = rtm::TrackArgs{*io->table_in, *io->table_out, io->det_xyxy, io->det_conf, io->det_cls, io->det_count,
                          io->det_stride, io->track_thresh, io->match_thresh, io->track_buffer, io->det_track_id,
                          io->det_kind, io->src_row, io->status,
-                         nullptr, nullptr, nullptr, nullptr, RTM_ASSIGN_GREEDY, 0.0};
+                         nullptr, nullptr, nullptr, nullptr, io->assignment, io->cost_limit};
   if (io->kalman_in) {
     a.trk.kf_mean_in = io->kalman_in->mean;
     a.trk.kf_cov_in = io->kalman_in->cov;
@@ -160,7 +163,8 @@ extern "C" int rtm_post_backbone_step(const rtm_step_io* io, const rtm_nms_param
   a.work_bytes = static_cast<int>(work);
   static size_t configured = 0;
   if (smem > configured) {
-    RTM_CUDA(cudaFuncSetAttribute(post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    RTM_CUDA(cudaFuncSetAttribute(post_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    RTM_CUDA(cudaFuncSetAttribute(post_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     configured = smem;
   }
   {
@@ -179,7 +183,8 @@ extern "C" int rtm_post_backbone_step(const rtm_step_io* io, const rtm_nms_param
     // by default only the scan is a programmatic dependent (of the previous step's post kernel).
     static const char* pdl_post = getenv("RTM_PDL_POST");
     cfg.numAttrs = (pdl_post && pdl_post[0] == '1' && rtm::pdl_enabled() && !rtm::g_profile_on) ? 1 : 0;
-    RTM_CUDA(cudaLaunchKernelEx(&cfg, post_kernel, a));
+    if (optimal) RTM_CUDA(cudaLaunchKernelEx(&cfg, post_kernel<true>, a));
+    else RTM_CUDA(cudaLaunchKernelEx(&cfg, post_kernel<false>, a));
   }
   RTM_LAUNCH_CHECK("post_kernel");
   return RTM_OK;

@@ -313,6 +313,8 @@ class StreamBatch:
         if self.use_kalman:
             io.kalman_in = C.pointer(self.tables[self.cur].kalman)
             io.kalman_out = C.pointer(self.tables[self.cur ^ 1].kalman)
+        if self.assignment == "lapjv":
+            io.assignment, io.cost_limit = _lib.ASSIGN_OPTIMAL, 1 - self.match_thresh      # tracker.py:170
         return io
 
     def _advance(self) -> None:
@@ -329,28 +331,8 @@ class StreamBatch:
         fid = self.frame_id if frame_id is None else frame_id
         with torch.cuda.device(self.device):
             io = self._io(heads, now, fid)
-            if self.assignment == "greedy":
-                _lib.check(self.lib.rtm_post_backbone_step(C.byref(io), C.byref(self.params), _lib.cuda_stream()))
-            else:
-                self._step_unfused(io)
+            _lib.check(self.lib.rtm_post_backbone_step(C.byref(io), C.byref(self.params), _lib.cuda_stream()))
         self._advance()
-
-    def _step_unfused(self, io) -> None:
-        """The three stages as separate entry points (the fused kernel only has the greedy assignment)."""
-        st = _lib.cuda_stream()
-        _lib.check(self.lib.rtm_decode_nms(io.head_p3, io.head_p4, io.head_p5, io.head_dtype, self.B, io.img_h, io.img_w,
-                                           C.byref(self.params), io.scale, io.det_xyxy, io.det_conf, io.det_cls,
-                                           io.det_anchor, io.det_keep, io.det_count, io.det_stride, io.status,
-                                           io.workspace, io.workspace_bytes, st))
-        tin, tout = self.tables[self.cur], self.tables[self.cur ^ 1]
-        opt = _lib.track_options(self.track_thresh, self.match_thresh, self.track_buffer, self.assignment,
-                                 tin.kalman if self.use_kalman else None, tout.kalman if self.use_kalman else None)
-        _lib.check(self.lib.rtm_track_step_ex(io.table_in, io.table_out, io.det_xyxy, io.det_conf, io.det_cls, io.det_count,
-                                              io.det_stride, C.byref(opt), io.det_track_id, io.det_kind, io.src_row,
-                                              io.status, st))
-        if self.zones is not None:
-            _lib.check(self.lib.rtm_zone_step(io.zones, io.table_out, io.src_row, io.state_in, io.state_out, io.now, None,
-                                              io.frame_id, io.events, io.event_stride, io.event_count, io.status, st))
 
     def track_only(self, det_xyxy, det_conf, det_cls, det_count, now: Optional[float] = None,
                    frame_id: Optional[int] = None) -> None:

@@ -29,15 +29,17 @@ def moving_heads(pkg, B, F, seed, n_obj=12):
     return frames
 
 
-@pytest.mark.parametrize("dtype,kalman", [("f32", False), ("bf16", False), ("bf16", True)])
-def test_fused_step_matches_oracle_chain(pkg, dtype, kalman):
+@pytest.mark.parametrize("dtype,kalman,assignment", [("f32", False, "greedy"), ("bf16", False, "greedy"), ("bf16", True, "greedy"),
+                                                     ("bf16", False, "lapjv"), ("bf16", True, "lapjv")])
+def test_fused_step_matches_oracle_chain(pkg, dtype, kalman, assignment):
     import torch
     B, F = 4, 25
     tdt = {"f32": torch.float32, "bf16": torch.bfloat16}[dtype]
     zones = [pkg.synth.make_zones(seed=b, num_zones=4, width=1920, height=1080, dwell_time_sec=0.2, cooldown_sec=0.4)
              for b in range(B)]
-    sb = pkg.StreamBatch(B, zones, src_hw=(1080, 1920), classes=WANTED, max_tracks=256, use_kalman=kalman)
-    trk = [tracker_ref.TrackerOracle(use_kalman=kalman) for _ in range(B)]
+    sb = pkg.StreamBatch(B, zones, src_hw=(1080, 1920), classes=WANTED, max_tracks=256, use_kalman=kalman, assignment=assignment)
+    assign = tracker_ref.assign_lapjv_emulated if assignment == "lapjv" else tracker_ref.assign_rowloop
+    trk = [tracker_ref.TrackerOracle(use_kalman=kalman, assign=assign) for _ in range(B)]
     zon = [zone_ref.ZoneOracle(z) for z in zones]
     n_events = 0
     for f, heads in enumerate(moving_heads(pkg, B, F, seed=4)):
