@@ -495,8 +495,14 @@ def e2e_bench(pkg, wl, sb, f0, K, W, total_streams, world, dev):
     """Same metric through rtm_post_backbone_step_host: pinned host heads -> H2D -> kernels -> D2H."""
     import torch
     import torch.distributed as dist
-    pinned = [[t.cpu().pin_memory() for t in frame] for frame in wl.heads]
     feeder = pkg.HostFeeder(sb, wl.dtype)
+    pinned = []
+    for frame in wl.heads:                                   # every frame of the cycle in page-locked host memory
+        host = feeder.alloc_pinned_heads()
+        for dst, src in zip(host, frame):
+            dst.copy_(src)
+        pinned.append(host)
+    torch.cuda.synchronize(dev)
     results = []
 
     def go(first, n):

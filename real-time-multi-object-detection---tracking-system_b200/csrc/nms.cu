@@ -193,7 +193,6 @@ struct TmaGeom {
   int total_tiles;
   int stages;
   int tile_bytes;
-  int pdl_wait;  // experiment switch: wait for the prerequisite grid before exiting
   int evict_first;    // L2 evict-first hint on the tile loads
   int static_rounds;  // ring rounds with the static schedule (tile = blockIdx + k * grid) before tickets take over
 };
@@ -348,13 +347,11 @@ __global__ void __launch_bounds__(tma_threads(kTileW)) decode_tma_kernel(const _
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int stages = tg.stages;
   const int tps = tg.tiles_before[3], tb1 = tg.tiles_before[1], tb2 = tg.tiles_before[2];
-  // Programmatic dependent launch (no-ops for an ordinary launch).  The kernel behind this one on
-  // the stream - the step's post kernel - may be scheduled as soon as SMs free up; it waits for this
-  // grid to complete before it reads the candidate lists.  This grid in turn may have been started
-  // while the PREVIOUS step's post kernel was still running: nothing here reads what that kernel
-  // writes, but every thread waits for it before exiting, so that "this grid is complete" implies
-  // "the previous post kernel is complete" for the kernels ordered after this one.
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // Programmatic dependent launch: this grid may have been started while the PREVIOUS step's post
+  // kernel (which releases its dependents as its first instruction) was still running.  Nothing here
+  // reads or writes what that kernel touches: the head tensors are inputs, the candidate list goes
+  // to another slot of the ring, the ticket counter of that slot was re-armed two steps ago.  The
+  // step's own post kernel is an ordinary launch and starts after everything before it has finished.
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -433,7 +430,6 @@ __global__ void __launch_bounds__(tma_threads(kTileW)) decode_tma_kernel(const _
         }
       }
     }
-    if (tg.pdl_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
     return;
   }
 
@@ -579,7 +575,6 @@ __global__ void __launch_bounds__(tma_threads(kTileW)) decode_tma_kernel(const _
       phase ^= 1;
     }
   }
-  if (tg.pdl_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1113,8 +1108,7 @@ int launch_decode_tma_w(const void* p3, const void* p4, const void* p5, const He
   for (int l = 0; l < 3; ++l) tg.tiles_before[l + 1] = tg.tiles_before[l] + (g.lv[l].hw + kTileW - 1) / kTileW;
   tg.total_tiles = tg.tiles_before[3] * B;
   tg.tile_bytes = ch * kTileW * static_cast<int>(sizeof(T));
-  static const int pdl_wait_env = env_int("RTM_PDL_WAIT", 0), static_env = env_int("RTM_TMA_STATIC_ROUNDS", 1);
-  tg.pdl_wait = pdl_wait_env;
+  static const int static_env = env_int("RTM_TMA_STATIC_ROUNDS", 1);
   tg.static_rounds = static_env < 1 ? 1 : static_env;
   static const int evict_env = env_int("RTM_TMA_EVICT_FIRST", 1);
   tg.evict_first = evict_env;
@@ -1153,8 +1147,7 @@ int launch_decode_tma_w(const void* p3, const void* p4, const void* p5, const He
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = (rtm::pdl_enabled() && !rtm::g_profile_on) ? 1 : 0;
-    static const int dry = env_int("RTM_SCAN_DRY", 0);  // timing experiment: nothing passes the gate
-    const float gate = dry ? FLT_MAX : logit_gate_for(prm.conf_thres);
+    const float gate = logit_gate_for(prm.conf_thres);
     if (g.num_classes == 80)
       RTM_CUDA(cudaLaunchKernelEx(&cfg, decode_tma_kernel<T, true, kTileW>, maps[0], maps[1], maps[2], tg, prm, gate, ws));
     else
@@ -1211,8 +1204,7 @@ int launch_decode(const void* p3, const void* p4, const void* p5, const HeadGeom
     const int tma = try_launch_decode_tma<T>(p3, p4, p5, g, B, prm, ws, stream);
     if (tma != 0) return tma < 0 ? tma : RTM_OK;
   }
-  static const int dry = env_int("RTM_SCAN_DRY", 0);  // timing experiment: nothing passes the gate
-  const float gate = dry ? FLT_MAX : logit_gate_for(prm.conf_thres);
+  const float gate = logit_gate_for(prm.conf_thres);
   if (impl == 2) {
     constexpr int THREADS = 128;
     const int groups = g.num_anchors / kVec;

@@ -41,15 +41,11 @@ __global__ void __launch_bounds__(kPostThreads, 1) post_kernel(const __grid_cons
   rtm::TrackPrefetch* tpf = reinterpret_cast<rtm::TrackPrefetch*>(smem_raw + a.work_bytes);
   rtm::ZonePrefetch* zpf = reinterpret_cast<rtm::ZonePrefetch*>(tpf + 1);
   const int b = blockIdx.x;
-  // Programmatic dependent launch (no-ops for an ordinary launch): the next step's head scan may
-  // start now - it fills another slot of the candidate ring and touches nothing this kernel reads
-  // or writes.  This kernel itself may have been scheduled while its own step's scan was still
-  // finishing: what does not depend on the scan (and was last written by the previous post kernel,
-  // complete by then - the scan waits for it before it exits) is fetched first, then the grid
-  // waits for the scan to complete.
+  // Programmatic dependent launch: the next step's head scan (launched with programmatic stream
+  // serialisation) may start now - it fills another slot of the candidate ring and touches nothing
+  // this kernel reads or writes.  This kernel itself is an ordinary launch.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   RTM_TL(0);
-  asm volatile("griddepcontrol.wait;" ::: "memory");
   auto prefetch = [&]() {
     if (a.has_zones) rtm::zone_prefetch<kPostThreads>(a.zone, b, zpf);
     rtm::track_prefetch<kPostThreads>(a.trk, b, tpf);
@@ -169,22 +165,11 @@ extern "C" int rtm_post_backbone_step(const rtm_step_io* io, const rtm_nms_param
   }
   {
     rtm::ProfileScope prof(RTM_K_POST, s);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(B);
-    cfg.blockDim = dim3(kPostThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    // RTM_PDL_POST=1 also lets this kernel be scheduled while its own step's scan drains.  Measured
-    // slower (56.7 vs 46.0 us per step: its CTAs need whole SMs and hold them while they wait), so
-    // by default only the scan is a programmatic dependent (of the previous step's post kernel).
-    static const char* pdl_post = getenv("RTM_PDL_POST");
-    cfg.numAttrs = (pdl_post && pdl_post[0] == '1' && rtm::pdl_enabled() && !rtm::g_profile_on) ? 1 : 0;
-    if (optimal) RTM_CUDA(cudaLaunchKernelEx(&cfg, post_kernel<true>, a));
-    else RTM_CUDA(cudaLaunchKernelEx(&cfg, post_kernel<false>, a));
+    // An ordinary launch on purpose.  Launching this kernel as a programmatic dependent of its own
+    // step's scan as well was measured slower (56.7 vs 46.0 us per step: its CTAs need whole SMs and
+    // hold them while they wait) and would need the scan to wait for the previous post kernel.
+    if (optimal) post_kernel<true><<<B, kPostThreads, smem, s>>>(a);
+    else post_kernel<false><<<B, kPostThreads, smem, s>>>(a);
   }
   RTM_LAUNCH_CHECK("post_kernel");
   return RTM_OK;

@@ -444,6 +444,18 @@ class HostFeeder:
         B, D, dev = batch.B, batch.det_stride, batch.device
         shapes = [(B, 64 + batch.nc, batch.imgsz[0] // s, batch.imgsz[1] // s) for s in (8, 16, 32)]
         pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True)
+        self._shapes, self._head_dtype = shapes, head_dtype
+
+        def views(flat):                                     # the three levels back to back in one buffer
+            out, o = [], 0
+            for sh in shapes:
+                n = int(np.prod(sh))
+                out.append(flat[o:o + n].view(sh))
+                o += n
+            return out
+
+        self._views = views
+        total = sum(int(np.prod(sh)) for sh in shapes)
         self.slots = []
         with torch.cuda.device(dev):
             for _ in range(self.depth):
@@ -453,8 +465,8 @@ class HostFeeder:
                 ev_stride = batch.zones.event_stride if batch.zones is not None else 1
                 self.slots.append(dict(
                     stream=stream, done=done,
-                    host_heads=[pin(s, head_dtype) for s in shapes],
-                    dev_heads=[torch.empty(s, dtype=head_dtype, device=dev) for s in shapes],
+                    host_heads=views(pin((total,), head_dtype)),
+                    dev_heads=views(torch.empty(total, dtype=head_dtype, device=dev)),
                     events=pin((B, ev_stride, 64), torch.uint8), event_count=pin((B,), torch.int32).zero_(),
                     det_xyxy=pin((B, D, 4), torch.float32), det_conf=pin((B, D), torch.float32),
                     det_cls=pin((B, D), torch.int32), det_track_id=pin((B, D), torch.int32),
@@ -465,6 +477,13 @@ class HostFeeder:
         s0 = self.slots[0]
         self.d2h_bytes = sum(s0[k].numel() * s0[k].element_size() for k in
                              ("events", "event_count", "det_xyxy", "det_conf", "det_cls", "det_track_id", "det_count", "status"))
+
+    def alloc_pinned_heads(self):
+        """Three page-locked host tensors (one per level) laid out back to back, for :meth:`step_pinned`:
+        contiguous levels cross PCIe as a single transfer."""
+        import torch
+        total = sum(int(np.prod(sh)) for sh in self._shapes)
+        return self._views(torch.empty((total,), dtype=self._head_dtype, pin_memory=True))
 
     def stage(self, slot_index: int, heads_host) -> None:
         """Copy host head tensors into the pinned staging buffers of a slot (plain memcpy)."""
