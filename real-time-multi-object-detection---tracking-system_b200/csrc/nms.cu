@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(tma_threads(kTileW)) decode_tma_kernel(const _
     am = fmaxf(am, __shfl_xor_sync(kFull, am, 8));
     am = fmaxf(am, __shfl_xor_sync(kFull, am, 16));
 
-    bool cand0 = false, cand1 = false;
+    bool cand0 = false, cand1 = false, released = false;
     if (__any_sync(kFull, am > logit_gate)) {
       // ---- exact N1 for the anchors that can pass, then D1 for the survivors ----
       float best0 = -1.f, best1 = -1.f;
@@ -529,19 +529,21 @@ __global__ void __launch_bounds__(tma_threads(kTileW)) decode_tma_kernel(const _
       cand0 = best0 > prm.conf_thres && class_wanted(prm, bc0 & 255);
       cand1 = best1 > prm.conf_thres && class_wanted(prm, bc1 & 255);
       if (__any_sync(kFull, cand0 || cand1)) {
-        float d0 = 0.f, d1 = 0.f;  // side q of the lane's two anchors
-        if (cand0) {
-          float x[kRegMax];
+        // side q of the lane's two anchors: both sets of 16 bins come out of shared memory first (a packed
+        // load yields both anchors), then the stage is handed back to the producer and the arithmetic follows
+        float x0[kRegMax], x1[kRegMax];
+        if (cand0 || cand1) {
 #pragma unroll
-          for (int k = 0; k < kRegMax; ++k) x[k] = to_float(tile[(q * kRegMax + k) * kTileW + col]);
-          d0 = dfl_expectation(x);
+          for (int k = 0; k < kRegMax; ++k) {
+            const typename P::V v = P::load(tile + (q * kRegMax + k) * kTileW + col);
+            x0[k] = P::lo(v);
+            x1[k] = P::hi(v);
+          }
         }
-        if (cand1) {
-          float x[kRegMax];
-#pragma unroll
-          for (int k = 0; k < kRegMax; ++k) x[k] = to_float(tile[(q * kRegMax + k) * kTileW + col + 1]);
-          d1 = dfl_expectation(x);
-        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);
+        released = true;
+        const float d0 = cand0 ? dfl_expectation(x0) : 0.f, d1 = cand1 ? dfl_expectation(x1) : 0.f;
         const float t0 = __shfl_down_sync(kFull, d0, 8), r0 = __shfl_down_sync(kFull, d0, 16), b0 = __shfl_down_sync(kFull, d0, 24);
         const float t1 = __shfl_down_sync(kFull, d1, 8), r1 = __shfl_down_sync(kFull, d1, 16), b1 = __shfl_down_sync(kFull, d1, 24);
         if (q == 0) {
@@ -568,8 +570,10 @@ __global__ void __launch_bounds__(tma_threads(kTileW)) decode_tma_kernel(const _
       *reinterpret_cast<uint16_t*>(mask_bytes + static_cast<size_t>(b) * ws.words * 4 + ((lv_anchor0 + pix) >> 3)) =
           static_cast<uint16_t>(even | (odd << 1));
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty_bar[s]);  // this warp is done with the stage
+    if (!released) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[s]);  // this warp is done with the stage
+    }
     if (++s == stages) {
       s = 0;
       phase ^= 1;
