@@ -758,15 +758,22 @@ struct Vec16<float> {
   }
 };
 
-// out of line on purpose: the exact path of decode_scan_kernel names it once per (anchor, class row)
-// of a batch, and is taken for a handful of them
-__device__ __noinline__ float sigmoidf_rn_call(float x) { return sigmoidf_rn(x); }
-
 __device__ __forceinline__ uint4 ld_stream16(const void* p) {  // read-once data: do not keep it in L1
   uint4 v;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
 }
+
+// Shared memory of one warp of decode_scan_kernel: the rows of the current batch as loaded (so that the
+// rare exact path can index them with run-time indices in compact loops - unrolled over 8 anchors x 20
+// rows it overflowed the instruction cache: ncu showed `no_instructions` as the dominant stall and 174 us),
+// and the running best (probability, class) of every (anchor, lane).
+template <typename T, int BATCH>
+struct ScanWarpSmem {
+  uint4 rows[BATCH > kRegMax ? BATCH : kRegMax][32][Vec16<T>::kLoads];
+  float best[8][32];
+  int cls[8][32];
+};
 
 template <typename T, int BATCH>
 __global__ void __launch_bounds__(kScanThreads) decode_scan_kernel(const HeadPtrs<T> heads, const HeadGeom g,
@@ -774,6 +781,8 @@ __global__ void __launch_bounds__(kScanThreads) decode_scan_kernel(const HeadPtr
                                                                    const Workspace ws) {
   using V = Vec16<T>;
   constexpr int L = V::kLoads;
+  extern __shared__ __align__(16) unsigned char scan_smem[];
+  ScanWarpSmem<T, BATCH>& sm = reinterpret_cast<ScanWarpSmem<T, BATCH>*>(scan_smem)[threadIdx.x >> 5];
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // see decode_tma_kernel
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31, gl = lane & 7, q = lane >> 3;
@@ -783,23 +792,27 @@ __global__ void __launch_bounds__(kScanThreads) decode_scan_kernel(const HeadPtr
   int li = 0;
   if (a0 >= g.lv[1].anchor0) li = 1;
   if (a0 >= g.lv[2].anchor0) li = 2;
-  const Level lv = g.lv[li];
-  const int pix0 = a0 - lv.anchor0;
+  const int lv_hw = li == 2 ? g.lv[2].hw : (li == 1 ? g.lv[1].hw : g.lv[0].hw);
+  const int lv_w = li == 2 ? g.lv[2].w : (li == 1 ? g.lv[1].w : g.lv[0].w);
+  const int lv_stride = li == 2 ? g.lv[2].stride : (li == 1 ? g.lv[1].stride : g.lv[0].stride);
+  const int lv_anchor0 = li == 2 ? g.lv[2].anchor0 : (li == 1 ? g.lv[1].anchor0 : 0);
+  const int pix0 = a0 - lv_anchor0;
   const int nc = g.num_classes;
-  const T* base = heads.p[li] + static_cast<size_t>(b) * (kBoxCh + nc) * lv.hw + pix0;
-  const size_t hw = lv.hw;
+  const T* base = heads.p[li] + static_cast<size_t>(b) * (kBoxCh + nc) * lv_hw + pix0;
+  const size_t hw = lv_hw;
+  const T* my_rows = reinterpret_cast<const T*>(&sm.rows[0][lane][0]);  // element (row i, anchor j) at i * kRowElems + j
+  constexpr int kRowElems = 32 * L * 16 / static_cast<int>(sizeof(T));
 
-  // ---- N1: this lane's classes (q, q + 4, ...) over its 8 anchors.  A batch of rows is loaded
-  //      (all loads in flight), folded into a packed maximum, and only if that maximum can pass the
-  //      confidence test is the batch looked at element by element - in registers - for the exact
-  //      float32 sigmoid and the FIRST arg-max (ascending classes, strict >) ----
-  float best[8];
-  int bcls[8];
+  // ---- N1: this lane's classes (q, q + 4, ...) over its 8 anchors.  A batch of rows is loaded (all
+  //      loads in flight) and folded into a packed maximum; only if that maximum can pass the
+  //      confidence test is the batch staged in shared memory and looked at element by element for
+  //      the exact float32 sigmoid and the FIRST arg-max (ascending classes, strict >) ----
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    best[j] = -1.f;
-    bcls[j] = 0x7fffffff;
+    sm.best[j][lane] = -1.f;
+    sm.cls[j][lane] = 0x7fffffff;
   }
+  unsigned pass = 0;  // anchors of the group for which this lane's quarter cleared the gate at least once
   const int iters = (nc + 3) >> 2;
   for (int i0 = 0; i0 < iters; i0 += BATCH) {
     uint4 v[BATCH][L];
@@ -819,37 +832,50 @@ __global__ void __launch_bounds__(kScanThreads) decode_scan_kernel(const HeadPtr
       if (in_range && 4 * (i0 + i) + q < nc) V::fold(mx, v[i]);
     float am[8];
     V::unpack(mx, am);
+    unsigned bpass = 0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (am[j] > logit_gate) {  // rare
+    for (int j = 0; j < 8; ++j)
+      if (am[j] > logit_gate) bpass |= 1u << j;
+    if (__any_sync(kFull, bpass != 0)) {  // rare per lane, common per warp: keep what follows compact
 #pragma unroll
+      for (int i = 0; i < BATCH; ++i)
+#pragma unroll
+        for (int l = 0; l < L; ++l) sm.rows[i][lane][l] = v[i][l];
+      __syncwarp();
+      pass |= bpass;
+#pragma unroll 1
+      for (int j = 0; j < 8; ++j) {
+        if (!((bpass >> j) & 1u)) continue;
+        float sc = sm.best[j][lane];
+        int jc = sm.cls[j][lane];
+#pragma unroll 1
         for (int i = 0; i < BATCH; ++i) {
           const int c = 4 * (i0 + i) + q;
-          const float x = to_float(reinterpret_cast<const T*>(&v[i][0])[j]);
-          if (c < nc && x > logit_gate) {
-            const float p = sigmoidf_rn_call(x);
-            if (p > best[j]) {
-              best[j] = p;
-              bcls[j] = c;
+          if (c >= nc) break;
+          const float x = to_float(my_rows[i * kRowElems + j]);
+          if (x > logit_gate) {
+            const float p = sigmoidf_rn(x);
+            if (p > sc) {
+              sc = p;
+              jc = c;
             }
           }
         }
+        sm.best[j][lane] = sc;
+        sm.cls[j][lane] = jc;
       }
+      __syncwarp();
     }
   }
 
   unsigned cand = 0;  // candidate bits of the group's 8 anchors (identical in its four lanes)
-  unsigned pass = 0;
-#pragma unroll
-  for (int j = 0; j < 8; ++j)
-    if (best[j] >= 0.f) pass |= 1u << j;
   if (__any_sync(kFull, pass != 0)) {
     // ---- combine the four class quarters of every anchor; class filter on the arg-max class ----
-#pragma unroll
+#pragma unroll 1
     for (int j = 0; j < 8; ++j) {
       if (!__any_sync(kFull, (pass >> j) & 1u)) continue;
-      float sc = best[j];
-      int jc = bcls[j];
+      float sc = sm.best[j][lane];
+      int jc = sm.cls[j][lane];
 #pragma unroll
       for (int d = 8; d <= 16; d <<= 1) {
         const float ob = __shfl_xor_sync(kFull, sc, d);
@@ -859,15 +885,12 @@ __global__ void __launch_bounds__(kScanThreads) decode_scan_kernel(const HeadPtr
           jc = oc;
         }
       }
-      best[j] = sc;
-      bcls[j] = jc;
+      sm.best[j][lane] = sc;
+      sm.cls[j][lane] = jc;
       if (sc > prm.conf_thres && class_wanted(prm, jc & 255)) cand |= 1u << j;
     }
     // ---- D1 for the candidates: lane q decodes side q of its group's candidate anchors ----
     if (__any_sync(kFull, cand != 0)) {
-      float dist[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) dist[j] = 0.f;
       if (cand) {
         uint4 bx[kRegMax][L];
 #pragma unroll
@@ -876,35 +899,35 @@ __global__ void __launch_bounds__(kScanThreads) decode_scan_kernel(const HeadPtr
           for (int l = 0; l < L; ++l)
             bx[k][l] = *reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(base + (q * kRegMax + k) * hw) + 16 * l);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if ((cand >> j) & 1u) {
-            float x[kRegMax];
+        for (int k = 0; k < kRegMax; ++k)
 #pragma unroll
-            for (int k = 0; k < kRegMax; ++k) x[k] = to_float(reinterpret_cast<const T*>(&bx[k][0])[j]);
-            dist[j] = dfl_expectation(x);
-          }
-        }
+          for (int l = 0; l < L; ++l) sm.rows[k][lane][l] = bx[k][l];
       }
-#pragma unroll
+      __syncwarp();
+#pragma unroll 1
       for (int j = 0; j < 8; ++j) {
         if (!__any_sync(kFull, (cand >> j) & 1u)) continue;
-        const float dl = dist[j];
-        const float dt = __shfl_down_sync(kFull, dist[j], 8), dr = __shfl_down_sync(kFull, dist[j], 16),
-                    db = __shfl_down_sync(kFull, dist[j], 24);
+        float dl = 0.f;
+        if ((cand >> j) & 1u) {
+          float x[kRegMax];
+#pragma unroll
+          for (int k = 0; k < kRegMax; ++k) x[k] = to_float(my_rows[k * kRowElems + j]);
+          dl = dfl_expectation(x);
+        }
+        const float dt = __shfl_down_sync(kFull, dl, 8), dr = __shfl_down_sync(kFull, dl, 16), db = __shfl_down_sync(kFull, dl, 24);
         if (q == 0 && ((cand >> j) & 1u)) {
           const int pix = pix0 + j;
-          const int y = pix / lv.w, x = pix - y * lv.w;
+          const int y = pix / lv_w, x = pix - y * lv_w;
           store_candidate(ws, b, a0 + j,
                           dist_to_xyxy(dl, dt, dr, db, static_cast<float>(x) + 0.5f, static_cast<float>(y) + 0.5f,
-                                       static_cast<float>(lv.stride), nullptr),
-                          best[j], bcls[j]);
+                                       static_cast<float>(lv_stride), nullptr),
+                          sm.best[j][lane], sm.cls[j][lane]);
         }
       }
     }
   }
   if (in_range && q == 0)
     reinterpret_cast<uint8_t*>(ws.mask + static_cast<size_t>(b) * ws.words)[a0 >> 3] = static_cast<uint8_t>(cand);
-  asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1229,6 +1252,13 @@ int launch_decode(const void* p3, const void* p4, const void* p5, const HeadGeom
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((warps + kScanThreads / 32 - 1) / (kScanThreads / 32), B);
     cfg.blockDim = dim3(kScanThreads);
+    cfg.dynamicSmemBytes = sizeof(ScanWarpSmem<T, BATCH>) * (kScanThreads / 32);
+    static bool configured = false;
+    if (!configured) {
+      RTM_CUDA(cudaFuncSetAttribute(decode_scan_kernel<T, BATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(cfg.dynamicSmemBytes)));
+      configured = true;
+    }
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
