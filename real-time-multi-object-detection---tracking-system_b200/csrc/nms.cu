@@ -227,17 +227,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
     if (spin > (1u << 26)) __trap();
 }
-__device__ __forceinline__ void tma_load_tile(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int b,
+__device__ __forceinline__ void tma_load_tile(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int b,
                                               const uint64_t policy) {
   if (policy) {  // read-once data: L2 evict-first
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
-        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(0), "r"(b), "l"(policy)
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(b), "l"(policy)
         : "memory");
   } else {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(0), "r"(b)
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(b)
         : "memory");
   }
 }
@@ -330,13 +330,23 @@ __device__ __forceinline__ void anchor_best(const T* cls_col, const int q, const
   *bc = j;
 }
 
-template <typename T, bool NC80, int kTileW>
-__global__ void __launch_bounds__(tma_threads(kTileW)) decode_tma_kernel(const __grid_constant__ CUtensorMap map0,
-                                                                 const __grid_constant__ CUtensorMap map1,
-                                                                 const __grid_constant__ CUtensorMap map2,
+// SPLIT: a tile holds the class planes only (the part every anchor needs); the 64 box channels are
+// fetched per consumer warp - a 64 x 16-anchor sub-tile (one 32-byte sector per row for 16-bit heads),
+// by a second TMA copy the warp issues itself - and only when its 16 anchors hold a candidate.  That
+// copy is waited for one tile later (the warp scans the next tile meanwhile), so its latency stays
+// off the ring.  Box bytes that no candidate needs never cross HBM.
+struct TmaMaps {
+  CUtensorMap tile[3];  // per level: the ring's tiles
+  CUtensorMap box[3];   // per level: 64 box channels x 16 anchors (SPLIT only)
+};
+
+template <typename T, bool NC80, int kTileW, bool SPLIT>
+__global__ void __launch_bounds__(tma_threads(kTileW)) decode_tma_kernel(const __grid_constant__ TmaMaps maps,
                                                                  const TmaGeom tg, const rtm_nms_params prm,
                                                                  const float logit_gate, const Workspace ws) {
+  const CUtensorMap &map0 = maps.tile[0], &map1 = maps.tile[1], &map2 = maps.tile[2];
   extern __shared__ __align__(128) unsigned char tile_smem[];
+  __shared__ __align__(8) uint64_t box_bar[8][2];  // SPLIT: per consumer warp, two box sub-tiles in flight
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   __shared__ int4 s_tile[kMaxStages];  // per stage: (stream, level, first anchor of the tile within the level, -) ; x < 0 = no more tiles
@@ -357,6 +367,10 @@ __global__ void __launch_bounds__(tma_threads(kTileW)) decode_tma_kernel(const _
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], kConsumerWarps);
     }
+    for (int w = 0; w < 8; ++w) {
+      mbar_init(&box_bar[w][0], 1);
+      mbar_init(&box_bar[w][1], 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -376,7 +390,7 @@ __global__ void __launch_bounds__(tma_threads(kTileW)) decode_tma_kernel(const _
         s_tile[s] = make_int4(b, li, x, 0);
         mbar_expect_tx(&full_bar[s], tg.tile_bytes);
         tma_load_tile(tile_smem + static_cast<size_t>(s) * tg.tile_bytes, li == 0 ? &map0 : (li == 1 ? &map1 : &map2),
-                      &full_bar[s], x, b, policy);
+                      &full_bar[s], x, SPLIT ? kBoxCh : 0, b, policy);
       };
       // first round of the ring: tiles blockIdx + k * grid, no ticket needed; the tickets of the
       // second round are drawn meanwhile (all in flight together), later ones one ring cycle ahead
@@ -444,19 +458,75 @@ __global__ void __launch_bounds__(tma_threads(kTileW)) decode_tma_kernel(const _
   const int hw0 = tg.g.lv[0].hw, hw1 = tg.g.lv[1].hw, hw2 = tg.g.lv[2].hw;
   uint8_t* mask_bytes = reinterpret_cast<uint8_t*>(ws.mask);
 
+  // SPLIT: candidates of the previous tile whose box sub-tile is still in flight
+  struct Pending {
+    bool valid, cand0, cand1;
+    float best0, best1;
+    int bc0, bc1, b, li, pix;
+  } pend;
+  pend.valid = false;
+  int box_cur = 0;
+  unsigned box_phase = 0;  // bit i = parity to wait for on box_bar[warp][i]
+  constexpr int kBoxElems = kBoxCh * kAnchorsPerWarp;  // elements of one box sub-tile
+  T* box_buf = reinterpret_cast<T*>(tile_smem + static_cast<size_t>(stages) * tg.tile_bytes) + warp * 2 * kBoxElems;
+  uint64_t box_policy = 0;
+  if (SPLIT && tg.evict_first) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(box_policy));
+  auto level_of = [&](int li, int* lv_w, int* lv_stride, int* lv_anchor0) {
+    *lv_w = li == 2 ? w2 : (li == 1 ? w1 : w0);
+    *lv_stride = li == 2 ? st2 : (li == 1 ? st1 : st0);
+    *lv_anchor0 = li == 2 ? a2 : (li == 1 ? a1 : 0);
+  };
+  // D1 for the lane's candidates from 16 bins x 4 sides (side q in this lane), then the store
+  auto decode_and_store = [&](const float (&x0)[kRegMax], const float (&x1)[kRegMax], bool c0, bool c1, float bst0, float bst1,
+                              int cl0, int cl1, int bb, int lli, int ppix) {
+    const float d0 = c0 ? dfl_expectation(const_cast<float(&)[kRegMax]>(x0)) : 0.f;
+    const float d1 = c1 ? dfl_expectation(const_cast<float(&)[kRegMax]>(x1)) : 0.f;
+    const float t0 = __shfl_down_sync(kFull, d0, 8), r0 = __shfl_down_sync(kFull, d0, 16), b0 = __shfl_down_sync(kFull, d0, 24);
+    const float t1 = __shfl_down_sync(kFull, d1, 8), r1 = __shfl_down_sync(kFull, d1, 16), b1 = __shfl_down_sync(kFull, d1, 24);
+    if (q == 0) {
+      int lv_w, lv_stride, lv_anchor0;
+      level_of(lli, &lv_w, &lv_stride, &lv_anchor0);
+      const int y = ppix / lv_w, x = ppix - y * lv_w;  // both anchors are in the same grid row (w is even)
+      const float ay = static_cast<float>(y) + 0.5f, fs = static_cast<float>(lv_stride);
+      if (c0)
+        store_candidate(ws, bb, lv_anchor0 + ppix, dist_to_xyxy(d0, t0, r0, b0, static_cast<float>(x) + 0.5f, ay, fs, nullptr), bst0, cl0);
+      if (c1)
+        store_candidate(ws, bb, lv_anchor0 + ppix + 1,
+                        dist_to_xyxy(d1, t1, r1, b1, static_cast<float>(x + 1) + 0.5f, ay, fs, nullptr), bst1, cl1);
+    }
+  };
+  // SPLIT: the pending tile's box sub-tile has (or will soon have) arrived: finish its candidates
+  auto finish_pending = [&](const int buf) {
+    mbar_wait(&box_bar[warp][buf], (box_phase >> buf) & 1u);
+    box_phase ^= 1u << buf;
+    const T* bb = box_buf + buf * kBoxElems;
+    float x0[kRegMax], x1[kRegMax];
+    if (pend.cand0 || pend.cand1) {
+#pragma unroll
+      for (int k = 0; k < kRegMax; ++k) {
+        const typename P::V v = P::load(bb + (q * kRegMax + k) * kAnchorsPerWarp + 2 * pr);
+        x0[k] = P::lo(v);
+        x1[k] = P::hi(v);
+      }
+    }
+    __syncwarp();  // every lane has read the buffer before it can be refilled
+    decode_and_store(x0, x1, pend.cand0, pend.cand1, pend.best0, pend.best1, pend.bc0, pend.bc1, pend.b, pend.li, pend.pix);
+    pend.valid = false;
+  };
+
   int s = 0, phase = 0;
   while (true) {
     mbar_wait(&full_bar[s], phase);
     int b, li, x0;
     asm volatile("ld.volatile.shared.v4.s32 {%0, %1, %2, _}, [%3];" : "=r"(b), "=r"(li), "=r"(x0) : "r"(smem_u32(&s_tile[s])));
     if (b < 0) break;
-    const int lv_w = li == 2 ? w2 : (li == 1 ? w1 : w0);
-    const int lv_stride = li == 2 ? st2 : (li == 1 ? st1 : st0);
-    const int lv_anchor0 = li == 2 ? a2 : (li == 1 ? a1 : 0);
+    int lv_w, lv_stride, lv_anchor0;
+    level_of(li, &lv_w, &lv_stride, &lv_anchor0);
     const int lv_hw = li == 2 ? hw2 : (li == 1 ? hw1 : hw0);
     const int pix = x0 + col;
     const T* tile = reinterpret_cast<const T*>(tile_smem + static_cast<size_t>(s) * tg.tile_bytes);
-    const T* cls_col = tile + (kBoxCh + q) * kTileW + col;  // row of class q
+    const T* cls_rows = tile + (SPLIT ? 0 : kBoxCh) * kTileW;  // first class row of the tile
+    const T* cls_col = cls_rows + q * kTileW + col;            // row of class q
 
     // ---- N1 gate: packed running maximum over this quarter's classes for both anchors ----
     typename P::V mv = P::lowest();
@@ -523,38 +593,51 @@ __global__ void __launch_bounds__(tma_threads(kTileW)) decode_tma_kernel(const _
           }
         }
       } else {
-        anchor_best<T, NC80, kTileW>(tile + kBoxCh * kTileW + col, q, iters, nc, m0, logit_gate, &best0, &bc0);
-        anchor_best<T, NC80, kTileW>(tile + kBoxCh * kTileW + col + 1, q, iters, nc, m1, logit_gate, &best1, &bc1);
+        anchor_best<T, NC80, kTileW>(cls_rows + col, q, iters, nc, m0, logit_gate, &best0, &bc0);
+        anchor_best<T, NC80, kTileW>(cls_rows + col + 1, q, iters, nc, m1, logit_gate, &best1, &bc1);
       }
       cand0 = best0 > prm.conf_thres && class_wanted(prm, bc0 & 255);
       cand1 = best1 > prm.conf_thres && class_wanted(prm, bc1 & 255);
       if (__any_sync(kFull, cand0 || cand1)) {
-        // side q of the lane's two anchors: both sets of 16 bins come out of shared memory first (a packed
-        // load yields both anchors), then the stage is handed back to the producer and the arithmetic follows
-        float x0[kRegMax], x1[kRegMax];
-        if (cand0 || cand1) {
-#pragma unroll
-          for (int k = 0; k < kRegMax; ++k) {
-            const typename P::V v = P::load(tile + (q * kRegMax + k) * kTileW + col);
-            x0[k] = P::lo(v);
-            x1[k] = P::hi(v);
+        if (SPLIT) {
+          // the class planes are done with: hand the stage back, ask for this warp's box sub-tile, and
+          // meanwhile finish the tile before this one
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(&empty_bar[s]);
+            mbar_expect_tx(&box_bar[warp][box_cur], kBoxElems * static_cast<int>(sizeof(T)));
+            tma_load_tile(box_buf + box_cur * kBoxElems, li == 0 ? &maps.box[0] : (li == 1 ? &maps.box[1] : &maps.box[2]),
+                          &box_bar[warp][box_cur], x0 + warp * kAnchorsPerWarp, 0, b, box_policy);
           }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[s]);
-        released = true;
-        const float d0 = cand0 ? dfl_expectation(x0) : 0.f, d1 = cand1 ? dfl_expectation(x1) : 0.f;
-        const float t0 = __shfl_down_sync(kFull, d0, 8), r0 = __shfl_down_sync(kFull, d0, 16), b0 = __shfl_down_sync(kFull, d0, 24);
-        const float t1 = __shfl_down_sync(kFull, d1, 8), r1 = __shfl_down_sync(kFull, d1, 16), b1 = __shfl_down_sync(kFull, d1, 24);
-        if (q == 0) {
-          const int y = pix / lv_w, x = pix - y * lv_w;  // both anchors are in the same grid row (w is even)
-          const float ay = static_cast<float>(y) + 0.5f, fs = static_cast<float>(lv_stride);
-          if (cand0)
-            store_candidate(ws, b, lv_anchor0 + pix, dist_to_xyxy(d0, t0, r0, b0, static_cast<float>(x) + 0.5f, ay, fs, nullptr),
-                            best0, bc0);
-          if (cand1)
-            store_candidate(ws, b, lv_anchor0 + pix + 1,
-                            dist_to_xyxy(d1, t1, r1, b1, static_cast<float>(x + 1) + 0.5f, ay, fs, nullptr), best1, bc1);
+          released = true;
+          box_cur ^= 1;
+                if (pend.valid) finish_pending(box_cur);  // requests alternate buffers: after the flip box_cur is the older one
+          pend.valid = true;
+          pend.cand0 = cand0;
+          pend.cand1 = cand1;
+          pend.best0 = best0;
+          pend.best1 = best1;
+          pend.bc0 = bc0;
+          pend.bc1 = bc1;
+          pend.b = b;
+          pend.li = li;
+          pend.pix = pix;
+        } else {
+          // side q of the lane's two anchors: both sets of 16 bins come out of shared memory first (a packed
+          // load yields both anchors), then the stage is handed back to the producer and the arithmetic follows
+          float x0v[kRegMax], x1v[kRegMax];
+          if (cand0 || cand1) {
+#pragma unroll
+            for (int k = 0; k < kRegMax; ++k) {
+              const typename P::V v = P::load(tile + (q * kRegMax + k) * kTileW + col);
+              x0v[k] = P::lo(v);
+              x1v[k] = P::hi(v);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty_bar[s]);
+          released = true;
+          decode_and_store(x0v, x1v, cand0, cand1, best0, best1, bc0, bc1, b, li, pix);
         }
       }
     }
@@ -579,6 +662,7 @@ __global__ void __launch_bounds__(tma_threads(kTileW)) decode_tma_kernel(const _
       phase ^= 1;
     }
   }
+  if (SPLIT && pend.valid) finish_pending(box_cur ^ 1);  // the most recent request
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1099,7 +1183,7 @@ template <>
 CUtensorMapDataType tensor_map_dtype<__nv_bfloat16>() { return CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; }
 
 // returns 1 when the TMA path was launched, 0 when the caller should fall back, < 0 on error
-template <typename T, int kTileW>
+template <typename T, int kTileW, bool SPLIT>
 int launch_decode_tma_w(const void* p3, const void* p4, const void* p5, const HeadGeom& g, int B,
                         const rtm_nms_params& prm, const Workspace& ws, cudaStream_t stream) {
   EncodeTiledFn encode = tensor_map_encoder();
@@ -1110,23 +1194,28 @@ int launch_decode_tma_w(const void* p3, const void* p4, const void* p5, const He
   for (int l = 0; l < 3; ++l)
     if (g.lv[l].hw % kAnchorsPerWarp != 0 || g.lv[l].w % 2 != 0) return 0;
   const int ch = kBoxCh + g.num_classes;
+  const int tile_rows = SPLIT ? g.num_classes : ch;
   const void* ptrs[3] = {p3, p4, p5};
-  CUtensorMap maps[3];
+  TmaMaps maps;
+  static const int promo_env = env_int("RTM_TMA_L2PROMO", 3);  // 0 none, 1 64B, 2 128B, 3 256B
+  const CUtensorMapL2promotion promo = promo_env == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                       : promo_env == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                       : promo_env == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                                        : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
   for (int l = 0; l < 3; ++l) {
     const cuuint64_t dims[3] = {static_cast<cuuint64_t>(g.lv[l].hw), static_cast<cuuint64_t>(ch), static_cast<cuuint64_t>(B)};
     const cuuint64_t strides[2] = {static_cast<cuuint64_t>(g.lv[l].hw) * sizeof(T),
                                    static_cast<cuuint64_t>(g.lv[l].hw) * ch * sizeof(T)};
-    const cuuint32_t box[3] = {kTileW, static_cast<cuuint32_t>(ch), 1};
+    const cuuint32_t box[3] = {kTileW, static_cast<cuuint32_t>(tile_rows), 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     if (ch > 256 || (strides[0] & 15) != 0) return 0;
-    static const int promo_env = env_int("RTM_TMA_L2PROMO", 3);  // 0 none, 1 64B, 2 128B, 3 256B
-    const CUtensorMapL2promotion promo = promo_env == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
-                                         : promo_env == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
-                                         : promo_env == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
-                                                          : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
-    const CUresult r = encode(&maps[l], tensor_map_dtype<T>(), 3, const_cast<void*>(ptrs[l]), dims, strides, box, estr,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo,
-                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = encode(&maps.tile[l], tensor_map_dtype<T>(), 3, const_cast<void*>(ptrs[l]), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return 0;
+    const cuuint32_t sub[3] = {kAnchorsPerWarp, kBoxCh, 1};  // a warp's box sub-tile (SPLIT); no L2 promotion: sector-sized rows
+    r = encode(&maps.box[l], tensor_map_dtype<T>(), 3, const_cast<void*>(ptrs[l]), dims, strides, sub, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return 0;
   }
   TmaGeom tg;
@@ -1134,7 +1223,7 @@ int launch_decode_tma_w(const void* p3, const void* p4, const void* p5, const He
   tg.tiles_before[0] = 0;
   for (int l = 0; l < 3; ++l) tg.tiles_before[l + 1] = tg.tiles_before[l] + (g.lv[l].hw + kTileW - 1) / kTileW;
   tg.total_tiles = tg.tiles_before[3] * B;
-  tg.tile_bytes = ch * kTileW * static_cast<int>(sizeof(T));
+  tg.tile_bytes = tile_rows * kTileW * static_cast<int>(sizeof(T));
   static const int static_env = env_int("RTM_TMA_STATIC_ROUNDS", 1);
   tg.static_rounds = static_env < 1 ? 1 : static_env;
   static const int evict_env = env_int("RTM_TMA_EVICT_FIRST", 1);
@@ -1143,17 +1232,18 @@ int launch_decode_tma_w(const void* p3, const void* p4, const void* p5, const He
   // ring depth and residency: as many tiles in flight per SM as fit (RTM_TMA_STAGES / RTM_TMA_CTAS override)
   static const int stages_env = env_int("RTM_TMA_STAGES", 0), ctas_env = env_int("RTM_TMA_CTAS", 0);
   const size_t smem_budget = 216 * 1024;
-  int ctas_per_sm = ctas_env > 0 ? ctas_env : (tg.tile_bytes <= 24 * 1024 ? 3 : (tg.tile_bytes <= 40 * 1024 ? 2 : 1));
-  tg.stages = stages_env > 0 ? stages_env : (sizeof(T) == 2 ? 3 : 4);
+  const size_t box_smem = SPLIT ? static_cast<size_t>(kTileW / kAnchorsPerWarp) * 2 * kBoxCh * kAnchorsPerWarp * sizeof(T) : 0;
+  int ctas_per_sm = ctas_env > 0 ? ctas_env : (SPLIT ? (sizeof(T) == 2 ? 3 : 2) : (tg.tile_bytes <= 24 * 1024 ? 3 : (tg.tile_bytes <= 40 * 1024 ? 2 : 1)));
+  tg.stages = stages_env > 0 ? stages_env : (SPLIT ? (sizeof(T) == 2 ? 4 : 2) : (sizeof(T) == 2 ? 3 : 4));
   if (tg.stages > kMaxStages) tg.stages = kMaxStages;
-  while (tg.stages > 1 && static_cast<size_t>(tg.stages) * tg.tile_bytes * ctas_per_sm > smem_budget) --tg.stages;
-  while (ctas_per_sm > 1 && static_cast<size_t>(tg.stages) * tg.tile_bytes * ctas_per_sm > smem_budget) --ctas_per_sm;
-  const size_t smem = static_cast<size_t>(tg.stages) * tg.tile_bytes;
+  while (tg.stages > 1 && (static_cast<size_t>(tg.stages) * tg.tile_bytes + box_smem) * ctas_per_sm > smem_budget) --tg.stages;
+  while (ctas_per_sm > 1 && (static_cast<size_t>(tg.stages) * tg.tile_bytes + box_smem) * ctas_per_sm > smem_budget) --ctas_per_sm;
+  const size_t smem = static_cast<size_t>(tg.stages) * tg.tile_bytes + box_smem;
   if (smem > 220 * 1024) return 0;
   static size_t configured = 0;
   if (smem > configured) {
-    RTM_CUDA(cudaFuncSetAttribute(decode_tma_kernel<T, true, kTileW>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    RTM_CUDA(cudaFuncSetAttribute(decode_tma_kernel<T, false, kTileW>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    RTM_CUDA(cudaFuncSetAttribute(decode_tma_kernel<T, true, kTileW, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    RTM_CUDA(cudaFuncSetAttribute(decode_tma_kernel<T, false, kTileW, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     configured = smem;
   }
   static const int grid_env = env_int("RTM_TMA_GRID", 0);  // experiments: any grid works with ticketed tiles
@@ -1176,9 +1266,9 @@ int launch_decode_tma_w(const void* p3, const void* p4, const void* p5, const He
     cfg.numAttrs = (rtm::pdl_enabled() && !rtm::g_profile_on) ? 1 : 0;
     const float gate = logit_gate_for(prm.conf_thres);
     if (g.num_classes == 80)
-      RTM_CUDA(cudaLaunchKernelEx(&cfg, decode_tma_kernel<T, true, kTileW>, maps[0], maps[1], maps[2], tg, prm, gate, ws));
+      RTM_CUDA(cudaLaunchKernelEx(&cfg, decode_tma_kernel<T, true, kTileW, SPLIT>, maps, tg, prm, gate, ws));
     else
-      RTM_CUDA(cudaLaunchKernelEx(&cfg, decode_tma_kernel<T, false, kTileW>, maps[0], maps[1], maps[2], tg, prm, gate, ws));
+      RTM_CUDA(cudaLaunchKernelEx(&cfg, decode_tma_kernel<T, false, kTileW, SPLIT>, maps, tg, prm, gate, ws));
   }
   RTM_LAUNCH_CHECK("decode_tma_kernel");
   return 1;
@@ -1193,17 +1283,22 @@ int try_launch_decode_tma(const void* p3, const void* p4, const void* p5, const 
   bool div80 = true;
   for (int l = 0; l < 3; ++l) div80 = div80 && g.lv[l].hw % 80 == 0;
   const int tile_w = tile_env > 0 ? tile_env : (div80 ? 80 : (sizeof(T) == 2 ? 64 : 32));
+  // RTM_TMA_SPLIT=1: class-plane tiles + per-warp box sub-tiles (80-wide tiles only).  Reads 27 % fewer bytes on
+  // the bench workload but is slower there (37.4 vs 36.1 us alone: 40 % of the warp-tiles hold a candidate, and each
+  // sub-tile is 64 requests of one sector); meant for sparse scenes, off by default
+  static const int split_env = env_int("RTM_TMA_SPLIT", 0);
   switch (tile_w) {
     case 32:
-      return launch_decode_tma_w<T, 32>(p3, p4, p5, g, B, prm, ws, stream);
+      return launch_decode_tma_w<T, 32, false>(p3, p4, p5, g, B, prm, ws, stream);
     case 64:
-      return launch_decode_tma_w<T, 64>(p3, p4, p5, g, B, prm, ws, stream);
+      return launch_decode_tma_w<T, 64, false>(p3, p4, p5, g, B, prm, ws, stream);
     case 80:
       for (int l = 0; l < 3; ++l)
         if (g.lv[l].hw % 80 != 0) return 0;
-      return launch_decode_tma_w<T, 80>(p3, p4, p5, g, B, prm, ws, stream);
+      if (split_env) return launch_decode_tma_w<T, 80, true>(p3, p4, p5, g, B, prm, ws, stream);
+      return launch_decode_tma_w<T, 80, false>(p3, p4, p5, g, B, prm, ws, stream);
     case 128:
-      return launch_decode_tma_w<T, 128>(p3, p4, p5, g, B, prm, ws, stream);
+      return launch_decode_tma_w<T, 128, false>(p3, p4, p5, g, B, prm, ws, stream);
     default:
       return 0;
   }
