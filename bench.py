@@ -397,18 +397,22 @@ def run_b200(args):
         extras = {}
         if not args.no_extras:
             # ---- latency mode: one step at a time, p50 / p99 of the per-step device time ----
+            # (the reference's profiler convention, latency_profiler.py / default.yaml:88: synchronise around the
+            # stage, 50 warm-up frames, then percentiles; here over 1000 steps of 64 stream-frames each)
             lat, ev_seen = [], 0
-            for _ in range(min(300, max(50, K))):
+            for i in range(50 + 1000):
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
                 f = run_steps(f, 1)
                 b.record()
                 b.synchronize()
-                lat.append(a.elapsed_time(b))
-                ev_seen += int(sb.zones.event_count.sum().item())
+                if i >= 50:
+                    lat.append(a.elapsed_time(b))
+                    ev_seen += int(sb.zones.event_count.sum().item())
             lat.sort()
             extras["latency_ms_per_step"] = {"p50": lat[len(lat) // 2], "p99": lat[min(len(lat) - 1, int(len(lat) * 0.99))],
-                                             "steps": len(lat), "streams_per_step": S, "zone_events_emitted": ev_seen}
+                                             "max": lat[-1], "steps": len(lat), "warmup_steps": 50, "streams_per_step": S,
+                                             "zone_events_emitted": ev_seen}
             if rank == 0:
                 extras["letterbox"] = letterbox_bench(pkg, lib, dev, S, hbm_peak)
                 extras["dense_crowd"] = dense_crowd_bench(pkg, dev)

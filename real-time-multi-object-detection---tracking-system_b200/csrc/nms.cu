@@ -38,6 +38,7 @@
 #include <string.h>
 
 #include <unordered_map>
+#include <vector>
 
 #include "nms_body.cuh"
 
@@ -1196,28 +1197,61 @@ int launch_decode_tma_w(const void* p3, const void* p4, const void* p5, const He
   const int ch = kBoxCh + g.num_classes;
   const int tile_rows = SPLIT ? g.num_classes : ch;
   const void* ptrs[3] = {p3, p4, p5};
-  TmaMaps maps;
-  static const int promo_env = env_int("RTM_TMA_L2PROMO", 3);  // 0 none, 1 64B, 2 128B, 3 256B
-  const CUtensorMapL2promotion promo = promo_env == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
-                                       : promo_env == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
-                                       : promo_env == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
-                                                        : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
-  for (int l = 0; l < 3; ++l) {
-    const cuuint64_t dims[3] = {static_cast<cuuint64_t>(g.lv[l].hw), static_cast<cuuint64_t>(ch), static_cast<cuuint64_t>(B)};
-    const cuuint64_t strides[2] = {static_cast<cuuint64_t>(g.lv[l].hw) * sizeof(T),
-                                   static_cast<cuuint64_t>(g.lv[l].hw) * ch * sizeof(T)};
-    const cuuint32_t box[3] = {kTileW, static_cast<cuuint32_t>(tile_rows), 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    if (ch > 256 || (strides[0] & 15) != 0) return 0;
-    CUresult r = encode(&maps.tile[l], tensor_map_dtype<T>(), 3, const_cast<void*>(ptrs[l]), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return 0;
-    const cuuint32_t sub[3] = {kAnchorsPerWarp, kBoxCh, 1};  // a warp's box sub-tile (SPLIT); no L2 promotion: sector-sized rows
-    r = encode(&maps.box[l], tensor_map_dtype<T>(), 3, const_cast<void*>(ptrs[l]), dims, strides, sub, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return 0;
+  // tensor maps are cached by what they describe (a caller cycles through a few sets of head buffers):
+  // encoding six maps per step is host time the step does not have to spare
+  struct MapKey {
+    const void* p[3];
+    int B, h, w, nc;
+    bool operator==(const MapKey& o) const {
+      return p[0] == o.p[0] && p[1] == o.p[1] && p[2] == o.p[2] && B == o.B && h == o.h && w == o.w && nc == o.nc;
+    }
+  };
+  struct MapEntry {
+    MapKey key;
+    TmaMaps maps;
+  };
+  static std::vector<MapEntry> cache;  // per instantiation (element type, tile width, split)
+  static size_t next_victim = 0;
+  const MapKey key{{p3, p4, p5}, B, g.lv[0].h, g.lv[0].w, g.num_classes};
+  const TmaMaps* cached = nullptr;
+  for (const MapEntry& e : cache)
+    if (e.key == key) {
+      cached = &e.maps;
+      break;
+    }
+  TmaMaps fresh;
+  if (!cached) {
+    TmaMaps& maps = fresh;
+    static const int promo_env = env_int("RTM_TMA_L2PROMO", 3);  // 0 none, 1 64B, 2 128B, 3 256B
+    const CUtensorMapL2promotion promo = promo_env == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                         : promo_env == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                         : promo_env == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                                          : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+    for (int l = 0; l < 3; ++l) {
+      const cuuint64_t dims[3] = {static_cast<cuuint64_t>(g.lv[l].hw), static_cast<cuuint64_t>(ch), static_cast<cuuint64_t>(B)};
+      const cuuint64_t strides[2] = {static_cast<cuuint64_t>(g.lv[l].hw) * sizeof(T),
+                                     static_cast<cuuint64_t>(g.lv[l].hw) * ch * sizeof(T)};
+      const cuuint32_t box[3] = {kTileW, static_cast<cuuint32_t>(tile_rows), 1};
+      const cuuint32_t estr[3] = {1, 1, 1};
+      if (ch > 256 || (strides[0] & 15) != 0) return 0;
+      CUresult r = encode(&maps.tile[l], tensor_map_dtype<T>(), 3, const_cast<void*>(ptrs[l]), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return 0;
+      const cuuint32_t sub[3] = {kAnchorsPerWarp, kBoxCh, 1};  // a warp's box sub-tile (SPLIT); no L2 promotion: sector-sized rows
+      r = encode(&maps.box[l], tensor_map_dtype<T>(), 3, const_cast<void*>(ptrs[l]), dims, strides, sub, estr,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return 0;
+    }
+    if (cache.size() < 64) {
+      cache.push_back(MapEntry{key, fresh});
+    } else {
+      cache[next_victim] = MapEntry{key, fresh};
+      next_victim = (next_victim + 1) % cache.size();
+    }
+    cached = &fresh;
   }
+  const TmaMaps& maps = *cached;
   TmaGeom tg;
   tg.g = g;
   tg.tiles_before[0] = 0;

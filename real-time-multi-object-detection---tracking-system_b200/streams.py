@@ -274,6 +274,7 @@ class StreamBatch:
         self.cur = 0
         self.frame_id = 0
         self._host = None
+        self._io_cache, self._head_cache = {}, {}
 
     # -- state views -------------------------------------------------------
     @property
@@ -282,16 +283,31 @@ class StreamBatch:
         return self.tables[self.cur]
 
     def _io(self, heads, now: float, frame_id: int) -> _lib.StepIO:
-        import torch
-        io = _lib.StepIO()
+        """rtm_step_io of this step.  Everything that does not change from step to step is filled in once
+        per table parity and reused (a step is ~40 us of GPU work: the host side has to stay well below)."""
+        key = (self.cur, self.zones.cur if self.zones is not None else 0)
+        io = self._io_cache.get(key)
+        if io is None:
+            io = self._io_cache[key] = self._build_io()
         if heads is not None:
-            p3, p4, p5 = heads
-            for t, s in zip(heads, (8, 16, 32)):
-                exp = (self.B, 64 + self.nc, self.imgsz[0] // s, self.imgsz[1] // s)
-                if tuple(t.shape) != exp or not t.is_contiguous() or t.device != self.device:
-                    raise ValueError(f"head level stride {s}: expected contiguous {exp} on {self.device}, got {tuple(t.shape)}")
+            hkey = (id(heads[0]), id(heads[1]), id(heads[2]))
+            ent = self._head_cache.get(hkey)
+            if ent is None or ent[0][0] is not heads[0] or ent[0][1] is not heads[1] or ent[0][2] is not heads[2]:
+                for t, s in zip(heads, (8, 16, 32)):
+                    exp = (self.B, 64 + self.nc, self.imgsz[0] // s, self.imgsz[1] // s)
+                    if tuple(t.shape) != exp or not t.is_contiguous() or t.device != self.device:
+                        raise ValueError(f"head level stride {s}: expected contiguous {exp} on {self.device}, got {tuple(t.shape)}")
+                if len(self._head_cache) > 256:
+                    self._head_cache.clear()
+                ent = self._head_cache[hkey] = (tuple(heads), _lib.dtype_code(heads[0].dtype))   # keeps the tensors (and their ids) alive
+            p3, p4, p5 = ent[0]
             io.head_p3, io.head_p4, io.head_p5 = p3.data_ptr(), p4.data_ptr(), p5.data_ptr()
-            io.head_dtype = _lib.dtype_code(p3.dtype)
+            io.head_dtype = ent[1]
+        io.now, io.frame_id = float(now), int(frame_id)
+        return io
+
+    def _build_io(self) -> _lib.StepIO:
+        io = _lib.StepIO()
         io.img_h, io.img_w = self.imgsz
         io.scale = self.scale.data_ptr()
         io.det_xyxy, io.det_conf, io.det_cls = self.det_xyxy.data_ptr(), self.det_conf.data_ptr(), self.det_cls.data_ptr()
@@ -308,7 +324,6 @@ class StreamBatch:
             io.state_out = C.pointer(self.zones.state_out()[2])
             io.events, io.event_stride = self.zones.events.data_ptr(), self.zones.event_stride
             io.event_count = self.zones.event_count.data_ptr()
-        io.now, io.frame_id = float(now), int(frame_id)
         io.status = self.status.data_ptr()
         if self.use_kalman:
             io.kalman_in = C.pointer(self.tables[self.cur].kalman)
@@ -329,9 +344,14 @@ class StreamBatch:
         import torch
         now = time.time() if now is None else now                     # zone_engine.py:84
         fid = self.frame_id if frame_id is None else frame_id
-        with torch.cuda.device(self.device):
-            io = self._io(heads, now, fid)
-            _lib.check(self.lib.rtm_post_backbone_step(C.byref(io), C.byref(self.params), _lib.cuda_stream()))
+        io = self._io(heads, now, fid)
+        if torch.cuda.current_device() == self.device.index:
+            rc = self.lib.rtm_post_backbone_step(C.byref(io), C.byref(self.params), torch.cuda.current_stream().cuda_stream)
+        else:
+            with torch.cuda.device(self.device):
+                rc = self.lib.rtm_post_backbone_step(C.byref(io), C.byref(self.params), torch.cuda.current_stream().cuda_stream)
+        if rc:
+            _lib.check(rc)
         self._advance()
 
     def track_only(self, det_xyxy, det_conf, det_cls, det_count, now: Optional[float] = None,
