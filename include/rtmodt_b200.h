@@ -317,6 +317,17 @@ typedef struct rtm_step_io {
    * lap's cost_limit for RTM_ASSIGN_OPTIMAL (see rtm_track_options) */
   int32_t assignment;
   double cost_limit;
+  /* Optional pipelining of consecutive steps.  scan_async = 0 (default): both kernels go to `stream`;
+   * the head scan of a step still overlaps the post kernel of the step before (programmatic
+   * dependent launch) but starts only when that kernel has started.  scan_async = 1: the caller
+   * states that the head tensors are complete once heads_ready_event (a cudaEvent_t, or NULL =
+   * complete already) has fired - e.g. the backbone runs on its own stream and records an event per
+   * frame.  The scan is then enqueued on a stream the library owns, behind that event only, so that
+   * consecutive scans run back to back; the post kernel still goes to `stream`, which the library
+   * makes wait for the scan.  Results are ordered on `stream` exactly as in the default mode, and
+   * work enqueued on `stream` after the call is ordered after the scan has read the head tensors. */
+  int32_t scan_async;
+  void* heads_ready_event;
 } rtm_step_io;
 
 int rtm_post_backbone_step(const rtm_step_io* io, const rtm_nms_params* params,

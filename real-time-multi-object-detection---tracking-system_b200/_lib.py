@@ -115,6 +115,7 @@ class StepIO(C.Structure):
         ("event_count", C.c_void_p), ("status", C.c_void_p),
         ("kalman_in", C.POINTER(KalmanState)), ("kalman_out", C.POINTER(KalmanState)),
         ("assignment", C.c_int32), ("cost_limit", C.c_double),
+        ("scan_async", C.c_int32), ("heads_ready_event", C.c_void_p),
     ]
 
 

@@ -115,6 +115,7 @@ size_t workspace_layout(int B, int A, char* base, Workspace* ws, int half = 0) {
     ws->num_anchors = A;
     ws->words = words;
     ws->cap_p2 = cap_p2;
+    ws->slot = half;
   }
   return off;
 }
@@ -1407,6 +1408,19 @@ extern "C" size_t rtm_nms_workspace_bytes(int32_t num_streams, int32_t num_ancho
   return workspace_layout(num_streams, num_anchors, nullptr, nullptr);
 }
 
+namespace {
+std::unordered_map<const void*, int>& slot_table() {
+  static std::unordered_map<const void*, int> t;
+  return t;
+}
+}  // namespace
+
+int rtm::next_scan_slot(const void* workspace) {
+  const auto& t = slot_table();
+  const auto it = t.find(workspace);
+  return it == t.end() ? 0 : it->second;
+}
+
 int rtm::launch_decode_stage(const void* head_p3, const void* head_p4, const void* head_p5, int head_dtype,
                              int num_streams, int img_h, int img_w, const rtm_nms_params* params, void* workspace,
                              size_t workspace_bytes, Workspace* ws, cudaStream_t s) {
@@ -1418,7 +1432,7 @@ int rtm::launch_decode_stage(const void* head_p3, const void* head_p4, const voi
   // that several stream batches, each with its own workspace and CUDA stream, can be interleaved).
   // The ticket counters must start at zero: the header is cleared the first time a workspace is seen;
   // afterwards every NMS stage leaves the counter of the slot it consumed at zero.
-  static std::unordered_map<const void*, int> next_slot;
+  std::unordered_map<const void*, int>& next_slot = slot_table();
   auto it = next_slot.find(workspace);
   if (it == next_slot.end()) {
     RTM_REQUIRE(workspace_bytes >= kWorkspaceHeader, "workspace too small");

@@ -40,6 +40,7 @@ struct Workspace {
   // consumes the list zeroes it again (the workspace starts zero-filled)
   int* tile_counter;
   int num_anchors, words, cap_p2;
+  int slot;  // which slot of the candidate ring this is (host-side bookkeeping)
 };
 
 struct NmsOut {
@@ -60,6 +61,9 @@ inline float iou_gate_for(double thr) {
   const float f = static_cast<float>(thr);
   return static_cast<double>(f) > thr ? f : nextafterf(f, INFINITY);
 }
+
+// slot of the candidate ring the next scan of `workspace` will take (defined in nms.cu)
+int next_scan_slot(const void* workspace);
 
 // D1 + N1 only (defined in nms.cu): scans the head tensors and leaves the candidate list of every
 // stream in `workspace`; *ws describes it for the NMS stage.

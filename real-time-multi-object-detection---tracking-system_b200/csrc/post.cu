@@ -12,6 +12,8 @@
 // so the fused step is bit-identical to rtm_decode_nms + rtm_track_step + rtm_zone_step.
 #include <stdlib.h>
 
+#include <unordered_map>
+
 #include "nms_body.cuh"
 #include "track_body.cuh"
 #include "zone_body.cuh"
@@ -69,6 +71,32 @@ extern "C" int rtm_debug_timeline(void* device_buffer) {  // (B, 32) u64, or nul
 namespace {
 #endif
 
+
+// scan_async: per workspace, the stream the scans go to and the events that order it with the caller's stream
+struct ScanCtx {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t scanned[3] = {nullptr, nullptr, nullptr};  // slot's candidate list is complete
+  cudaEvent_t consumed[3] = {nullptr, nullptr, nullptr}; // slot's post kernel is done (recorded on the caller's stream)
+  bool consumed_valid[3] = {false, false, false};
+};
+
+std::unordered_map<const void*, ScanCtx>& scan_table() {
+  static std::unordered_map<const void*, ScanCtx> table;
+  return table;
+}
+
+int scan_ctx(const void* workspace, ScanCtx** out) {
+  ScanCtx& c = scan_table()[workspace];
+  if (!c.stream) {
+    RTM_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 3; ++i) {
+      RTM_CUDA(cudaEventCreateWithFlags(&c.scanned[i], cudaEventDisableTiming));
+      RTM_CUDA(cudaEventCreateWithFlags(&c.consumed[i], cudaEventDisableTiming));
+    }
+  }
+  *out = &c;
+  return RTM_OK;
+}
 
 bool fuse_enabled() {
   static int v = -1;
@@ -134,9 +162,33 @@ extern "C" int rtm_post_backbone_step(const rtm_step_io* io, const rtm_nms_param
   }
 
   PostArgs a;
-  int rc = rtm::launch_decode_stage(io->head_p3, io->head_p4, io->head_p5, io->head_dtype, B, io->img_h, io->img_w, params,
-                                    io->workspace, io->workspace_bytes, &a.ws, s);
-  if (rc) return rc;
+  ScanCtx* ctx = nullptr;
+  int rc;
+  if (io->scan_async) {
+    // the scan goes to the library's own stream, behind "heads ready" and behind the post kernel that last
+    // read the slot it is about to fill; the caller's stream waits for it before the post kernel
+    rc = scan_ctx(io->workspace, &ctx);
+    if (rc) return rc;
+    const int slot = rtm::next_scan_slot(io->workspace);
+    // (waits that are already satisfied are not enqueued: they would sit between consecutive scans)
+    if (io->heads_ready_event && cudaEventQuery(static_cast<cudaEvent_t>(io->heads_ready_event)) != cudaSuccess)
+      RTM_CUDA(cudaStreamWaitEvent(ctx->stream, static_cast<cudaEvent_t>(io->heads_ready_event), 0));
+    if (ctx->consumed_valid[slot] && cudaEventQuery(ctx->consumed[slot]) != cudaSuccess)
+      RTM_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->consumed[slot], 0));
+    (void)cudaGetLastError();  // cudaEventQuery reports "not ready" through the error state
+    rc = rtm::launch_decode_stage(io->head_p3, io->head_p4, io->head_p5, io->head_dtype, B, io->img_h, io->img_w, params,
+                                  io->workspace, io->workspace_bytes, &a.ws, ctx->stream);
+    if (rc) return rc;
+    RTM_CUDA(cudaEventRecord(ctx->scanned[a.ws.slot], ctx->stream));
+    RTM_CUDA(cudaStreamWaitEvent(s, ctx->scanned[a.ws.slot], 0));
+  } else {
+    rc = rtm::launch_decode_stage(io->head_p3, io->head_p4, io->head_p5, io->head_dtype, B, io->img_h, io->img_w, params,
+                                  io->workspace, io->workspace_bytes, &a.ws, s);
+    if (rc) return rc;
+    // a workspace that has been stepped with scan_async before keeps its slot bookkeeping up to date
+    const auto it = scan_table().find(io->workspace);
+    if (it != scan_table().end()) ctx = &it->second;
+  }
   a.prm = *params;
   a.iou_gate = rtm::iou_gate_for(params->iou_thres);
   a.out = rtm::NmsOut{io->scale, io->det_xyxy, io->det_conf, io->det_cls, io->det_anchor, io->det_keep, io->det_count,
@@ -172,5 +224,9 @@ extern "C" int rtm_post_backbone_step(const rtm_step_io* io, const rtm_nms_param
     else post_kernel<false><<<B, kPostThreads, smem, s>>>(a);
   }
   RTM_LAUNCH_CHECK("post_kernel");
+  if (ctx) {
+    RTM_CUDA(cudaEventRecord(ctx->consumed[a.ws.slot], s));
+    ctx->consumed_valid[a.ws.slot] = true;
+  }
   return RTM_OK;
 }

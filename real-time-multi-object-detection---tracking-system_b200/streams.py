@@ -339,12 +339,24 @@ class StreamBatch:
         self.frame_id += 1
 
     # -- stepping ----------------------------------------------------------
-    def step(self, heads, now: Optional[float] = None, frame_id: Optional[int] = None) -> None:
-        """One frame of every stream from device-resident head tensors (asynchronous)."""
+    def step(self, heads, now: Optional[float] = None, frame_id: Optional[int] = None, heads_ready=None) -> None:
+        """One frame of every stream from device-resident head tensors (asynchronous).
+
+        ``heads_ready``: None (default) - the head tensors are ordered on the current stream like any
+        other input.  ``True`` - they are complete already; a ``torch.cuda.Event`` - they are complete
+        once it has fired (e.g. the backbone runs on its own stream).  In both cases the head scan is
+        enqueued on a stream of the library's own (rtm_step_io.scan_async), so that consecutive scans
+        run back to back instead of queueing behind the previous step's post kernel; results are
+        ordered on the current stream exactly as in the default mode."""
         import torch
         now = time.time() if now is None else now                     # zone_engine.py:84
         fid = self.frame_id if frame_id is None else frame_id
         io = self._io(heads, now, fid)
+        if heads_ready is None:
+            io.scan_async, io.heads_ready_event = 0, None
+        else:
+            io.scan_async = 1
+            io.heads_ready_event = None if heads_ready is True else heads_ready.cuda_event
         if torch.cuda.current_device() == self.device.index:
             rc = self.lib.rtm_post_backbone_step(C.byref(io), C.byref(self.params), torch.cuda.current_stream().cuda_stream)
         else:

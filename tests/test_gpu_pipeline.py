@@ -184,3 +184,56 @@ def test_interleaved_stream_batches_do_not_disturb_each_other(pkg):
         assert np.array_equal(got[0], alone[k][0]) and np.array_equal(got[1], alone[k][1])
         for a, b in zip(got[2] + got[3], alone[k][2] + alone[k][3]):
             np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize("mode", ["resident", "event", "mixed"])
+def test_async_scan_steps_equal_synchronised_steps(pkg, mode):
+    """rtm_step_io.scan_async: the head scan runs on a stream of the library's own, behind a 'heads
+    ready' event, so that consecutive scans are back to back.  Same final state as one step at a time -
+    with resident heads, with heads copied in on a side stream (event per frame), and when the two
+    modes are mixed on one batch."""
+    import torch
+    from rtmodt_b200.workload import PostBackboneWorkload
+    S, F, steps = 12, 8, 60
+    dev = torch.device("cuda", 0)
+    wl = PostBackboneWorkload(S, F, first_stream=40, device=dev, dtype=torch.bfloat16)
+
+    def final(sb):
+        torch.cuda.synchronize()
+        sb.check_status()
+        h = sb.table.to_host()
+        n = h["count"]
+        ec = sb.zones.event_count.cpu().numpy()
+        return (n.copy(), h["next_id"].copy(), [h["track_id"][b, :n[b]].copy() for b in range(S)],
+                [h["xyxy"][b, :n[b]].copy() for b in range(S)], ec.copy(), [sb.zones.events[b, :ec[b]].cpu().numpy() for b in range(S)])
+
+    ref = pkg.StreamBatch(S, wl.zones, src_hw=(1080, 1920), classes=WANTED, max_tracks=512, device=dev)
+    for f in range(steps):
+        ref.step(wl.heads[f % F], now=1.7e9 + f / 30.0, frame_id=f)
+        torch.cuda.synchronize()
+    want = final(ref)
+
+    for attempt in range(3):
+        sb = pkg.StreamBatch(S, wl.zones, src_hw=(1080, 1920), classes=WANTED, max_tracks=512, device=dev)
+        side = torch.cuda.Stream(device=dev)
+        staging = [[torch.empty_like(t) for t in wl.heads[0]] for _ in range(3)]
+        for f in range(steps):
+            if mode == "resident" or (mode == "mixed" and f % 3 == 0):
+                sb.step(wl.heads[f % F], now=1.7e9 + f / 30.0, frame_id=f, heads_ready=True)
+            elif mode == "mixed" and f % 3 == 1:
+                sb.step(wl.heads[f % F], now=1.7e9 + f / 30.0, frame_id=f)
+            else:
+                # the frame's heads are produced on a side stream (stand-in for the backbone's stream)
+                buf = staging[f % 3]
+                if f >= 3:
+                    torch.cuda.current_stream().synchronize()          # the buffer's previous frame has been consumed
+                with torch.cuda.stream(side):
+                    for d, src in zip(buf, wl.heads[f % F]):
+                        d.copy_(src, non_blocking=True)
+                    ready = torch.cuda.Event()
+                    ready.record(side)
+                sb.step(buf, now=1.7e9 + f / 30.0, frame_id=f, heads_ready=ready)
+        got = final(sb)
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and np.array_equal(got[4], want[4])
+        for a, b in zip(got[2] + got[3] + got[5], want[2] + want[3] + want[5]):
+            np.testing.assert_array_equal(a, b)
