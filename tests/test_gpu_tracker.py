@@ -197,3 +197,18 @@ def test_optimal_assignment_resolves_conflicts_the_greedy_rule_cannot(pkg):
             np.testing.assert_array_equal(tid, exp_tid)
             np.testing.assert_array_equal(kind, exp_kind)
         assert trk._core._next_id == orc.next_id == (4 if mode == "greedy" else 3)
+
+
+@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("assignment,kalman", [("greedy", False), ("greedy", True), ("lapjv", False), ("lapjv", True)])
+def test_tracker_modes_soak(pkg, seed, assignment, kalman):
+    """Seeded clips with randomly drawn density, speed and dropout through every combination of the
+    assignment rule and the motion model: state, ids and per-detection assignments bit-exact."""
+    rng = np.random.default_rng(500 + seed)
+    n = int(rng.choice([5, 40, 150]))
+    kw = dict(num_objects=n, w_range=(20, float(rng.uniform(40, 160))), h_range=(30, float(rng.uniform(60, 300))),
+              vmax=float(rng.uniform(0.5, 6.0)), dropout=float(rng.uniform(0.0, 0.4)))
+    assign = tracker_ref.assign_lapjv_emulated if assignment == "lapjv" else tracker_ref.assign_rowloop
+    run_batch_against_oracle(pkg, B=3, F=25, slots=256, clip_kw=kw, max_tracks=2048, seed=700 + seed,
+                             track_kw=dict(assignment=assignment, use_kalman=kalman),
+                             oracle_kw=dict(assign=assign, use_kalman=kalman))
