@@ -12,23 +12,32 @@
 //       then the first max_det survivors
 //   N3  scale_boxes: subtract padding, divide by gain, clip to the source image
 //
-// Kernel plan
+// Kernel plan (numbers and experiments: DESIGN.md section 5)
 //   decode_tma   the production head scan.  Persistent CTAs; a producer warp pulls whole tiles
 //                (all 64 + nc channels x 80 consecutive anchors of one stream and level) into a
 //                ring of shared-memory stages with one TMA tensor copy each (full / empty
-//                mbarriers), so every head byte crosses HBM exactly once.  Five consumer warps
-//                work independently of each other (no block barrier): a warp owns 16 anchors of
-//                the tile, a lane owns two adjacent anchors x one class quarter and keeps a packed
-//                (bf16x2 / f16x2) running maximum over its class rows, bank-conflict free; the
-//                four lanes of an anchor combine by shuffle, and anchors that pass the confidence
-//                test get their four DFL sides decoded by their four lanes from shared memory.
-//   decode_ldg   fallback for shapes the tiling does not cover: 16-byte global loads of the
-//                class planes, warp-co-operative decode of the few passing anchors.
-//   candidates   are written dense by anchor plus a bitmask (see nms_body.cuh): no atomics, no
-//                per-frame reset, and the list order is ultralytics' filtered-tensor order.
-//   nms          one CTA per stream (nms_body.cuh): shuffle/shared-memory bitonic sort of 64-bit
-//                (score desc, rank asc) keys, greedy scan one survivor at a time with the alive
-//                bitmask rebuilt by warp ballots, stop at max_det, rescale, write in score order.
+//                mbarriers, L2 evict-first), so every head byte crosses HBM exactly once.  Tiles
+//                are handed out by a ticket counter after a static first ring round, so that any
+//                set of resident CTAs shares the work - the scan runs beside the previous step's
+//                post kernel (programmatic dependent launch) or on a stream of its own
+//                (scan_async).  Five consumer warps work independently of each other (no block
+//                barrier): a warp owns 16 anchors of the tile, a lane owns two adjacent anchors x
+//                one class quarter and keeps a packed (bf16x2 / f16x2) running maximum over its
+//                class rows, bank-conflict free; the four lanes of an anchor combine by shuffle,
+//                and anchors that pass the confidence test get their four DFL sides decoded by
+//                their four lanes from shared memory.  SPLIT variant (RTM_TMA_SPLIT=1): class
+//                planes in the ring, box planes as per-warp sub-tiles fetched only for candidates.
+//   decode_scan  no ring: streams the class planes with 16-byte loads, reads the box planes only
+//                for the 8-anchor groups that hold a candidate; the path for shapes the tiling
+//                does not cover (RTM_DECODE_IMPL=scan forces it).
+//   decode_ldg   the first version of the scan, kept for A/B runs (RTM_DECODE_IMPL=ldg).
+//   candidates   are written dense by anchor plus a bitmask into one slot of a ring of three (see
+//                nms_body.cuh): no atomics, no per-frame reset, and the list order is ultralytics'
+//                filtered-tensor order.
+//   nms          one CTA per stream (nms_body.cuh): counting-rank sort of (class, score desc, rank
+//                asc) keys, class-parallel greedy scan (warp heads, parallel filter, warp tails;
+//                block-wide scan for long segments, agnostic NMS and boxes outside the class
+//                guard), first max_det survivors by score, rescale, write in score order.
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through the runtime)
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
