@@ -1,15 +1,19 @@
 // rtm_post_backbone_step: the whole post-backbone step of B streams in two launches.
 //
-//   1. decode_tma / decode_ldg (nms.cu)   head scan, candidate lists            HBM-bound
+//   1. decode_tma / decode_scan (nms.cu)  head scan, candidate lists            HBM-bound
 //   2. post_kernel (this file)            one CTA per stream: NMS -> tracker step -> zone step
 //
 // The three per-stream stages are small and strictly ordered; as separate kernels each paid a
-// launch / drain overhead that was larger than its work (profiles/r1_*: 64-CTA kernels of
-// 12-30 us whose SMs were busy a fraction of that).  Fused, the detections of a stream stay with
-// the CTA that produced them (the tracker reads them back through L1 right after the block
-// barrier) and the step costs one dependent launch instead of three.  The stage bodies are the
-// same device functions the stand-alone kernels run (nms_body.cuh, track_body.cuh, zone_body.cuh),
-// so the fused step is bit-identical to rtm_decode_nms + rtm_track_step + rtm_zone_step.
+// launch / drain overhead that was larger than its work.  Fused, the detections of a stream stay
+// with the CTA that produced them and the step costs one dependent launch instead of three.  The
+// stage bodies are the same device functions the stand-alone kernels run (nms_body.cuh,
+// track_body.cuh, zone_body.cuh), so the fused step is bit-identical to rtm_decode_nms +
+// rtm_track_step_ex + rtm_zone_step.  What does not depend on this frame's detections (head of the
+// track table, zone table, polygons) is prefetched into shared memory behind the NMS.
+//
+// Consecutive steps overlap: the post kernel releases its dependents at once, and the next scan is
+// a programmatic dependent launch (single stream), or runs on a stream of the library's own behind
+// a caller-supplied "heads ready" event (rtm_step_io.scan_async) so that scans are back to back.
 #include <stdlib.h>
 
 #include <unordered_map>
