@@ -78,3 +78,31 @@ def test_tracker_oracle_with_motion_model_bridges_a_detection_gap():
     assert plain.next_id - 1 == 2 * n_obj                 # every identity broke at the gap
     assert kal.next_id - 1 == n_obj                       # none did
     assert len(kal.kf_mean) == len(kal) and kal.kf_mean.dtype == np.float32
+
+
+def test_lapjv_emulation_is_the_exhaustive_optimum_on_small_matrices():
+    """The scipy emulation of lap.lapjv(extend_cost=True, cost_limit) against brute force: over all
+    partial matchings that use only pairs cheaper than the limit, it attains the minimum of
+    sum(cost of matched pairs) + limit/2 * (unmatched rows + unmatched columns)."""
+    import itertools
+    rng = np.random.default_rng(11)
+    thresh = 0.8
+    limit = 1 - thresh
+    for _ in range(300):
+        t, n = int(rng.integers(1, 5)), int(rng.integers(1, 5))
+        iou = rng.uniform(0.6, 1.0, (t, n)).astype(np.float32)
+        cost = (np.float32(1) - iou).astype(np.float64)
+        best = None
+        for k in range(0, min(t, n) + 1):
+            for rows in itertools.combinations(range(t), k):
+                for cols in itertools.permutations(range(n), k):
+                    if any(cost[r, c] >= limit for r, c in zip(rows, cols)):
+                        continue
+                    total = sum(cost[r, c] for r, c in zip(rows, cols)) + limit / 2 * ((t - k) + (n - k))
+                    if best is None or total < best - 1e-15:
+                        best = total
+        rows, cols, ur, uc = tracker_ref.assign_lapjv_emulated(iou, thresh)
+        got = sum(cost[r, c] for r, c in zip(rows, cols)) + limit / 2 * (len(ur) + len(uc))
+        assert abs(got - best) < 1e-12, (iou, rows, cols)
+        assert all(cost[r, c] < limit for r, c in zip(rows, cols))
+        assert sorted(rows + ur) == list(range(t)) and sorted(cols + uc) == list(range(n))
