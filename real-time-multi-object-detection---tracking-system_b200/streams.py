@@ -547,6 +547,7 @@ class HostFeeder:
         now = time.time() if now is None else now
         fid = b.frame_id if frame_id is None else frame_id
         io = b._io(None, now, fid)
+        io.scan_async, io.heads_ready_event = 0, None          # the copy and the kernels share the slot's stream
         io.head_p3, io.head_p4, io.head_p5 = (t.data_ptr() for t in slot["dev_heads"])
         io.head_dtype = _lib.dtype_code(slot["dev_heads"][0].dtype)
         h = _lib.StepHostIO()
