@@ -130,7 +130,9 @@ extern "C" int rtm_post_backbone_step(const rtm_step_io* io, const rtm_nms_param
   const size_t smem = work + sizeof(rtm::TrackPrefetch) + sizeof(rtm::ZonePrefetch);
 
   if (!fuse_enabled() || smem > 200 * 1024) {
-    // unfused fallback: the three stand-alone entry points back to back
+    // unfused fallback: the three stand-alone entry points back to back, all on the caller's stream
+    if (io->scan_async && io->heads_ready_event)
+      RTM_CUDA(cudaStreamWaitEvent(s, static_cast<cudaEvent_t>(io->heads_ready_event), 0));
     int rc = rtm_decode_nms(io->head_p3, io->head_p4, io->head_p5, io->head_dtype, B, io->img_h, io->img_w, params,
                             io->scale, io->det_xyxy, io->det_conf, io->det_cls, io->det_anchor, io->det_keep,
                             io->det_count, io->det_stride, io->status, io->workspace, io->workspace_bytes, stream);
