@@ -84,7 +84,7 @@ int next_pow2(int v) {
 // candidate interchange arrays + one set of spill arrays.  Consecutive head scans take
 // consecutive slots, so the scan of step k+2 may already run while the post kernel of step k
 // still reads its own slot (programmatic dependent launch: see decode_tma_kernel and post.cu).
-constexpr int kCandSlots = 3;
+using rtm::kCandSlots;
 constexpr size_t kWorkspaceHeader = 128 * kCandSlots;
 
 size_t workspace_layout(int B, int A, char* base, Workspace* ws, int half = 0) {
@@ -206,6 +206,7 @@ struct TmaGeom {
   int tile_bytes;
   int evict_first;    // L2 evict-first hint on the tile loads
   int static_rounds;  // ring rounds with the static schedule (tile = blockIdx + k * grid) before tickets take over
+  int trigger;        // release programmatic dependents (the next scan on the same stream) at once
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -373,6 +374,9 @@ __global__ void __launch_bounds__(tma_threads(kTileW)) decode_tma_kernel(const _
   // reads or writes what that kernel touches: the head tensors are inputs, the candidate list goes
   // to another slot of the ring, the ticket counter of that slot was re-armed two steps ago.  The
   // step's own post kernel is an ordinary launch and starts after everything before it has finished.
+  // The scan releases its own dependents at once as well: when the next launch on its stream is the
+  // next step's scan (rtm_step_io.scan_async), that grid's CTAs move in as this one's retire.
+  if (tg.trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -407,9 +411,12 @@ __global__ void __launch_bounds__(tma_threads(kTileW)) decode_tma_kernel(const _
       // second round are drawn meanwhile (all in flight together), later ones one ring cycle ahead
       const int nstatic = stages * tg.static_rounds;
       const int dyn0 = nstatic * static_cast<int>(gridDim.x);
+      // (static_rounds = 0: the first round comes off the counter as well, `stages` tickets in one draw - a CTA
+      // that only becomes resident late, e.g. behind another kernel's CTAs, then holds no tile of its own back)
+      const int first = nstatic == 0 ? atomicAdd(ws.tile_counter, stages) : 0;
       bool done = false;
       for (int k = 0; k < stages && !done; ++k) {
-        const int t = static_cast<int>(blockIdx.x) + k * static_cast<int>(gridDim.x);
+        const int t = nstatic == 0 ? first + k : static_cast<int>(blockIdx.x) + k * static_cast<int>(gridDim.x);
         if (t < tg.total_tiles) {
           issue(k, t);
         } else {
@@ -1269,9 +1276,11 @@ int launch_decode_tma_w(const void* p3, const void* p4, const void* p5, const He
   tg.total_tiles = tg.tiles_before[3] * B;
   tg.tile_bytes = tile_rows * kTileW * static_cast<int>(sizeof(T));
   static const int static_env = env_int("RTM_TMA_STATIC_ROUNDS", 1);
-  tg.static_rounds = static_env < 1 ? 1 : static_env;
+  tg.static_rounds = static_env < 0 ? 0 : static_env;
   static const int evict_env = env_int("RTM_TMA_EVICT_FIRST", 1);
   tg.evict_first = evict_env;
+  static const int trigger_env = env_int("RTM_SCAN_TRIGGER", 0);
+  tg.trigger = trigger_env;
   if (tg.tile_bytes % 128 != 0) return 0;
   // ring depth and residency: as many tiles in flight per SM as fit (RTM_TMA_STAGES / RTM_TMA_CTAS override)
   static const int stages_env = env_int("RTM_TMA_STAGES", 0), ctas_env = env_int("RTM_TMA_CTAS", 0);

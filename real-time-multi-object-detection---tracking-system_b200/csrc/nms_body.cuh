@@ -19,7 +19,10 @@
 namespace rtm {
 
 constexpr float kMaxWh = 7680.f;    // ultralytics non_max_suppression max_wh
-constexpr int kNmsSmemCand = 2048;  // candidates handled entirely in shared memory
+#ifndef RTM_NMS_SMEM_CAND
+#define RTM_NMS_SMEM_CAND 2048
+#endif
+constexpr int kNmsSmemCand = RTM_NMS_SMEM_CAND;  // candidates handled entirely in shared memory
 constexpr int kIdxBits = 15;        // candidate rank (< 32768) in the low key bits
 constexpr int kMaxAnchors = 1 << 15;
 constexpr int kMaxDetCap = 1024;
@@ -62,8 +65,15 @@ inline float iou_gate_for(double thr) {
   return static_cast<double>(f) > thr ? f : nextafterf(f, INFINITY);
 }
 
+// Ring of candidate-list slots in the workspace: consecutive head scans fill consecutive slots.  Three would do
+// for the overlap of a scan with the previous step's post kernel; the ring is deeper so that in scan_async mode
+// the "slot free again" ordering can be enqueued for kSlotWaitEvery scans at a time instead of before every scan
+// (an event wait between two scans keeps the second from being launched ahead, ~1.6 us per step when measured).
+constexpr int kCandSlots = 8;
+constexpr int kSlotWaitEvery = 4;  // must divide kCandSlots; kCandSlots - kSlotWaitEvery steps of run-ahead remain
 // slot of the candidate ring the next scan of `workspace` will take (defined in nms.cu)
 int next_scan_slot(const void* workspace);
+
 
 // D1 + N1 only (defined in nms.cu): scans the head tensors and leaves the candidate list of every
 // stream in `workspace`; *ws describes it for the NMS stage.

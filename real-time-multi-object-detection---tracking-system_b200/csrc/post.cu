@@ -25,6 +25,9 @@
 namespace {
 
 constexpr int kPostThreads = 512;
+#ifndef RTM_POST_CTAS_PER_SM
+#define RTM_POST_CTAS_PER_SM 1  // register budget: 2 = at most 64 registers
+#endif
 
 struct PostArgs {
   rtm::Workspace ws;
@@ -38,7 +41,7 @@ struct PostArgs {
 };
 
 template <bool WITH_OPTIMAL>
-__global__ void __launch_bounds__(kPostThreads, 1) post_kernel(const __grid_constant__ PostArgs a) {
+__global__ void __launch_bounds__(kPostThreads, RTM_POST_CTAS_PER_SM) post_kernel(const __grid_constant__ PostArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_keep[rtm::kMaxDetCap];
   __shared__ int s_scan[33];
@@ -79,9 +82,10 @@ namespace {
 // scan_async: per workspace, the stream the scans go to and the events that order it with the caller's stream
 struct ScanCtx {
   cudaStream_t stream = nullptr;
-  cudaEvent_t scanned[3] = {nullptr, nullptr, nullptr};  // slot's candidate list is complete
-  cudaEvent_t consumed[3] = {nullptr, nullptr, nullptr}; // slot's post kernel is done (recorded on the caller's stream)
-  bool consumed_valid[3] = {false, false, false};
+  cudaEvent_t scanned[rtm::kCandSlots] = {};   // slot's candidate list is complete
+  cudaEvent_t consumed[rtm::kCandSlots] = {};  // slot's post kernel is done (recorded on the caller's stream)
+  bool consumed_valid[rtm::kCandSlots] = {};
+  int covered = 0;  // scans to come (on `stream`) whose slots are already known to be free: see the waits below
 };
 
 std::unordered_map<const void*, ScanCtx>& scan_table() {
@@ -93,7 +97,7 @@ int scan_ctx(const void* workspace, ScanCtx** out) {
   ScanCtx& c = scan_table()[workspace];
   if (!c.stream) {
     RTM_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < rtm::kCandSlots; ++i) {
       RTM_CUDA(cudaEventCreateWithFlags(&c.scanned[i], cudaEventDisableTiming));
       RTM_CUDA(cudaEventCreateWithFlags(&c.consumed[i], cudaEventDisableTiming));
     }
@@ -101,6 +105,18 @@ int scan_ctx(const void* workspace, ScanCtx** out) {
   *out = &c;
   return RTM_OK;
 }
+
+#ifdef RTM_PROBES
+// tools/probe_overlap.py: what the orderings around the scan cost (results are NOT valid with any bit set)
+int probe_bits() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RTM_PROBE_BITS");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+#endif
 
 bool fuse_enabled() {
   static int v = -1;
@@ -179,21 +195,40 @@ extern "C" int rtm_post_backbone_step(const rtm_step_io* io, const rtm_nms_param
     // (waits that are already satisfied are not enqueued: they would sit between consecutive scans)
     if (io->heads_ready_event && cudaEventQuery(static_cast<cudaEvent_t>(io->heads_ready_event)) != cudaSuccess)
       RTM_CUDA(cudaStreamWaitEvent(ctx->stream, static_cast<cudaEvent_t>(io->heads_ready_event), 0));
-    if (ctx->consumed_valid[slot] && cudaEventQuery(ctx->consumed[slot]) != cudaSuccess)
-      RTM_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->consumed[slot], 0));
+#ifdef RTM_PROBES
+    if (!(probe_bits() & 2))  // timing probe only: slot reuse unordered
+#endif
+    if (ctx->covered == 0) {
+      // this scan's slot and the ones after it up to the next multiple of kSlotWaitEvery: their last readers
+      // (post kernels of at least kCandSlots - kSlotWaitEvery + 1 steps ago) must be done before they are refilled
+      const int group_end = (slot / rtm::kSlotWaitEvery + 1) * rtm::kSlotWaitEvery;
+      for (int sl = slot; sl < group_end; ++sl)
+        if (ctx->consumed_valid[sl] && cudaEventQuery(ctx->consumed[sl]) != cudaSuccess)
+          RTM_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->consumed[sl], 0));
+      ctx->covered = group_end - slot;
+    }
+    --ctx->covered;
     (void)cudaGetLastError();  // cudaEventQuery reports "not ready" through the error state
     rc = rtm::launch_decode_stage(io->head_p3, io->head_p4, io->head_p5, io->head_dtype, B, io->img_h, io->img_w, params,
                                   io->workspace, io->workspace_bytes, &a.ws, ctx->stream);
     if (rc) return rc;
-    RTM_CUDA(cudaEventRecord(ctx->scanned[a.ws.slot], ctx->stream));
-    RTM_CUDA(cudaStreamWaitEvent(s, ctx->scanned[a.ws.slot], 0));
+#ifdef RTM_PROBES
+    if (!(probe_bits() & 1))  // timing probe only: the post kernel races with its scan
+#endif
+    {
+      RTM_CUDA(cudaEventRecord(ctx->scanned[a.ws.slot], ctx->stream));
+      RTM_CUDA(cudaStreamWaitEvent(s, ctx->scanned[a.ws.slot], 0));
+    }
   } else {
     rc = rtm::launch_decode_stage(io->head_p3, io->head_p4, io->head_p5, io->head_dtype, B, io->img_h, io->img_w, params,
                                   io->workspace, io->workspace_bytes, &a.ws, s);
     if (rc) return rc;
     // a workspace that has been stepped with scan_async before keeps its slot bookkeeping up to date
     const auto it = scan_table().find(io->workspace);
-    if (it != scan_table().end()) ctx = &it->second;
+    if (it != scan_table().end()) {
+      ctx = &it->second;
+      ctx->covered = 0;  // this scan is not on the scan stream: the next asynchronous one orders itself afresh
+    }
   }
   a.prm = *params;
   a.iou_gate = rtm::iou_gate_for(params->iou_thres);
@@ -226,6 +261,11 @@ extern "C" int rtm_post_backbone_step(const rtm_step_io* io, const rtm_nms_param
     // An ordinary launch on purpose.  Launching this kernel as a programmatic dependent of its own
     // step's scan as well was measured slower (56.7 vs 46.0 us per step: its CTAs need whole SMs and
     // hold them while they wait) and would need the scan to wait for the previous post kernel.
+#ifdef RTM_PROBES
+    if (probe_bits() & 4)  // timing probe only: scans alone (the NMS stage would have re-armed the slot's ticket counter)
+      RTM_CUDA(cudaMemsetAsync(a.ws.tile_counter, 0, sizeof(int), s));
+    else
+#endif
     if (optimal) post_kernel<true><<<B, kPostThreads, smem, s>>>(a);
     else post_kernel<false><<<B, kPostThreads, smem, s>>>(a);
   }

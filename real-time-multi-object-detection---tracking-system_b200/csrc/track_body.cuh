@@ -153,7 +153,10 @@ __device__ __forceinline__ float box_area(const float4 b) {
 
 // The head of a stream's input table, staged in shared memory ahead of use: the fused kernel
 // issues these loads before the NMS stage so that their latency is off the critical path.
-constexpr int kTrackPrefRows = 512;
+#ifndef RTM_TRACK_PREF_ROWS
+#define RTM_TRACK_PREF_ROWS 512
+#endif
+constexpr int kTrackPrefRows = RTM_TRACK_PREF_ROWS;
 struct TrackPrefetch {
   float4 box[kTrackPrefRows];   // stored box (tracker.py:100: the last matched detection)
   float4 abox[kTrackPrefRows];  // box the association sees: the stored one, or the filter's prediction

@@ -50,7 +50,10 @@ __device__ __forceinline__ int point_in_polygon(const int2* __restrict__ poly, i
 // The stream's zone table and polygons, staged in shared memory ahead of use (the fused kernel
 // issues these loads before the NMS stage).  kZonePrefVertices vertices are staged; streams with
 // more read their polygons from global memory.
-constexpr int kZonePrefVertices = 2048;
+#ifndef RTM_ZONE_PREF_VERTICES
+#define RTM_ZONE_PREF_VERTICES 2048
+#endif
+constexpr int kZonePrefVertices = RTM_ZONE_PREF_VERTICES;
 struct ZonePrefetch {
   int2 poly[kZonePrefVertices];
   double dwell[kMaxZonesPerStream], cool[kMaxZonesPerStream];
