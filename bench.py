@@ -462,9 +462,9 @@ def run_b200(args):
             "single_stream": {"value": total_streams * K / (ms_single / 1e3), "ms_per_step": ms_single / K,
                               "note": "the same K steps with both kernels on the caller's stream (rtm_step_io.scan_async = 0)"},
             "clocks": sampler.summary(), "e2e": e2e,
-            # kernels of the library inside the timed region: head scan + NMS + tracker/zones per step in the
-            # scan_async mode `value` is timed in (RTM_SPLIT_POST=0: head scan + fused post kernel)
-            "gpu_launches": K * (2 if os.environ.get("RTM_SPLIT_POST", "1") == "0" else 3), "roofline": roofline,
+            # kernels of the library inside the timed region: head scan + fused post kernel per step (the per-kernel
+            # pass above counted exactly these launches for the same K steps)
+            "gpu_launches": sum(v["launches"] for v in kernels.values()), "roofline": roofline,
             "cpu_baseline": cpu, "kernels": kernels, "parity": parity,
             "summary": dict(zip(sharding.COUNTERS, totals), live_tracks_rank0=int(sum(len(t) for t in tracks)),
                             streams_reporting=len(gathered)),
