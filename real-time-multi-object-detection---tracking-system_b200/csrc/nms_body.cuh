@@ -340,6 +340,13 @@ __device__ __forceinline__ void segment_tail(const float4* sbox, const float* sa
     __syncwarp();
     if (lane == 0) alive0[base >> 5] = 0u;  // consumed (bits past e belong to the next segment's head: already zero)
     if (!__any_sync(kFull, valid) || kc >= max_det) continue;
+#ifdef RTM_TIMELINE
+    if (lane == 0 && g_timeline) {
+      atomicAdd(&g_timeline[blockIdx.x * 32 + 22], 1ull);                                         // chunks with work
+      atomicAdd(&g_timeline[blockIdx.x * 32 + 23], (unsigned long long)__popc(word));  // alive candidates in it
+    }
+    const unsigned long long t_a = clock64();
+#endif
     const float4 mb = valid ? sbox[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     const float ma = valid ? sarea[i] : 0.f;
     bool alive = valid;
@@ -351,11 +358,24 @@ __device__ __forceinline__ void segment_tail(const float4* sbox, const float* sa
         if (alive && suppresses(sbox[p], sarea[p], mb, ma, gate)) alive = false;
       }
     }
+#ifdef RTM_TIMELINE
+    const unsigned long long t_b = clock64();
+#endif
     uint32_t keptbits;
     kc = warp_chunk_resolve(mb, ma, alive, kc, max_det, gate, &keptbits);
     if (lane == 0 && keptbits) atomicOr(&kmask[base >> 5], keptbits);
     __syncwarp();
+#ifdef RTM_TIMELINE
+    if (lane == 0 && g_timeline) {
+      atomicAdd(&g_timeline[blockIdx.x * 32 + 24], (unsigned long long)__popc(keptbits));   // survivors found in the tail
+      atomicAdd(&g_timeline[blockIdx.x * 32 + 25], t_b - t_a);                               // cycles: vs earlier tail survivors
+      atomicAdd(&g_timeline[blockIdx.x * 32 + 26], (unsigned long long)clock64() - t_b);     // cycles: chunk resolve
+    }
+#endif
   }
+#ifdef RTM_TIMELINE
+  if (lane == 0 && g_timeline) atomicMax(&g_timeline[blockIdx.x * 32 + 27], (unsigned long long)(e - s));  // longest segment
+#endif
 }
 
 // Block-wide greedy scan over the candidates whose bit is set in alive0 (register-resident:

@@ -64,3 +64,20 @@ tot = t[:, :, 30] - t[:, :, 0]
 print(f"  {'whole CTA':28s} mean {tot.mean():8.0f}   max {tot.max(axis=1).mean():8.0f}")
 span = t[:, :, 30].max(axis=1) - t[:, :, 0].min(axis=1)
 print(f"  first CTA start -> last CTA end: {span.mean():.0f} ns")
+# the slowest CTA of each step: where its time went (mean over steps) - that CTA sets the kernel's duration
+slow = tot.argmax(axis=1)
+print("  slowest CTA of a step, per stage:")
+prev = ids[0]
+for i in ids[1:]:
+    a, b = t[np.arange(len(slow)), slow, i], t[np.arange(len(slow)), slow, prev]
+    ok = (a > 0) & (b > 0)
+    if ok.any():
+        print(f"    {MARKS[i]:28s} {np.mean((a - b)[ok]):8.0f}   (in {int(ok.sum())} of {len(slow)} steps)")
+        prev = i
+print("  slowest streams:", np.bincount(slow, minlength=S).argsort()[::-1][:6].tolist())
+# tail counters (RTM_TIMELINE builds): per CTA and step
+names = {22: "tail chunks with work", 23: "alive candidates in them", 24: "tail survivors", 25: "cycles vs earlier tail survivors",
+         26: "cycles chunk resolve", 27: "longest class segment"}
+for k, nm in names.items():
+    v = t[:, :, k]
+    print(f"  {nm:34s} mean {v.mean():9.1f}   slowest CTA {v[np.arange(len(slow)), slow].mean():9.1f}   max {v.max():9.0f}")
