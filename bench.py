@@ -296,7 +296,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "detections": sum(r[3] for r in res), "events": sum(r[4] for r in res),
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, total_streams):
@@ -470,7 +470,7 @@ def run_b200(args):
                             streams_reporting=len(gathered)),
         }
         line.update(extras)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -659,8 +659,20 @@ def letterbox_bench(pkg, lib, dev, S, hbm_peak, iters=20):
             "algorithmic_bytes_per_launch": alg, "config": f"{S} x 1080p u8 BGR -> 640x640 bf16 CHW"}
 
 
+def emit(line) -> None:
+    """The one JSON line of the run, on the process's original stdout."""
+    os.write(_STDOUT_FD, (json.dumps(line) + "\n").encode())
+
+
+_STDOUT_FD = 1
+
 if __name__ == "__main__":
     a = parse_args()
+    # stdout carries exactly one JSON line: whatever libraries print there (NCCL's version banner under torchrun,
+    # for one) goes to stderr instead
+    sys.stdout.flush()
+    _STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
     if a.impl == "reference":
         run_reference(a)
     else:
