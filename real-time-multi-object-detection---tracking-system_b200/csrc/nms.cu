@@ -1291,7 +1291,10 @@ int launch_decode_tma_w(const void* p3, const void* p4, const void* p5, const He
   if (tg.stages > kMaxStages) tg.stages = kMaxStages;
   while (tg.stages > 1 && (static_cast<size_t>(tg.stages) * tg.tile_bytes + box_smem) * ctas_per_sm > smem_budget) --tg.stages;
   while (ctas_per_sm > 1 && (static_cast<size_t>(tg.stages) * tg.tile_bytes + box_smem) * ctas_per_sm > smem_budget) --ctas_per_sm;
-  const size_t smem = static_cast<size_t>(tg.stages) * tg.tile_bytes + box_smem;
+  // RTM_TMA_SMEM_PAD_KB: unused shared memory on top of the ring (experiments: caps how many scan CTAs - of this and of
+  // an overlapping scan - fit on an SM, i.e. how much room is left for another kernel's CTAs; 0 = none)
+  static const int pad_env = env_int("RTM_TMA_SMEM_PAD_KB", 0);
+  const size_t smem = static_cast<size_t>(tg.stages) * tg.tile_bytes + box_smem + static_cast<size_t>(pad_env > 0 ? pad_env : 0) * 1024;
   if (smem > 220 * 1024) return 0;
   static size_t configured = 0;
   if (smem > configured) {

@@ -441,6 +441,7 @@ template <int THREADS, bool IN_SMEM>
 __device__ __forceinline__ int nms_run(const Workspace& ws, const rtm_nms_params& prm, const float iou_gate,
                                        const NmsOut& out, const int b, const int n, unsigned char* smem,
                                        int* s_keep, int* s_scan) {
+  static_assert(kNmsSmemCand % THREADS == 0 && kNmsSmemCand / 32 <= 2048, "per-thread candidate slots are kNmsSmemCand / THREADS");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int kWarps = THREADS / 32;
   const int A = ws.num_anchors, W = ws.words;
