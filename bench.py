@@ -4,20 +4,22 @@
     python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
     python bench.py --impl reference [--gpus N] [--steps K] ...    # the reference's CPU path
 
-Workload (config.workload): BASELINE.json configs[2] per GPU - 64 synthetic 1080p streams,
-YOLOv8 head tensors of 8400 anchors x (64 + 80) channels per stream-frame (planted objects,
-bf16 like the reference's half=True network output), class-aware NMS, ByteTrack-style
-association and 4 polygon zones per stream.  One step = one frame of every stream of the
-rank: decode + NMS -> tracker -> zones.  N ranks shard streams with no per-frame collective
-(weak scaling: 64 streams per GPU; N = 8 is configs[3], 512 streams); one NCCL reduction of
-the run summary happens after the timed region.
+Workload (config.workload).  N = 1: BASELINE.json configs[2] - 64 synthetic 1080p streams, YOLOv8 head
+tensors of 8400 anchors x (64 + 80) channels per stream-frame (planted objects, bf16 like the
+reference's half=True network output), class-aware NMS, ByteTrack-style association and 4 polygon
+zones per stream.  N > 1: configs[3] - 512 such streams in contiguous shards of 512 / N per GPU
+(256 / 128 / 64), no per-frame collective; one NCCL reduction of the run summary and one gather of the
+event records happen after the timed region.  One step = one frame of every stream of the rank:
+decode + NMS -> tracker -> zones, ONE kernel launch.  Every stream's tensors depend on its global id
+only, so both arms and every sharding see identical inputs.
 
-The JSON line carries: `value` (device-resident inputs, CUDA-event timed, max over ranks),
-`e2e` (same step through rtm_post_backbone_step_host: pinned host head tensors -> H2D ->
-kernels -> D2H of detections/events, copies inside the timed region), `roofline` of the
-dominant kernel (decode_candidates: algorithmic bytes / measured launch time vs the measured
-HBM peak), `cpu_baseline` (the oracle port on one host core over a bounded sample), latency
-percentiles, clocks and a parity spot-check against the oracle.
+The JSON line carries: `value` (device-resident inputs, CUDA-event timed, max over ranks), `e2e` (same
+step through rtm_post_backbone_step_host: pinned host head tensors -> H2D -> kernel -> D2H of
+detections / events, copies inside the timed region, with the bare-copy ceiling of the same run beside
+it), `roofline` (algorithmic head bytes / the step kernel's average duration in the timed region vs the
+measured HBM peak), `cpu_baseline` (the CPU chain on one host core over a bounded sample), latency
+percentiles, clocks, and `parity`: every rank checks its first 64 streams x 16 frames against the oracle
+chain, and rank 0 re-runs streams of the other ranks' shards to show N ranks = 1 rank bit for bit.
 """
 
 from __future__ import annotations
@@ -37,7 +39,8 @@ if ROOT not in sys.path:
 METRIC = "tracked_frames_per_sec_post_backbone"
 UNIT = "frames/s"
 WANTED = [0, 1, 2, 3, 5, 7]
-STREAMS_PER_GPU = 64
+STREAMS_1GPU = 64          # configs[2]
+TOTAL_STREAMS_MULTI = 512  # configs[3]
 CYCLE_FRAMES = 16
 FPS = 30.0
 T0 = 1_700_000_000.0
@@ -49,14 +52,18 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--streams", type=int, default=STREAMS_PER_GPU, help="streams per GPU")
+    ap.add_argument("--streams", type=int, default=0, help="streams per GPU (default: 64 on one GPU, 512 / N on N)")
     ap.add_argument("--frames", type=int, default=CYCLE_FRAMES, help="distinct frames in the replayed cycle")
     ap.add_argument("--head-dtype", default="bf16", choices=["bf16", "f16", "f32"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip letterbox / latency / f32-head side measurements")
-    return ap.parse_args()
+    ap.add_argument("--no-extras", action="store_true", help="skip letterbox / latency / dense-crowd / opt-in mode side measurements")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity leg (experiments only)")
+    a = ap.parse_args()
+    if a.streams <= 0:
+        a.streams = STREAMS_1GPU if a.gpus <= 1 else max(1, TOTAL_STREAMS_MULTI // a.gpus)
+    return a
 
 
 def peaks():
@@ -221,7 +228,7 @@ def cpu_port_throughput(host_frames, zones, seconds):
 
 def _reference_worker(args):
     """Worker process of the reference arm: owns `streams`, steps them W + K times."""
-    (streams, frames, steps, warmup, threads, barrier_path) = args
+    (streams, frames, steps, warmup, threads, barrier_path, head_dtype) = args
     import torch
     torch.set_num_threads(threads)
     if ROOT not in sys.path:
@@ -229,7 +236,11 @@ def _reference_worker(args):
     importlib.import_module("rtmodt_b200")
     from rtmodt_b200.workload import PostBackboneWorkload
     ref = load_reference_modules()
-    wl = [PostBackboneWorkload(1, frames, first_stream=s, device="cpu", dtype=torch.float32) for s in streams]
+    # the very tensors the CUDA arm reads: generated per global stream id, rounded to the head dtype, widened to f32
+    tdt = {"bf16": torch.bfloat16, "f16": torch.float16, "f32": torch.float32}[head_dtype]
+    wl = [PostBackboneWorkload(1, frames, first_stream=s, device="cpu", dtype=tdt) for s in streams]
+    for w in wl:
+        w.heads = [[t.float() for t in fr] for fr in w.heads]
     cpu = [CpuStream(w.zones[0], ref, os.path.dirname(barrier_path)) for w in wl]
     dets = evs = 0
 
@@ -278,7 +289,7 @@ def run_reference(args):
         f.write(str(workers))
     ctx = mp.get_context("spawn")
     with ctx.Pool(workers) as pool:
-        res = pool.map(_reference_worker, [(s, args.frames, args.steps, args.warmup, threads, barrier) for s in shards])
+        res = pool.map(_reference_worker, [(s, args.frames, args.steps, args.warmup, threads, barrier, args.head_dtype) for s in shards])
     t0 = min(r[0] for r in res)
     t1 = max(r[1] for r in res)
     frames = sum(r[2] for r in res)
@@ -289,7 +300,7 @@ def run_reference(args):
               + cpu_chain_description(True if used_ref else None))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * (t1 - t0) / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * (t1 - t0) / args.steps, "higher_is_better": True, "scaling": scaling_label(args.gpus),
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, total_streams),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers * threads, "kind": "port", "sample": sample},
@@ -299,14 +310,27 @@ def run_reference(args):
     emit(line)
 
 
+def scaling_label(n_gpus):
+    # N = 1 is configs[2] (64 streams); N = 2 / 4 / 8 all run configs[3], a fixed total of 512 streams
+    return "weak" if n_gpus <= 1 else "strong"
+
+
 def workload_config(args, total_streams):
-    return {"workload": "BASELINE.json configs[2] per GPU: 64 synthetic 1080p streams, 8400 anchors x 80 classes, "
-                        "ByteTrack + 4 zones (N=8: configs[3], 512 streams)",
+    if args.gpus <= 1:
+        name = ("BASELINE.json configs[2]: %d synthetic 1080p streams on one GPU, 8400 anchors x 80 classes, ByteTrack + 4 zones"
+                % total_streams)
+    else:
+        name = ("BASELINE.json configs[3]: %d synthetic 1080p streams sharded over %d GPUs (%d per GPU, contiguous), full "
+                "post-backbone pipeline: 8400 anchors x 80 classes, ByteTrack + 4 zones" % (total_streams, args.gpus, args.streams))
+    return {"workload": name,
             "streams_per_gpu": args.streams, "total_streams": total_streams, "head_dtype": args.head_dtype,
             "anchors": 8400, "classes": 80, "zones_per_stream": 4, "objects_per_stream": 30,
             "cycle_frames": args.frames, "class_filter": WANTED, "conf": 0.35, "iou": 0.45, "max_det": 100,
             "track_thresh": 0.5, "match_thresh": 0.8, "track_buffer": 30,
-            "step_mode": "scan_async: head tensors declared complete (resident), scans on the library's own stream, post kernels on the caller's",
+            "scaling_note": "N = 1 runs configs[2] (64 streams); N = 2 / 4 / 8 run configs[3] (512 streams in all, 512 / N per GPU); "
+                            "the 64-streams-per-GPU (weak) figure of the same run is in `weak_scaling`",
+            "step_mode": "heads declared complete (resident): one step kernel per step on the library's stream, each a programmatic "
+                         "dependent of the one before (its head scan overlaps the previous step's NMS / tracker / zone stage)",
             "l2_policy": "inputs larger than L2: every step reads a different frame of the cycle "
                          "(streams x 8400 x 144 head elements per step, cycle of frames resident in HBM)"}
 
@@ -341,82 +365,108 @@ def run_b200(args):
     total_streams = S * world
     my_streams = sharding.shard_streams(total_streams, world, rank)
     wl = PostBackboneWorkload(S, F, first_stream=my_streams.start, device=dev, dtype=tdt)
-    sb = pkg.StreamBatch(S, wl.zones, src_hw=(1080, 1920), classes=WANTED, max_tracks=512, device=dev)
-    lib = sb.lib
+    lib = _lib.lib()
     hbm_peak, peak_src = peaks()
+
+    def new_batch(n, zones):
+        return pkg.StreamBatch(n, zones, src_hw=(1080, 1920), classes=WANTED, max_tracks=512, device=dev)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def run_steps(first, n, heads_ready=None):
-        for f in range(first, first + n):
-            sb.step(wl.heads[f % F], now=T0 + f / FPS, frame_id=f, heads_ready=heads_ready)
-        return first + n
-
-    counters = {"detections": 0, "births0": 0, "events": 0}
     sampler = ClockSampler(local, getattr(torch.cuda.get_device_properties(dev), "uuid", None))
     with sampler:
-        # ---- warm-up + parity spot-check against the oracle (first frames, sampled streams) ----
-        parity = parity_check(pkg, wl, sb, args) if rank == 0 else None
-        f = run_steps(0, W) if rank != 0 else run_steps(parity["frames"], W)
-        sb.check_status()
+        # ---- parity: this rank's first 64 streams, every frame of the cycle, against the oracle chain; then the
+        #      equivalence of shardings: rank 0 re-runs streams that belong to the other ranks ----
+        parity = None
+        if not args.no_parity:
+            parity = parity_leg(pkg, wl, new_batch, args, rank, world, my_streams, total_streams, dev, tdt)
+
+        sb = new_batch(S, wl.zones)
+        state = {"f": 0}
+
+        def run_steps(batch, heads, n, heads_ready=None):
+            f = state["f"]
+            for i in range(f, f + n):
+                batch.step(heads[i % F], now=T0 + i / FPS, frame_id=i, heads_ready=heads_ready)
+            state["f"] = f + n
 
         # ---- timed region: K steps, device-resident inputs, CUDA events ----
         # The head tensors are resident and complete before the region starts, and the step is told so
-        # (heads_ready=True -> rtm_step_io.scan_async): the scans go to the library's own stream and run back
-        # to back, the post kernels follow on the current stream.  The closing event is recorded on the
-        # current stream after the last post kernel, which itself waits for the last scan.  The same K
-        # steps in the default single-stream mode are timed right after, for comparison.
-        def timed(heads_ready):
-            nonlocal f
+        # (heads_ready=True -> rtm_step_io.scan_async): every step is one kernel on the library's own stream, a
+        # programmatic dependent of the one before; the current stream is made to wait for each of them, so the
+        # closing event (current stream) fires after the last step.  The same K steps in the default mode (ordinary
+        # launches on the current stream, no overlap between steps) are timed right after, for comparison.
+        def timed(batch, heads, heads_ready):
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             barrier()
             ev0.record()
-            f = run_steps(f, K, heads_ready)
+            run_steps(batch, heads, K, heads_ready)
             ev1.record()
             barrier()
             ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-            sb.check_status()
+            batch.check_status()
             return float(ms.item())
 
-        f = run_steps(f, W, True)
-        ms_total = timed(True)
+        run_steps(sb, wl.heads, W, True)
+        ms_total = timed(sb, wl.heads, True)
         value = total_streams * K / (ms_total / 1e3)
-        f = run_steps(f, W)
-        ms_single = timed(None)
+        run_steps(sb, wl.heads, W)
+        ms_single = timed(sb, wl.heads, None)
 
-        # ---- roofline pass: same steps with per-kernel CUDA events (rtm_profile_*) ----
+        # ---- the other scaling curve: 64 streams per GPU whatever N is (N > 1 only; N = 1 is that already) ----
+        weak = None
+        if world > 1 and S > STREAMS_1GPU:
+            sb64 = new_batch(STREAMS_1GPU, wl.zones[:STREAMS_1GPU])
+            heads64 = [[t[:STREAMS_1GPU] for t in fr] for fr in wl.heads]
+            run_steps(sb64, heads64, W, True)
+            ms64 = timed(sb64, heads64, True)
+            weak = {"streams_per_gpu": STREAMS_1GPU, "total_streams": STREAMS_1GPU * world, "scaling": "weak",
+                    "value": STREAMS_1GPU * world * K / (ms64 / 1e3), "ms_per_step": ms64 / K}
+            sb64.close()
+        elif world > 1:
+            weak = {"streams_per_gpu": S, "total_streams": total_streams, "scaling": "weak", "value": value,
+                    "ms_per_step": ms_total / K, "note": "this run is the 64-streams-per-GPU point itself"}
+
+        # ---- per-kernel pass: same steps with CUDA events around every launch (rtm_profile_*), each kernel alone ----
         lib.rtm_profile_enable(1)
         _lib.profile_read()
         barrier()
-        f = run_steps(f, K)
+        run_steps(sb, wl.heads, K)
         torch.cuda.synchronize(dev)
         prof = _lib.profile_read()
         lib.rtm_profile_enable(0)
         kernels = {k: {"avg_us": 1e3 * v[0] / v[1], "launches": v[1]} for k, v in prof.items()}
-        dec_us = kernels["decode"]["avg_us"]
+        # The step is ONE kernel (step_kernel: head scan + NMS + tracker + zones; `decode` + `post` on the two-launch
+        # fallback).  Timed alone (profiling pass: no overlap between steps) a launch lasts scan + post tail; inside
+        # the timed region consecutive launches overlap, so the kernel's average duration THERE is the region's
+        # length / launches - that is what `achieved` is computed from.
+        top = "step" if "step" in kernels else "decode"
+        alone_us = kernels[top]["avg_us"]
         alg_bytes = S * wl.bytes_per_stream_frame
-        achieved = alg_bytes / (dec_us * 1e-6) / 1e9
-        roofline = {"bound": "hbm", "kernel": "decode_tma_kernel", "achieved": achieved, "peak": hbm_peak,
-                    "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": ncu_traffic("decode_tma_kernel"), "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_us": dec_us,
-                    "share_of_step": dec_us / sum(v["avg_us"] for v in kernels.values()),
+        in_region_us = 1e3 * ms_total / K if top == "step" else alone_us
+        achieved = alg_bytes / (in_region_us * 1e-6) / 1e9
+        kname = "step_kernel" if top == "step" else "decode_tma_kernel"
+        roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": hbm_peak,
+                    "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": ncu_traffic(kname), "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_us": in_region_us, "launch_alone_us": alone_us,
+                    "share_of_step": alone_us / sum(v["avg_us"] for v in kernels.values()),
                     "whole_step_frac": (alg_bytes * K / (ms_total / 1e3) / 1e9) / hbm_peak}
 
         extras = {}
         if not args.no_extras:
             # ---- latency mode: one step at a time, p50 / p99 of the per-step device time ----
             # (the reference's profiler convention, latency_profiler.py / default.yaml:88: synchronise around the
-            # stage, 50 warm-up frames, then percentiles; here over 1000 steps of 64 stream-frames each)
+            # stage, 50 warm-up frames, then percentiles; here over 1000 steps of S stream-frames each)
             lat, ev_seen = [], 0
             for i in range(50 + 1000):
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
-                f = run_steps(f, 1)
+                run_steps(sb, wl.heads, 1)
                 b.record()
                 b.synchronize()
                 if i >= 50:
@@ -426,23 +476,25 @@ def run_b200(args):
             extras["latency_ms_per_step"] = {"p50": lat[len(lat) // 2], "p99": lat[min(len(lat) - 1, int(len(lat) * 0.99))],
                                              "max": lat[-1], "steps": len(lat), "warmup_steps": 50, "streams_per_step": S,
                                              "zone_events_emitted": ev_seen}
-            if rank == 0:
+            if rank == 0 and world == 1:
+                extras["config1_single_stream"] = single_stream_bench(pkg, dev)
                 extras["letterbox"] = letterbox_bench(pkg, lib, dev, S, hbm_peak)
-                extras["dense_crowd"] = dense_crowd_bench(pkg, dev)
+                extras["dense_crowd"] = dense_crowd_bench(pkg, dev, hbm_peak)
                 extras["opt_in_modes"] = modes_bench(pkg, wl, dev, S, F)
 
         # ---- e2e: the same step fed from pinned HOST head tensors through the C ABI ----
         e2e = None
         if not args.no_e2e:
-            e2e = e2e_bench(pkg, wl, sb, f, K, W, total_streams, world, dev)
-            f += K + W
+            e2e = e2e_bench(pkg, wl, sb, state["f"], K, W, total_streams, world, dev)
+            state["f"] += K + W
         sb.check_status()
 
-    # ---- run summary: the only collective of the run (NCCL all_reduce + all_gather) ----
+    # ---- run summary: the only collectives of the run (NCCL all_reduce + all_gather), after the timed regions ----
     tracks, next_id = sb.read_tracks()
-    ev_per_stream = [len(e) for e in sb.read_events()]
+    ev_records = sb.event_records()
     totals, gathered = sharding.reduce_summary(
-        [S * f, int(sb.det_count.sum().item()), int((next_id - 1).sum()), sum(ev_per_stream)], ev_per_stream, device=dev)
+        [S * state["f"], int(sb.det_count.sum().item()), int((next_id - 1).sum()), len(ev_records)], ev_records, device=dev,
+        first_stream=my_streams.start)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -457,60 +509,72 @@ def run_b200(args):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": scaling_label(world), "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args, total_streams),
             "single_stream": {"value": total_streams * K / (ms_single / 1e3), "ms_per_step": ms_single / K,
-                              "note": "the same K steps with both kernels on the caller's stream (rtm_step_io.scan_async = 0)"},
+                              "note": "the same K steps as ordinary launches on the caller's stream (rtm_step_io.scan_async = 0): "
+                                      "head tensors ordered on the stream like any input, no overlap between steps"},
+            "weak_scaling": weak,
             "clocks": sampler.summary(), "e2e": e2e,
-            # kernels of the library inside the timed region: head scan + fused post kernel per step (the per-kernel
-            # pass above counted exactly these launches for the same K steps)
+            # kernels of the library inside the timed region: one step kernel per step (the per-kernel pass above
+            # counted exactly these launches for the same K steps)
             "gpu_launches": sum(v["launches"] for v in kernels.values()), "roofline": roofline,
             "cpu_baseline": cpu, "kernels": kernels, "parity": parity,
             "summary": dict(zip(sharding.COUNTERS, totals), live_tracks_rank0=int(sum(len(t) for t in tracks)),
-                            streams_reporting=len(gathered)),
+                            event_records_gathered=len(gathered)),
         }
         line.update(extras)
         emit(line)
+    sb.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
-def parity_check(pkg, wl, sb, args, frames=6, streams=(0, 1, 2, 3)):
-    """First `frames` frames on the fresh StreamBatch: sampled streams against the oracle chain."""
-    import numpy as np
-    from oracle import detect_ref, tracker_ref, zone_ref
-    streams = [s for s in streams if s < wl.S]
-    trk = {s: tracker_ref.TrackerOracle() for s in streams}
-    zon = {s: zone_ref.ZoneOracle(wl.zones[s]) for s in streams}
-    flips = box_bad = id_bad = ev_bad = dets = 0
-    for f in range(frames):
-        now = T0 + f / FPS
-        sb.step(wl.heads[f % wl.F], now=now, frame_id=f)
-        got = sb.read_detections()
-        tracks, next_id = sb.read_tracks()
-        events = sb.read_events()
-        ref = detect_ref.detect_post(wl.host_frame(f, streams), (1080, 1920), classes=WANTED)
-        for k, s in enumerate(streams):
-            r, g = ref[k], got[s]
-            dets += len(r["conf"])
-            if len(r["conf"]) != len(g["confidence"]) or not np.array_equal(r["anchor"], g["anchor"]):
-                flips += 1
-                continue
-            box_bad += int(not np.allclose(g["xyxy"], r["xyxy"], rtol=1e-4, atol=1e-2))
-            tid, _ = trk[s].step(g["xyxy"], g["confidence"], g["class_id"])
-            id_bad += int(not np.array_equal(tid, g["track_id"])) + int(trk[s].next_id != int(next_id[s]))
-            id_bad += int([t["track_id"] for t in tracks[s]] != trk[s].track_id.tolist())
-            act = trk[s].active_rows()
-            exp = zon[s].process(zip(trk[s].track_id[act], trk[s].xyxy[act], trk[s].cls[act]), f, now)
-            ev_bad += int([(e.track_id, e.zone_name, e.centroid, e.dwell_time_sec) for e in events[s]] !=
-                          [(e.track_id, e.zone_name, e.centroid, e.dwell_time_sec) for e in exp])
-    ok = not (flips or box_bad or id_bad or ev_bad)
-    if not ok:
-        print(f"bench.py: PARITY FAILURE flips={flips} boxes={box_bad} ids={id_bad} events={ev_bad}", file=sys.stderr)
-    return {"ok": ok, "frames": frames, "streams": len(streams), "detections_checked": dets, "nms_index_flips": flips,
-            "box_mismatch": box_bad, "track_id_mismatch": id_bad, "event_mismatch": ev_bad,
-            "checked_against": "oracle port (torch CPU decode, torchvision NMS, NumPy tracker, zone engine restatement)"}
+def parity_leg(pkg, wl, new_batch, args, rank, world, my_streams, total_streams, dev, tdt, per_rank=64, frames=16):
+    """Every rank: its first `per_rank` streams x `frames` frames against the oracle chain (oracle/chain.py).  With
+    N > 1 ranks: the digests of what every rank's CUDA path produced are gathered, and rank 0 re-runs two streams of
+    every other rank's shard on its own GPU - the same global streams in another batch on another device must give the
+    same bits (streams are independent, tracker.py:55-56 / zone_engine.py:72-75; SURVEY section 4 tier 5)."""
+    import torch.distributed as dist
+    from oracle import chain
+    from rtmodt_b200.workload import PostBackboneWorkload
+    n = min(per_rank, wl.S)
+    frames = min(frames, wl.F)
+    heads = [[t[:n] for t in fr] for fr in wl.heads]
+    sb = new_batch(n, wl.zones[:n])
+    res = chain.run_chain_parity(sb, lambda f: heads[f % wl.F], lambda f: [t.float().cpu() for t in heads[f % wl.F]],
+                                 wl.zones[:n], frames, classes=WANTED, t0=T0, fps=FPS)
+    sb.close()
+    digests = res.pop("digests")
+    if not res["ok"]:
+        print(f"bench.py: PARITY FAILURE on rank {rank}: {res}", file=sys.stderr)
+    out = dict(res, ranks_checked=1, streams_per_rank=n)
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, {"rank": rank, "first": my_streams.start, "res": res, "digests": digests})
+        if rank == 0:
+            for k in ("detections_checked", "events_checked", "nms_index_flips", "box_mismatch", "track_id_mismatch",
+                      "track_table_mismatch", "event_mismatch"):
+                out[k] = sum(g["res"][k] for g in gathered)
+            out["streams"] = sum(g["res"]["streams"] for g in gathered)
+            out["ok"] = all(g["res"]["ok"] for g in gathered)
+            out["ranks_checked"] = world
+            # sharding equivalence: two streams of every other rank, re-run here as batches of their own
+            picks = [(g["first"] + k, g["digests"][k]) for g in gathered[1:] for k in (0, n - 1)]
+            same = 0
+            for gid, want in picks:
+                w1 = PostBackboneWorkload(1, wl.F, first_stream=gid, device=dev, dtype=tdt)
+                sb1 = new_batch(1, w1.zones)
+                r1 = chain.run_chain_parity(sb1, lambda f: w1.heads[f % wl.F], lambda f: [t.float().cpu() for t in w1.heads[f % wl.F]],
+                                            w1.zones, frames, classes=WANTED, t0=T0, fps=FPS)
+                sb1.close()
+                same += int(r1["digests"][0] == want)
+            out["sharding_equivalence"] = {"streams_rerun_on_rank0": len(picks), "bit_identical": same, "ok": same == len(picks),
+                                           "what": "global streams owned by other ranks, re-run on rank 0 as single-stream batches: "
+                                                   "sha1 over detections, track ids, track tables and events of every frame"}
+            out["ok"] = out["ok"] and same == len(picks)
+    return out
 
 
 def e2e_bench(pkg, wl, sb, f0, K, W, total_streams, world, dev):

@@ -12,7 +12,7 @@
  * Conventions
  *   - every pointer named in a struct or argument list is a DEVICE pointer unless the name
  *     starts with host_; the caller owns every buffer; nothing is allocated, freed or
- *     synchronised on the per-frame path; all kernels are enqueued on `stream`
+ *     synchronised on the per-frame path (the first call that sees a workspace sets it up); all kernels are enqueued on `stream`
  *     (a cudaStream_t passed as void*, e.g. torch.cuda.current_stream().cuda_stream);
  *   - return value 0 = ok, negative = error (rtm_last_error() gives the message);
  *   - conditions only the device can detect (a table or list that would overflow its
@@ -105,10 +105,13 @@ typedef struct rtm_nms_params {
 /* bytes of scratch rtm_decode_nms / rtm_nms_pred / rtm_post_backbone_step need for num_streams
  * streams of num_anchors.  The workspace holds a ring of candidate lists (consecutive calls with the
  * same workspace rotate through it, which is what allows the head scan of one step to overlap the
- * post kernel of the step before) and a small header of tile counters.  Give every stream batch its
- * own workspace, 256-byte aligned, and hand it over zero-filled (the library clears the header the
- * first time it sees a workspace address; do not let other data live at that address in between). */
+ * post stage of the step before) and a small header of counters.  Give every stream batch its own
+ * workspace, 256-byte aligned.  The library clears the header the first time it sees a workspace
+ * address on a device (synchronously: not on the per-frame path) and keeps a little host-side
+ * bookkeeping for it (a CUDA stream and events of its own once rtm_step_io.scan_async is used);
+ * rtm_workspace_release drops that bookkeeping - call it before the memory is freed or reused. */
 size_t rtm_nms_workspace_bytes(int32_t num_streams, int32_t num_anchors);
+int rtm_workspace_release(void* workspace);
 
 /*
  * head[l]  (B, 64 + nc, img_h/stride_l, img_w/stride_l), strides 8/16/32, contiguous NCHW,
@@ -317,17 +320,30 @@ typedef struct rtm_step_io {
    * lap's cost_limit for RTM_ASSIGN_OPTIMAL (see rtm_track_options) */
   int32_t assignment;
   double cost_limit;
-  /* Optional pipelining of consecutive steps.  scan_async = 0 (default): both kernels go to `stream`;
-   * the head scan of a step still overlaps the post kernel of the step before (programmatic
-   * dependent launch) but starts only when that kernel has started.  scan_async = 1: the caller
-   * states that the head tensors are complete once heads_ready_event (a cudaEvent_t, or NULL =
-   * complete already) has fired - e.g. the backbone runs on its own stream and records an event per
-   * frame.  The scan is then enqueued on a stream the library owns, behind that event only, so that
-   * consecutive scans run back to back; the post kernel still goes to `stream`, which the library
-   * makes wait for the scan.  Results are ordered on `stream` exactly as in the default mode, and
-   * work enqueued on `stream` after the call is ordered after the scan has read the head tensors. */
+  /* Pipelining of consecutive steps.  scan_async = 0 (default): everything goes to `stream` as ordinary
+   * launches; the head tensors are ordered on `stream` like any other input and a step starts when the
+   * step before it has finished.  scan_async = 1: the caller states that the head tensors are complete
+   * once heads_ready_event (a cudaEvent_t, or NULL = complete already) has fired - e.g. the backbone runs
+   * on its own stream and records an event per frame.  The step's kernel is then enqueued on a stream the
+   * library owns, behind that event only, as a programmatic dependent of the previous step's kernel: its
+   * head scan runs while the previous step's NMS / tracker / zone stage is still at work.  What must not be
+   * overtaken is ordered on the device: a stream's post stage follows the same stream's previous one, and it
+   * starts only once `stream` has reached this call (the result buffers and tables it overwrites may still be
+   * read by work enqueued on `stream` before).  `stream` is made to wait for the kernel, so results are
+   * ordered on `stream` exactly as in the default mode, and work enqueued on `stream` after the call is
+   * ordered after the scan has read the head tensors.  (Do not enqueue cooperative launches that need the
+   * whole GPU on `stream` between such calls: up to 64 post CTAs may be resident, waiting for the mark.) */
   int32_t scan_async;
   void* heads_ready_event;
+  /* scan_async only.  0: the post stage of this step starts once `stream` has reached THIS call - it overwrites
+   * result buffers (det_*, events, event_count) that work enqueued on `stream` since the previous call may still
+   * read; as `stream` also waits for every step's kernel, the post stages of consecutive steps then follow each
+   * other at kernel granularity.  1: the caller alternates between two sets of result buffers from call to call
+   * (what this step overwrites was last read before the previous call), so the post stage only waits until
+   * `stream` has reached the PREVIOUS call - consecutive post stages then follow each other stream by stream.
+   * Either way the track tables / zone state / Kalman state the caller passes must not be touched by other work
+   * on `stream` between scan_async calls without a synchronisation. */
+  int32_t results_alternate;
 } rtm_step_io;
 
 int rtm_post_backbone_step(const rtm_step_io* io, const rtm_nms_params* params,
@@ -344,7 +360,7 @@ typedef struct rtm_step_host_io {
   const void* host_head_p3;
   const void* host_head_p4;
   const void* host_head_p5;
-  rtm_zone_event* host_events; /* (B, event_stride) */
+  rtm_zone_event* host_events; /* (B, host_event_stride or event_stride) */
   int32_t* host_event_count;   /* (B) */
   float* host_det_xyxy;        /* (B, det_stride, 4) or NULL */
   float* host_det_conf;        /* (B, det_stride)    or NULL */
@@ -358,6 +374,10 @@ typedef struct rtm_step_host_io {
    * done_event is recorded after the last device->host copy. */
   void* wait_event;
   void* done_event;
+  /* records per stream of host_events: only the first host_event_stride records of every stream's slab are
+   * copied back (0 = all io->event_stride of them).  host_event_count tells how many a stream emitted; a count
+   * beyond host_event_stride means the rest stayed on the device (io->events) for this step. */
+  int32_t host_event_stride;
 } rtm_step_host_io;
 
 int rtm_post_backbone_step_host(const rtm_step_io* io, const rtm_step_host_io* host_io,
@@ -377,7 +397,8 @@ enum {
   RTM_K_TRACK = 3,
   RTM_K_ZONE = 4,
   RTM_K_PRED = 5,
-  RTM_K_POST = 6, /* fused NMS + tracker + zones of rtm_post_backbone_step */
+  RTM_K_POST = 6, /* fused NMS + tracker + zones of rtm_post_backbone_step (two-launch path) */
+  RTM_K_STEP = 7, /* step_kernel: head scan + NMS + tracker + zones in one launch */
   RTM_K_COUNT = 8
 };
 int rtm_profile_enable(int32_t on);

@@ -18,6 +18,7 @@ STATUS_TRACK_OVERFLOW, STATUS_DET_OVERFLOW, STATUS_CAND_OVERFLOW = 1, 2, 4
 STATUS_EVENT_OVERFLOW, STATUS_ZONE_LIMIT, STATUS_ASSIGN_LIMIT = 8, 16, 32
 DET_NONE, DET_STAGE1, DET_STAGE2, DET_BIRTH = 0, 1, 2, 3
 MAX_ZONES_PER_STREAM = 64
+ZONE_STEP_EVENTS = 4096     # kZoneStepEvents: events one stream can emit in one step
 
 _STATUS_TEXT = {
     STATUS_TRACK_OVERFLOW: "live tracks exceed the track table capacity (raise max_tracks)",
@@ -115,7 +116,7 @@ class StepIO(C.Structure):
         ("event_count", C.c_void_p), ("status", C.c_void_p),
         ("kalman_in", C.POINTER(KalmanState)), ("kalman_out", C.POINTER(KalmanState)),
         ("assignment", C.c_int32), ("cost_limit", C.c_double),
-        ("scan_async", C.c_int32), ("heads_ready_event", C.c_void_p),
+        ("scan_async", C.c_int32), ("heads_ready_event", C.c_void_p), ("results_alternate", C.c_int32),
     ]
 
 
@@ -125,7 +126,7 @@ class StepHostIO(C.Structure):
                 ("host_det_xyxy", C.c_void_p), ("host_det_conf", C.c_void_p),
                 ("host_det_cls", C.c_void_p), ("host_det_track_id", C.c_void_p),
                 ("host_det_count", C.c_void_p), ("host_status", C.c_void_p),
-                ("wait_event", C.c_void_p), ("done_event", C.c_void_p)]
+                ("wait_event", C.c_void_p), ("done_event", C.c_void_p), ("host_event_stride", C.c_int32)]
 
 
 #: every symbol include/rtmodt_b200.h declares: name -> (restype, argtypes)
@@ -139,6 +140,7 @@ SIGNATURES = {
                                    C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_int32, C.c_void_p]),
     "rtm_nms_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "rtm_workspace_release": (C.c_int, [C.c_void_p]),
     "rtm_decode_nms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                  C.c_int32, C.POINTER(NmsParams), C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
@@ -208,8 +210,8 @@ def raise_on_status(status_host, what: str = "") -> None:
     raise RtmError(f"{what}: {'; '.join(msgs)} (streams {streams})")
 
 
-K_LETTERBOX, K_DECODE, K_NMS, K_TRACK, K_ZONE, K_PRED, K_POST, K_COUNT = 0, 1, 2, 3, 4, 5, 6, 8
-KERNEL_NAMES = {K_LETTERBOX: "letterbox", K_DECODE: "decode", K_NMS: "nms", K_TRACK: "track", K_ZONE: "zone", K_PRED: "pred_filter", K_POST: "post"}
+K_LETTERBOX, K_DECODE, K_NMS, K_TRACK, K_ZONE, K_PRED, K_POST, K_STEP, K_COUNT = 0, 1, 2, 3, 4, 5, 6, 7, 8
+KERNEL_NAMES = {K_LETTERBOX: "letterbox", K_DECODE: "decode", K_NMS: "nms", K_TRACK: "track", K_ZONE: "zone", K_PRED: "pred_filter", K_POST: "post", K_STEP: "step"}
 
 
 def profile_read():

@@ -4,6 +4,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
 #include <vector>
 
 #include "rtm_common.cuh"
@@ -20,12 +23,26 @@ void set_error(const char* fmt, ...) {
 }
 
 int sm_count() {
-  static int cached = 0;
-  if (!cached) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+  static int cached[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  int& c = cached[dev & 63];
+  if (!c) cudaDeviceGetAttribute(&c, cudaDevAttrMultiProcessorCount, dev);
+  return c;
+}
+
+int ensure_dynamic_smem(const void* func, size_t bytes) {
+  static std::mutex m;
+  static std::map<std::pair<const void*, int>, size_t> configured;  // per (kernel, device)
+  int dev = 0;
+  RTM_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(m);
+  size_t& have = configured[std::make_pair(func, dev)];
+  if (bytes > have) {
+    RTM_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+    have = bytes;
   }
-  return cached;
+  return RTM_OK;
 }
 
 bool g_profile_on = false;
@@ -47,6 +64,7 @@ struct ProfileRecord {
 };
 std::vector<ProfileRecord> g_records;
 std::vector<cudaEvent_t> g_free_events;
+std::mutex g_profile_mutex;
 
 cudaEvent_t take_event() {
   if (!g_free_events.empty()) {
@@ -61,12 +79,14 @@ cudaEvent_t take_event() {
 }  // namespace
 
 void profile_begin(int kind, cudaStream_t s) {
+  std::lock_guard<std::mutex> lock(g_profile_mutex);
   ProfileRecord r{kind, take_event(), take_event()};
   cudaEventRecord(r.start, s);
   g_records.push_back(r);
 }
 
 void profile_end(cudaStream_t s) {
+  std::lock_guard<std::mutex> lock(g_profile_mutex);
   if (!g_records.empty()) cudaEventRecord(g_records.back().stop, s);
 }
 
@@ -79,6 +99,7 @@ extern "C" int rtm_profile_enable(int32_t on) {
 
 extern "C" int rtm_profile_read(double* ms_sum, int32_t* launches) {
   RTM_REQUIRE(ms_sum && launches, "rtm_profile_read: null output");
+  std::lock_guard<std::mutex> lock(rtm::g_profile_mutex);
   for (int k = 0; k < RTM_K_COUNT; ++k) {
     ms_sum[k] = 0.0;
     launches[k] = 0;
@@ -152,8 +173,12 @@ extern "C" int rtm_post_backbone_step_host(const rtm_step_io* io, const rtm_step
   const size_t D = static_cast<size_t>(io->det_stride);
   if (io->zones && h->host_events && h->host_event_count) {
     RTM_CUDA(cudaMemcpyAsync(h->host_event_count, io->event_count, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-    RTM_CUDA(cudaMemcpyAsync(h->host_events, io->events, B * io->event_stride * sizeof(rtm_zone_event),
-                             cudaMemcpyDeviceToHost, s));
+    const size_t hs = h->host_event_stride > 0 && h->host_event_stride < io->event_stride ? h->host_event_stride : io->event_stride;
+    if (hs == static_cast<size_t>(io->event_stride))
+      RTM_CUDA(cudaMemcpyAsync(h->host_events, io->events, B * hs * sizeof(rtm_zone_event), cudaMemcpyDeviceToHost, s));
+    else  // the head of every stream's slab only
+      RTM_CUDA(cudaMemcpy2DAsync(h->host_events, hs * sizeof(rtm_zone_event), io->events, io->event_stride * sizeof(rtm_zone_event),
+                                 hs * sizeof(rtm_zone_event), B, cudaMemcpyDeviceToHost, s));
   }
   if (h->host_det_count) RTM_CUDA(cudaMemcpyAsync(h->host_det_count, io->det_count, B * 4, cudaMemcpyDeviceToHost, s));
   if (h->host_det_xyxy) RTM_CUDA(cudaMemcpyAsync(h->host_det_xyxy, io->det_xyxy, B * D * 16, cudaMemcpyDeviceToHost, s));

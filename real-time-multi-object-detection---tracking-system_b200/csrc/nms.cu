@@ -38,18 +38,13 @@
 //                asc) keys, class-parallel greedy scan (warp heads, parallel filter, warp tails;
 //                block-wide scan for long segments, agnostic NMS and boxes outside the class
 //                guard), first max_det survivors by score, rescale, write in score order.
-#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through the runtime)
-#include <cuda_bf16.h>
-#include <cuda_fp16.h>
-#include <float.h>
-#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include <unordered_map>
 #include <vector>
 
-#include "nms_body.cuh"
+#include "decode_body.cuh"
 
 namespace {
 
@@ -57,20 +52,22 @@ using rtm::kFull;
 using rtm::NmsOut;
 using rtm::Workspace;
 
-constexpr int kRegMax = 16;
-constexpr int kBoxCh = 4 * kRegMax;  // 64
+using rtm::kRegMax;
+using rtm::kBoxCh;
+using rtm::Level;
+using rtm::HeadGeom;
+using rtm::TmaGeom;
+using rtm::TmaMaps;
+using rtm::to_float;
+using rtm::sigmoidf_rn;
+using rtm::class_wanted;
+using rtm::dist_to_xyxy;
+using rtm::dfl_expectation;
+using rtm::store_candidate;
+using rtm::kAnchorsPerWarp;
+using rtm::kMaxStages;
+using rtm::tma_threads;
 constexpr int kNmsThreads = 512;
-
-struct Level {
-  int h, w, hw, stride;
-  int anchor0;  // first anchor index of the level
-};
-
-struct HeadGeom {
-  Level lv[3];
-  int num_anchors;
-  int num_classes;
-};
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -80,12 +77,19 @@ int next_pow2(int v) {
   return p;
 }
 
-// Workspace = header (one tile ticket counter per slot) + a ring of kCandSlots copies of the
-// candidate interchange arrays + one set of spill arrays.  Consecutive head scans take
-// consecutive slots, so the scan of step k+2 may already run while the post kernel of step k
-// still reads its own slot (programmatic dependent launch: see decode_tma_kernel and post.cu).
+// Workspace = header + a ring of kCandSlots copies of the candidate interchange arrays + one set of
+// spill arrays.  Consecutive head scans take consecutive slots, so the scan of a later step may already
+// run while the post stage of an earlier step still reads its own slot.
+// Header: per slot 128 bytes of counters - [0] tile tickets of the scan filling the slot (two-launch pipeline),
+// and for the one-launch step (all running totals, never reset) [1] tiles of the slot's scans finished, [2] streams
+// whose post stage has finished reading it, [3] post-stage tickets drawn - then the step kernel's per-workspace
+// words: [0] the caller-stream mark, [64 .. 128) a ring of tile-ticket counters (one per launch, re-armed 32
+// launches ahead), [128 + b] steps completed by stream b.
 using rtm::kCandSlots;
-constexpr size_t kWorkspaceHeader = 128 * kCandSlots;
+constexpr size_t kSlotHeader = 128 * kCandSlots;
+constexpr int kSyncWords = rtm::kSyncStreamSeq;  // words in front of the per-stream sequence numbers
+
+size_t header_bytes(int B) { return align_up(kSlotHeader + sizeof(int) * (kSyncWords + static_cast<size_t>(B)), 256); }
 
 size_t workspace_layout(int B, int A, char* base, Workspace* ws, int half = 0) {
   const int words = (A + 31) / 32, cap_p2 = next_pow2(A);
@@ -95,7 +99,7 @@ size_t workspace_layout(int B, int A, char* base, Workspace* ws, int half = 0) {
     off = align_up(off + bytes, 256);
     return o;
   };
-  const size_t o_head = take(kWorkspaceHeader);
+  const size_t o_head = take(header_bytes(B));
   size_t o_mask[kCandSlots], o_box[kCandSlots], o_score[kCandSlots], o_cls[kCandSlots];
   for (int h = 0; h < kCandSlots; ++h) {
     o_mask[h] = take(sizeof(uint32_t) * B * words);
@@ -111,6 +115,7 @@ size_t workspace_layout(int B, int A, char* base, Workspace* ws, int half = 0) {
   const size_t o_alive = take(sizeof(uint32_t) * B * 2 * words);
   if (ws) {
     ws->tile_counter = reinterpret_cast<int*>(base + o_head) + 32 * half;  // 128 bytes apart
+    ws->sync = reinterpret_cast<int*>(base + o_head + kSlotHeader);
     ws->mask = reinterpret_cast<uint32_t*>(base + o_mask[half]);
     ws->box = reinterpret_cast<float4*>(base + o_box[half]);
     ws->score = reinterpret_cast<float*>(base + o_score[half]);
@@ -129,558 +134,26 @@ size_t workspace_layout(int B, int A, char* base, Workspace* ws, int half = 0) {
   return off;
 }
 
-__device__ __forceinline__ float to_float(float v) { return v; }
-__device__ __forceinline__ float to_float(__half v) { return __half2float(v); }
-__device__ __forceinline__ float to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
-
-__device__ __forceinline__ float sigmoidf_rn(float x) {
-  return __fdiv_rn(1.f, __fadd_rn(1.f, expf(-x)));
-}
-
-__device__ __forceinline__ bool class_wanted(const rtm_nms_params& p, int c) {
-  return (p.class_mask[c >> 5] >> (c & 31)) & 1u;
-}
-
-// dist2bbox(xywh) * stride followed by xywh2xyxy, in the operation order of ultralytics
-__device__ __forceinline__ float4 dist_to_xyxy(float l, float t, float r, float b, float ax, float ay,
-                                               float stride, float4* xywh) {
-  const float x1 = __fsub_rn(ax, l), y1 = __fsub_rn(ay, t);
-  const float x2 = __fadd_rn(ax, r), y2 = __fadd_rn(ay, b);
-  // x / 2 == x * 0.5f bit for bit (exact scaling by a power of two); the division sequence is ~10x the instructions
-  const float cx = __fmul_rn(__fmul_rn(__fadd_rn(x1, x2), 0.5f), stride);
-  const float cy = __fmul_rn(__fmul_rn(__fadd_rn(y1, y2), 0.5f), stride);
-  const float w = __fmul_rn(__fsub_rn(x2, x1), stride);
-  const float h = __fmul_rn(__fsub_rn(y2, y1), stride);
-  if (xywh) *xywh = make_float4(cx, cy, w, h);
-  const float dw = __fmul_rn(w, 0.5f), dh = __fmul_rn(h, 0.5f);
-  return make_float4(__fsub_rn(cx, dw), __fsub_rn(cy, dh), __fadd_rn(cx, dw), __fadd_rn(cy, dh));
-}
-
-// DFL expectation of one side from 16 logits: sum_k k * softmax(x)_k.  Shared by all decode
-// kernels so that they agree bit for bit; checked against the oracle within 1e-4 relative
-// (D1 is the tolerance-checked stage: torch's CPU softmax rounds differently anyway), hence
-// the fast exponential and a single division.
-__device__ __forceinline__ float dfl_expectation(float (&x)[kRegMax]) {
-  float mx = x[0];
-#pragma unroll
-  for (int k = 1; k < kRegMax; ++k) mx = fmaxf(mx, x[k]);
-  float sum = 0.f, acc = 0.f;
-#pragma unroll
-  for (int k = 0; k < kRegMax; ++k) {
-    const float e = __expf(x[k] - mx);
-    sum += e;
-    acc = __fmaf_rn(static_cast<float>(k), e, acc);
-  }
-  return __fdiv_rn(acc, sum);
-}
-
-__device__ __forceinline__ void store_candidate(const Workspace& ws, int b, int anchor, float4 box, float score, int cls) {
-  const size_t o = static_cast<size_t>(b) * ws.num_anchors + anchor;
-  ws.box[o] = box;
-  ws.score[o] = score;
-  ws.cls[o] = cls;
-}
-
 template <typename T>
 struct HeadPtrs {
   const T* p[3];
 };
 
 // ---------------------------------------------------------------------------------------
-// decode_tma
+// decode_tma: the tiled head scan as a kernel of its own (decode_body.cuh holds the CTA's work)
 // ---------------------------------------------------------------------------------------
-// Tile width (anchors per tile) is a template parameter: 64 / 128 make every channel row of a
-// 16-bit tile a whole number of 128-byte lines (one or two full-line L2 requests per row), 80
-// divides 6400 / 1600 / 400 exactly but gives 160-byte rows that straddle lines.  Tiles that run
-// past the end of a level are zero-filled by the TMA unit and their anchors masked out.
-constexpr int kAnchorsPerWarp = 16;  // a lane owns 2 adjacent anchors x one class quarter
-constexpr int kMaxStages = 8;
-constexpr int tma_consumer_warps(int tile_w) { return tile_w / kAnchorsPerWarp; }
-constexpr int tma_threads(int tile_w) { return (tma_consumer_warps(tile_w) + 1) * 32; }  // + one producer warp
-
-struct TmaGeom {
-  HeadGeom g;
-  int tiles_before[4];  // tiles of one stream before level l (prefix), [3] = tiles per stream
-  int total_tiles;
-  int stages;
-  int tile_bytes;
-  int evict_first;    // L2 evict-first hint on the tile loads
-  int static_rounds;  // ring rounds with the static schedule (tile = blockIdx + k * grid) before tickets take over
-  int trigger;        // release programmatic dependents (the next scan on the same stream) at once
-};
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  // bounded: a lost completion traps (launch error) instead of hanging the GPU
-  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
-    if (spin > (1u << 26)) __trap();
-}
-__device__ __forceinline__ void tma_load_tile(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int b,
-                                              const uint64_t policy) {
-  if (policy) {  // read-once data: L2 evict-first
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
-        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(b), "l"(policy)
-        : "memory");
-  } else {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(b)
-        : "memory");
-  }
-}
-
-// two horizontally adjacent anchors of one channel row: one 4-byte (16-bit heads) or 8-byte load,
-// running maximum kept packed (HMNMX2 on bf16x2 / f16x2)
-template <typename T>
-struct Pair;
-template <>
-struct Pair<__nv_bfloat16> {
-  using V = __nv_bfloat162;
-  static __device__ __forceinline__ V lowest() { return __float2bfloat162_rn(-INFINITY); }
-  static __device__ __forceinline__ V load(const __nv_bfloat16* p) { return *reinterpret_cast<const V*>(p); }
-  static __device__ __forceinline__ V vmax(V a, V b) { return __hmax2(a, b); }
-  static __device__ __forceinline__ float lo(V v) { return __low2float(v); }
-  static __device__ __forceinline__ float hi(V v) { return __high2float(v); }
-};
-template <>
-struct Pair<__half> {
-  using V = __half2;
-  static __device__ __forceinline__ V lowest() { return __float2half2_rn(-INFINITY); }
-  static __device__ __forceinline__ V load(const __half* p) { return *reinterpret_cast<const V*>(p); }
-  static __device__ __forceinline__ V vmax(V a, V b) { return __hmax2(a, b); }
-  static __device__ __forceinline__ float lo(V v) { return __low2float(v); }
-  static __device__ __forceinline__ float hi(V v) { return __high2float(v); }
-};
-template <>
-struct Pair<float> {
-  using V = float2;
-  static __device__ __forceinline__ V lowest() { return make_float2(-INFINITY, -INFINITY); }
-  static __device__ __forceinline__ V load(const float* p) { return *reinterpret_cast<const V*>(p); }
-  static __device__ __forceinline__ V vmax(V a, V b) { return make_float2(fmaxf(a.x, b.x), fmaxf(a.y, b.y)); }
-  static __device__ __forceinline__ float lo(V v) { return v.x; }
-  static __device__ __forceinline__ float hi(V v) { return v.y; }
-};
-
-// exact N1 of one anchor column for the lanes of its four class quarters: probability and index
-// of the FIRST class attaining the maximum float32 sigmoid; lanes whose quarter cannot pass
-// contribute (-1, INT_MAX).  `m` is the lane's maximum logit over its classes q, q+4, ...
-// The quarter's class values are read in one unrolled sweep (independent shared-memory loads) that
-// only notes which of them clear the gate - a handful at most; the sigmoid is evaluated for those,
-// in ascending class order with a strict comparison, which is torch's max(1) on the sigmoid tensor.
 template <typename T, bool NC80, int kTileW>
-__device__ __forceinline__ void anchor_best(const T* cls_col, const int q, const int iters, const int nc, const float m,
-                                            const float logit_gate, float* best, int* bc) {
-  float sc = -1.f;
-  int j = 0x7fffffff;
-  if (m > logit_gate) {
-    unsigned bits = 0u;
-    if (NC80) {
-#pragma unroll
-      for (int i = 0; i < 20; ++i) bits |= (to_float(cls_col[(4 * i + q) * kTileW]) > logit_gate ? 1u : 0u) << i;
-    } else {
-      for (int i = 0; i < iters && i < 32; ++i)
-        if (4 * i + q < nc) bits |= (to_float(cls_col[(4 * i + q) * kTileW]) > logit_gate ? 1u : 0u) << i;
-    }
-    while (bits) {
-      const int i = __ffs(bits) - 1;
-      bits &= bits - 1;
-      const float p = sigmoidf_rn(to_float(cls_col[(4 * i + q) * kTileW]));
-      if (p > sc) {
-        sc = p;
-        j = 4 * i + q;
-      }
-    }
-    for (int i = 32; i < iters; ++i) {  // nc > 128: the classes the bitmask does not cover
-      const int c = 4 * i + q;
-      if (c < nc) {
-        const float v = to_float(cls_col[c * kTileW]);
-        if (v > logit_gate) {
-          const float p = sigmoidf_rn(v);
-          if (p > sc) {
-            sc = p;
-            j = c;
-          }
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int d = 8; d <= 16; d <<= 1) {
-    const float ob = __shfl_xor_sync(kFull, sc, d);
-    const int oc = __shfl_xor_sync(kFull, j, d);
-    if (ob > sc || (ob == sc && oc < j)) {
-      sc = ob;
-      j = oc;
-    }
-  }
-  *best = sc;
-  *bc = j;
-}
-
-// SPLIT: a tile holds the class planes only (the part every anchor needs); the 64 box channels are
-// fetched per consumer warp - a 64 x 16-anchor sub-tile (one 32-byte sector per row for 16-bit heads),
-// by a second TMA copy the warp issues itself - and only when its 16 anchors hold a candidate.  That
-// copy is waited for one tile later (the warp scans the next tile meanwhile), so its latency stays
-// off the ring.  Box bytes that no candidate needs never cross HBM.
-struct TmaMaps {
-  CUtensorMap tile[3];  // per level: the ring's tiles
-  CUtensorMap box[3];   // per level: 64 box channels x 16 anchors (SPLIT only)
-};
-
-template <typename T, bool NC80, int kTileW, bool SPLIT>
 __global__ void __launch_bounds__(tma_threads(kTileW)) decode_tma_kernel(const __grid_constant__ TmaMaps maps,
                                                                  const TmaGeom tg, const rtm_nms_params prm,
                                                                  const float logit_gate, const Workspace ws) {
-  const CUtensorMap &map0 = maps.tile[0], &map1 = maps.tile[1], &map2 = maps.tile[2];
   extern __shared__ __align__(128) unsigned char tile_smem[];
-  __shared__ __align__(8) uint64_t box_bar[8][2];  // SPLIT: per consumer warp, two box sub-tiles in flight
-  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
-  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
-  __shared__ int4 s_tile[kMaxStages];  // per stage: (stream, level, first anchor of the tile within the level, -) ; x < 0 = no more tiles
-  __shared__ int s_next[kMaxStages];  // ticket drawn for the stage's next fill (producer lane only)
-  using P = Pair<T>;
-  constexpr int kConsumerWarps = kTileW / kAnchorsPerWarp;
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int stages = tg.stages;
-  const int tps = tg.tiles_before[3], tb1 = tg.tiles_before[1], tb2 = tg.tiles_before[2];
-  // Programmatic dependent launch: this grid may have been started while the PREVIOUS step's post
-  // kernel (which releases its dependents as its first instruction) was still running.  Nothing here
-  // reads or writes what that kernel touches: the head tensors are inputs, the candidate list goes
-  // to another slot of the ring, the ticket counter of that slot was re-armed two steps ago.  The
-  // step's own post kernel is an ordinary launch and starts after everything before it has finished.
-  // The scan releases its own dependents at once as well: when the next launch on its stream is the
-  // next step's scan (rtm_step_io.scan_async), that grid's CTAs move in as this one's retire.
+  __shared__ __align__(16) rtm::ScanCtl ctl;
+  // Programmatic dependent launch (only attached when the launch before this one on the stream is the
+  // library's own, see launch_decode_tma_w): nothing here reads or writes what the previous step's kernels
+  // touch - the head tensors are inputs, the candidate list goes to another slot of the ring.
   if (tg.trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  if (tid == 0) {
-    for (int s = 0; s < stages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], kConsumerWarps);
-    }
-    for (int w = 0; w < 8; ++w) {
-      mbar_init(&box_bar[w][0], 1);
-      mbar_init(&box_bar[w][1], 1);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
-  // Tiles are handed out by a ticket counter (tile t = stream t / tps, tile t % tps of that stream),
-  // so whichever CTAs are resident share the work evenly - also while the previous step's
-  // post kernel still occupies part of the GPU.
-  if (warp == kConsumerWarps) {
-    // ===== producer warp: one elected lane keeps the ring full =====
-    if (lane == 0) {
-      uint64_t policy = 0;
-      if (tg.evict_first) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-      auto issue = [&](int s, int t) {
-        const int b = t / tps, r = t - b * tps;
-        const int li = r >= tb2 ? 2 : (r >= tb1 ? 1 : 0);
-        const int x = (r - (li == 2 ? tb2 : (li == 1 ? tb1 : 0))) * kTileW;
-        s_tile[s] = make_int4(b, li, x, 0);
-        mbar_expect_tx(&full_bar[s], tg.tile_bytes);
-        tma_load_tile(tile_smem + static_cast<size_t>(s) * tg.tile_bytes, li == 0 ? &map0 : (li == 1 ? &map1 : &map2),
-                      &full_bar[s], x, SPLIT ? kBoxCh : 0, b, policy);
-      };
-      // first round of the ring: tiles blockIdx + k * grid, no ticket needed; the tickets of the
-      // second round are drawn meanwhile (all in flight together), later ones one ring cycle ahead
-      const int nstatic = stages * tg.static_rounds;
-      const int dyn0 = nstatic * static_cast<int>(gridDim.x);
-      // (static_rounds = 0: the first round comes off the counter as well, `stages` tickets in one draw - a CTA
-      // that only becomes resident late, e.g. behind another kernel's CTAs, then holds no tile of its own back)
-      const int first = nstatic == 0 ? atomicAdd(ws.tile_counter, stages) : 0;
-      bool done = false;
-      for (int k = 0; k < stages && !done; ++k) {
-        const int t = nstatic == 0 ? first + k : static_cast<int>(blockIdx.x) + k * static_cast<int>(gridDim.x);
-        if (t < tg.total_tiles) {
-          issue(k, t);
-        } else {
-          s_tile[k] = make_int4(-1, 0, 0, 0);
-          mbar_arrive(&full_bar[k]);
-          done = true;
-        }
-      }
-      if (!done) {
-        // tiles stages .. nstatic-1 of this CTA are static too; tickets are drawn for the ones after
-        int tk[kMaxStages];
-#pragma unroll
-        for (int k = 0; k < kMaxStages; ++k)
-          tk[k] = (k < stages && stages + k >= nstatic) ? atomicAdd(ws.tile_counter, 1) : 0;
-#pragma unroll
-        for (int k = 0; k < kMaxStages; ++k)
-          if (k < stages)
-            s_next[k] = stages + k < nstatic ? static_cast<int>(blockIdx.x) + (stages + k) * static_cast<int>(gridDim.x) : dyn0 + tk[k];
-        int issued = 2 * stages;  // tiles of this CTA that have a source by now
-        int s = 0, fill = 1, drawn = 0, drawn_for = -1;  // ticket in flight and the stage it is for
-        while (true) {
-          mbar_wait(&empty_bar[s], (fill - 1) & 1);
-          if (drawn_for >= 0) s_next[drawn_for] = dyn0 + drawn;  // arrived while the ring drained
-          const int t = s_next[s];
-          if (t >= tg.total_tiles) {
-            s_tile[s] = make_int4(-1, 0, 0, 0);
-            mbar_arrive(&full_bar[s]);
-            break;
-          }
-          issue(s, t);
-          if (issued < nstatic) {
-            s_next[s] = static_cast<int>(blockIdx.x) + issued * static_cast<int>(gridDim.x);
-            drawn_for = -1;
-          } else {
-            drawn = atomicAdd(ws.tile_counter, 1);
-            drawn_for = s;
-          }
-          ++issued;
-          if (++s == stages) {
-            s = 0;
-            ++fill;
-          }
-        }
-      }
-    }
-    return;
-  }
-
-  // ===== consumer warps =====
-  const int pr = lane & 7, q = lane >> 3;          // anchor pair within the warp's 16, class quarter / DFL side
-  const int col = warp * kAnchorsPerWarp + 2 * pr;  // first of the lane's two anchor columns in the tile
-  const int nc = NC80 ? 80 : tg.g.num_classes;
-  const int iters = (nc + 3) >> 2;  // quarter q scans classes q, q + 4, q + 8, ... (bank-conflict free)
-  const int w0 = tg.g.lv[0].w, w1 = tg.g.lv[1].w, w2 = tg.g.lv[2].w;
-  const int a1 = tg.g.lv[1].anchor0, a2 = tg.g.lv[2].anchor0;
-  const int st0 = tg.g.lv[0].stride, st1 = tg.g.lv[1].stride, st2 = tg.g.lv[2].stride;
-  const int hw0 = tg.g.lv[0].hw, hw1 = tg.g.lv[1].hw, hw2 = tg.g.lv[2].hw;
-  uint8_t* mask_bytes = reinterpret_cast<uint8_t*>(ws.mask);
-
-  // SPLIT: candidates of the previous tile whose box sub-tile is still in flight
-  struct Pending {
-    bool valid, cand0, cand1;
-    float best0, best1;
-    int bc0, bc1, b, li, pix;
-  } pend;
-  pend.valid = false;
-  int box_cur = 0;
-  unsigned box_phase = 0;  // bit i = parity to wait for on box_bar[warp][i]
-  constexpr int kBoxElems = kBoxCh * kAnchorsPerWarp;  // elements of one box sub-tile
-  T* box_buf = reinterpret_cast<T*>(tile_smem + static_cast<size_t>(stages) * tg.tile_bytes) + warp * 2 * kBoxElems;
-  uint64_t box_policy = 0;
-  if (SPLIT && tg.evict_first) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(box_policy));
-  auto level_of = [&](int li, int* lv_w, int* lv_stride, int* lv_anchor0) {
-    *lv_w = li == 2 ? w2 : (li == 1 ? w1 : w0);
-    *lv_stride = li == 2 ? st2 : (li == 1 ? st1 : st0);
-    *lv_anchor0 = li == 2 ? a2 : (li == 1 ? a1 : 0);
-  };
-  // D1 for the lane's candidates from 16 bins x 4 sides (side q in this lane), then the store
-  auto decode_and_store = [&](const float (&x0)[kRegMax], const float (&x1)[kRegMax], bool c0, bool c1, float bst0, float bst1,
-                              int cl0, int cl1, int bb, int lli, int ppix) {
-    const float d0 = c0 ? dfl_expectation(const_cast<float(&)[kRegMax]>(x0)) : 0.f;
-    const float d1 = c1 ? dfl_expectation(const_cast<float(&)[kRegMax]>(x1)) : 0.f;
-    const float t0 = __shfl_down_sync(kFull, d0, 8), r0 = __shfl_down_sync(kFull, d0, 16), b0 = __shfl_down_sync(kFull, d0, 24);
-    const float t1 = __shfl_down_sync(kFull, d1, 8), r1 = __shfl_down_sync(kFull, d1, 16), b1 = __shfl_down_sync(kFull, d1, 24);
-    if (q == 0) {
-      int lv_w, lv_stride, lv_anchor0;
-      level_of(lli, &lv_w, &lv_stride, &lv_anchor0);
-      const int y = ppix / lv_w, x = ppix - y * lv_w;  // both anchors are in the same grid row (w is even)
-      const float ay = static_cast<float>(y) + 0.5f, fs = static_cast<float>(lv_stride);
-      if (c0)
-        store_candidate(ws, bb, lv_anchor0 + ppix, dist_to_xyxy(d0, t0, r0, b0, static_cast<float>(x) + 0.5f, ay, fs, nullptr), bst0, cl0);
-      if (c1)
-        store_candidate(ws, bb, lv_anchor0 + ppix + 1,
-                        dist_to_xyxy(d1, t1, r1, b1, static_cast<float>(x + 1) + 0.5f, ay, fs, nullptr), bst1, cl1);
-    }
-  };
-  // SPLIT: the pending tile's box sub-tile has (or will soon have) arrived: finish its candidates
-  auto finish_pending = [&](const int buf) {
-    mbar_wait(&box_bar[warp][buf], (box_phase >> buf) & 1u);
-    box_phase ^= 1u << buf;
-    const T* bb = box_buf + buf * kBoxElems;
-    float x0[kRegMax], x1[kRegMax];
-    if (pend.cand0 || pend.cand1) {
-#pragma unroll
-      for (int k = 0; k < kRegMax; ++k) {
-        const typename P::V v = P::load(bb + (q * kRegMax + k) * kAnchorsPerWarp + 2 * pr);
-        x0[k] = P::lo(v);
-        x1[k] = P::hi(v);
-      }
-    }
-    __syncwarp();  // every lane has read the buffer before it can be refilled
-    decode_and_store(x0, x1, pend.cand0, pend.cand1, pend.best0, pend.best1, pend.bc0, pend.bc1, pend.b, pend.li, pend.pix);
-    pend.valid = false;
-  };
-
-  int s = 0, phase = 0;
-  while (true) {
-    mbar_wait(&full_bar[s], phase);
-    int b, li, x0;
-    asm volatile("ld.volatile.shared.v4.s32 {%0, %1, %2, _}, [%3];" : "=r"(b), "=r"(li), "=r"(x0) : "r"(smem_u32(&s_tile[s])));
-    if (b < 0) break;
-    int lv_w, lv_stride, lv_anchor0;
-    level_of(li, &lv_w, &lv_stride, &lv_anchor0);
-    const int lv_hw = li == 2 ? hw2 : (li == 1 ? hw1 : hw0);
-    const int pix = x0 + col;
-    const T* tile = reinterpret_cast<const T*>(tile_smem + static_cast<size_t>(s) * tg.tile_bytes);
-    const T* cls_rows = tile + (SPLIT ? 0 : kBoxCh) * kTileW;  // first class row of the tile
-    const T* cls_col = cls_rows + q * kTileW + col;            // row of class q
-
-    // ---- N1 gate: packed running maximum over this quarter's classes for both anchors ----
-    typename P::V mv = P::lowest();
-    if (NC80) {
-#pragma unroll
-      for (int i = 0; i < 20; ++i) mv = P::vmax(mv, P::load(cls_col + 4 * i * kTileW));
-    } else {
-      for (int i = 0; i < iters; ++i)
-        if (4 * i + q < nc) mv = P::vmax(mv, P::load(cls_col + 4 * i * kTileW));
-    }
-    // anchors past the end of the level (zero-filled tail of the last tile) never pass; the test is
-    // warp-uniform because every level holds a multiple of 16 anchors
-    const bool in_level = pix < lv_hw;
-    const float m0 = in_level ? P::lo(mv) : -INFINITY, m1 = in_level ? P::hi(mv) : -INFINITY;
-    float am = fmaxf(m0, m1);
-    am = fmaxf(am, __shfl_xor_sync(kFull, am, 8));
-    am = fmaxf(am, __shfl_xor_sync(kFull, am, 16));
-
-    bool cand0 = false, cand1 = false, released = false;
-    if (__any_sync(kFull, am > logit_gate)) {
-      // ---- exact N1 for the anchors that can pass, then D1 for the survivors ----
-      float best0 = -1.f, best1 = -1.f;
-      int bc0 = 0x7fffffff, bc1 = 0x7fffffff;
-      if (NC80) {
-        // both anchors of the lane in one sweep: a packed load yields the two class values of a row
-        if (m0 > logit_gate || m1 > logit_gate) {
-          unsigned bits0 = 0u, bits1 = 0u;
-#pragma unroll
-          for (int i = 0; i < 20; ++i) {
-            const typename P::V v = P::load(cls_col + 4 * i * kTileW);
-            bits0 |= (P::lo(v) > logit_gate ? 1u : 0u) << i;
-            bits1 |= (P::hi(v) > logit_gate ? 1u : 0u) << i;
-          }
-          while (bits0) {  // ascending classes, strict >: the first maximum (torch's max(1) on the sigmoid tensor)
-            const int i = __ffs(bits0) - 1;
-            bits0 &= bits0 - 1;
-            const float p = sigmoidf_rn(to_float(cls_col[4 * i * kTileW]));
-            if (p > best0) {
-              best0 = p;
-              bc0 = 4 * i + q;
-            }
-          }
-          while (bits1) {
-            const int i = __ffs(bits1) - 1;
-            bits1 &= bits1 - 1;
-            const float p = sigmoidf_rn(to_float(cls_col[4 * i * kTileW + 1]));
-            if (p > best1) {
-              best1 = p;
-              bc1 = 4 * i + q;
-            }
-          }
-        }
-#pragma unroll
-        for (int d = 8; d <= 16; d <<= 1) {
-          const float ob0 = __shfl_xor_sync(kFull, best0, d), ob1 = __shfl_xor_sync(kFull, best1, d);
-          const int oc0 = __shfl_xor_sync(kFull, bc0, d), oc1 = __shfl_xor_sync(kFull, bc1, d);
-          if (ob0 > best0 || (ob0 == best0 && oc0 < bc0)) {
-            best0 = ob0;
-            bc0 = oc0;
-          }
-          if (ob1 > best1 || (ob1 == best1 && oc1 < bc1)) {
-            best1 = ob1;
-            bc1 = oc1;
-          }
-        }
-      } else {
-        anchor_best<T, NC80, kTileW>(cls_rows + col, q, iters, nc, m0, logit_gate, &best0, &bc0);
-        anchor_best<T, NC80, kTileW>(cls_rows + col + 1, q, iters, nc, m1, logit_gate, &best1, &bc1);
-      }
-      cand0 = best0 > prm.conf_thres && class_wanted(prm, bc0 & 255);
-      cand1 = best1 > prm.conf_thres && class_wanted(prm, bc1 & 255);
-      if (__any_sync(kFull, cand0 || cand1)) {
-        if (SPLIT) {
-          // the class planes are done with: hand the stage back, ask for this warp's box sub-tile, and
-          // meanwhile finish the tile before this one
-          __syncwarp();
-          if (lane == 0) {
-            mbar_arrive(&empty_bar[s]);
-            mbar_expect_tx(&box_bar[warp][box_cur], kBoxElems * static_cast<int>(sizeof(T)));
-            tma_load_tile(box_buf + box_cur * kBoxElems, li == 0 ? &maps.box[0] : (li == 1 ? &maps.box[1] : &maps.box[2]),
-                          &box_bar[warp][box_cur], x0 + warp * kAnchorsPerWarp, 0, b, box_policy);
-          }
-          released = true;
-          box_cur ^= 1;
-                if (pend.valid) finish_pending(box_cur);  // requests alternate buffers: after the flip box_cur is the older one
-          pend.valid = true;
-          pend.cand0 = cand0;
-          pend.cand1 = cand1;
-          pend.best0 = best0;
-          pend.best1 = best1;
-          pend.bc0 = bc0;
-          pend.bc1 = bc1;
-          pend.b = b;
-          pend.li = li;
-          pend.pix = pix;
-        } else {
-          // side q of the lane's two anchors: both sets of 16 bins come out of shared memory first (a packed
-          // load yields both anchors), then the stage is handed back to the producer and the arithmetic follows
-          float x0v[kRegMax], x1v[kRegMax];
-          if (cand0 || cand1) {
-#pragma unroll
-            for (int k = 0; k < kRegMax; ++k) {
-              const typename P::V v = P::load(tile + (q * kRegMax + k) * kTileW + col);
-              x0v[k] = P::lo(v);
-              x1v[k] = P::hi(v);
-            }
-          }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&empty_bar[s]);
-          released = true;
-          decode_and_store(x0v, x1v, cand0, cand1, best0, best1, bc0, bc1, b, li, pix);
-        }
-      }
-    }
-    // candidate bits of this warp's 16 anchors: two bytes of the stream's mask
-    uint32_t even = __ballot_sync(kFull, cand0 && q == 0) & 0xffu, odd = __ballot_sync(kFull, cand1 && q == 0) & 0xffu;
-    if (lane == 0 && in_level) {
-      even = (even | (even << 4)) & 0x0f0fu;
-      even = (even | (even << 2)) & 0x3333u;
-      even = (even | (even << 1)) & 0x5555u;
-      odd = (odd | (odd << 4)) & 0x0f0fu;
-      odd = (odd | (odd << 2)) & 0x3333u;
-      odd = (odd | (odd << 1)) & 0x5555u;
-      *reinterpret_cast<uint16_t*>(mask_bytes + static_cast<size_t>(b) * ws.words * 4 + ((lv_anchor0 + pix) >> 3)) =
-          static_cast<uint16_t>(even | (odd << 1));
-    }
-    if (!released) {
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty_bar[s]);  // this warp is done with the stage
-    }
-    if (++s == stages) {
-      s = 0;
-      phase ^= 1;
-    }
-  }
-  if (SPLIT && pend.valid) finish_pending(box_cur ^ 1);  // the most recent request
+  rtm::tma_scan_cta<T, NC80, kTileW, 1>(maps, tg, prm, logit_gate, ws, rtm::ScanSync{nullptr, 0, nullptr},
+                                         static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x), tile_smem, &ctl);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -885,7 +358,6 @@ __global__ void __launch_bounds__(kScanThreads) decode_scan_kernel(const HeadPtr
   constexpr int L = V::kLoads;
   extern __shared__ __align__(16) unsigned char scan_smem[];
   ScanWarpSmem<T, BATCH>& sm = reinterpret_cast<ScanWarpSmem<T, BATCH>*>(scan_smem)[threadIdx.x >> 5];
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // see decode_tma_kernel
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31, gl = lane & 7, q = lane >> 3;
   const int grp = (blockIdx.x * (kScanThreads / 32) + (threadIdx.x >> 5)) * 8 + gl;  // group of 8 consecutive anchors
@@ -1142,12 +614,7 @@ int make_geom(int img_h, int img_w, int nc, HeadGeom* g) {
 }
 
 int run_nms(const Workspace& ws, int B, const rtm_nms_params& prm, const NmsOut& out, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
-    RTM_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(rtm::kNmsSmemBytes)));
-    configured = true;
-  }
+  if (int rc = rtm::ensure_dynamic_smem(reinterpret_cast<const void*>(nms_kernel), rtm::kNmsSmemBytes)) return rc;
   {
     rtm::ProfileScope prof(RTM_K_NMS, stream);
     nms_kernel<<<B, kNmsThreads, rtm::kNmsSmemBytes, stream>>>(ws, prm, rtm::iou_gate_for(prm.iou_thres), out);
@@ -1200,10 +667,11 @@ CUtensorMapDataType tensor_map_dtype<__half>() { return CU_TENSOR_MAP_DATA_TYPE_
 template <>
 CUtensorMapDataType tensor_map_dtype<__nv_bfloat16>() { return CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; }
 
-// returns 1 when the TMA path was launched, 0 when the caller should fall back, < 0 on error
-template <typename T, int kTileW, bool SPLIT>
-int launch_decode_tma_w(const void* p3, const void* p4, const void* p5, const HeadGeom& g, int B,
-                        const rtm_nms_params& prm, const Workspace& ws, cudaStream_t stream) {
+// Everything a launch of the tiled scan needs that can be derived from the head tensors: the (cached) tensor maps
+// and the tile geometry.  Returns 1 when the tiling applies, 0 when the caller should fall back, < 0 on error.
+// tg.stages is left to the caller.
+template <typename T, int kTileW>
+int plan_tma_scan(const void* p3, const void* p4, const void* p5, const HeadGeom& g, int B, TmaMaps* out_maps, TmaGeom* out_tg) {
   EncodeTiledFn encode = tensor_map_encoder();
   if (!encode) return 0;
   // a warp owns 16 consecutive anchors = two bytes of the stream's mask: every level must hold a
@@ -1212,24 +680,25 @@ int launch_decode_tma_w(const void* p3, const void* p4, const void* p5, const He
   for (int l = 0; l < 3; ++l)
     if (g.lv[l].hw % kAnchorsPerWarp != 0 || g.lv[l].w % 2 != 0) return 0;
   const int ch = kBoxCh + g.num_classes;
-  const int tile_rows = SPLIT ? g.num_classes : ch;
   const void* ptrs[3] = {p3, p4, p5};
   // tensor maps are cached by what they describe (a caller cycles through a few sets of head buffers):
-  // encoding six maps per step is host time the step does not have to spare
+  // encoding three maps per step is host time the step does not have to spare
   struct MapKey {
     const void* p[3];
-    int B, h, w, nc;
+    int B, h, w, nc, dev;
     bool operator==(const MapKey& o) const {
-      return p[0] == o.p[0] && p[1] == o.p[1] && p[2] == o.p[2] && B == o.B && h == o.h && w == o.w && nc == o.nc;
+      return p[0] == o.p[0] && p[1] == o.p[1] && p[2] == o.p[2] && B == o.B && h == o.h && w == o.w && nc == o.nc && dev == o.dev;
     }
   };
   struct MapEntry {
     MapKey key;
     TmaMaps maps;
   };
-  static std::vector<MapEntry> cache;  // per instantiation (element type, tile width, split)
+  static std::vector<MapEntry> cache;  // per instantiation (element type, tile width); guarded by the API mutex
   static size_t next_victim = 0;
-  const MapKey key{{p3, p4, p5}, B, g.lv[0].h, g.lv[0].w, g.num_classes};
+  int dev = 0;
+  RTM_CUDA(cudaGetDevice(&dev));
+  const MapKey key{{p3, p4, p5}, B, g.lv[0].h, g.lv[0].w, g.num_classes, dev};
   const TmaMaps* cached = nullptr;
   for (const MapEntry& e : cache)
     if (e.key == key) {
@@ -1238,7 +707,6 @@ int launch_decode_tma_w(const void* p3, const void* p4, const void* p5, const He
     }
   TmaMaps fresh;
   if (!cached) {
-    TmaMaps& maps = fresh;
     static const int promo_env = env_int("RTM_TMA_L2PROMO", 3);  // 0 none, 1 64B, 2 128B, 3 256B
     const CUtensorMapL2promotion promo = promo_env == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
                                          : promo_env == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
@@ -1248,16 +716,11 @@ int launch_decode_tma_w(const void* p3, const void* p4, const void* p5, const He
       const cuuint64_t dims[3] = {static_cast<cuuint64_t>(g.lv[l].hw), static_cast<cuuint64_t>(ch), static_cast<cuuint64_t>(B)};
       const cuuint64_t strides[2] = {static_cast<cuuint64_t>(g.lv[l].hw) * sizeof(T),
                                      static_cast<cuuint64_t>(g.lv[l].hw) * ch * sizeof(T)};
-      const cuuint32_t box[3] = {kTileW, static_cast<cuuint32_t>(tile_rows), 1};
+      const cuuint32_t box[3] = {kTileW, static_cast<cuuint32_t>(ch), 1};
       const cuuint32_t estr[3] = {1, 1, 1};
       if (ch > 256 || (strides[0] & 15) != 0) return 0;
-      CUresult r = encode(&maps.tile[l], tensor_map_dtype<T>(), 3, const_cast<void*>(ptrs[l]), dims, strides, box, estr,
+      CUresult r = encode(&fresh.tile[l], tensor_map_dtype<T>(), 3, const_cast<void*>(ptrs[l]), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      if (r != CUDA_SUCCESS) return 0;
-      const cuuint32_t sub[3] = {kAnchorsPerWarp, kBoxCh, 1};  // a warp's box sub-tile (SPLIT); no L2 promotion: sector-sized rows
-      r = encode(&maps.box[l], tensor_map_dtype<T>(), 3, const_cast<void*>(ptrs[l]), dims, strides, sub, estr,
-                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return 0;
     }
     if (cache.size() < 64) {
@@ -1268,48 +731,56 @@ int launch_decode_tma_w(const void* p3, const void* p4, const void* p5, const He
     }
     cached = &fresh;
   }
-  const TmaMaps& maps = *cached;
-  TmaGeom tg;
+  *out_maps = *cached;
+  TmaGeom& tg = *out_tg;
   tg.g = g;
   tg.tiles_before[0] = 0;
   for (int l = 0; l < 3; ++l) tg.tiles_before[l + 1] = tg.tiles_before[l] + (g.lv[l].hw + kTileW - 1) / kTileW;
   tg.total_tiles = tg.tiles_before[3] * B;
-  tg.tile_bytes = tile_rows * kTileW * static_cast<int>(sizeof(T));
+  tg.tile_bytes = ch * kTileW * static_cast<int>(sizeof(T));
   static const int static_env = env_int("RTM_TMA_STATIC_ROUNDS", 1);
   tg.static_rounds = static_env < 0 ? 0 : static_env;
   static const int evict_env = env_int("RTM_TMA_EVICT_FIRST", 1);
   tg.evict_first = evict_env;
-  static const int trigger_env = env_int("RTM_SCAN_TRIGGER", 0);
-  tg.trigger = trigger_env;
+  tg.trigger = 0;
+  tg.stages = 0;
   if (tg.tile_bytes % 128 != 0) return 0;
+  return 1;
+}
+
+// returns 1 when the TMA path was launched, 0 when the caller should fall back, < 0 on error
+template <typename T, int kTileW>
+int launch_decode_tma_w(const void* p3, const void* p4, const void* p5, const HeadGeom& g, int B,
+                        const rtm_nms_params& prm, const Workspace& ws, cudaStream_t stream, bool own_stream) {
+  TmaMaps maps;
+  TmaGeom tg;
+  const int ok = plan_tma_scan<T, kTileW>(p3, p4, p5, g, B, &maps, &tg);
+  if (ok <= 0) return ok;
+  // RTM_SCAN_TRIGGER=1 (experiments): consecutive scans on the library's own stream release each other at once
+  static const int trigger_env = env_int("RTM_SCAN_TRIGGER", 0);
+  tg.trigger = trigger_env && own_stream;
   // ring depth and residency: as many tiles in flight per SM as fit (RTM_TMA_STAGES / RTM_TMA_CTAS override)
   static const int stages_env = env_int("RTM_TMA_STAGES", 0), ctas_env = env_int("RTM_TMA_CTAS", 0);
   const size_t smem_budget = 216 * 1024;
-  const size_t box_smem = SPLIT ? static_cast<size_t>(kTileW / kAnchorsPerWarp) * 2 * kBoxCh * kAnchorsPerWarp * sizeof(T) : 0;
-  int ctas_per_sm = ctas_env > 0 ? ctas_env : (SPLIT ? (sizeof(T) == 2 ? 3 : 2) : (tg.tile_bytes <= 24 * 1024 ? 3 : (tg.tile_bytes <= 40 * 1024 ? 2 : 1)));
-  tg.stages = stages_env > 0 ? stages_env : (SPLIT ? (sizeof(T) == 2 ? 4 : 2) : (sizeof(T) == 2 ? 3 : 4));
+  int ctas_per_sm = ctas_env > 0 ? ctas_env : (tg.tile_bytes <= 24 * 1024 ? 3 : (tg.tile_bytes <= 40 * 1024 ? 2 : 1));
+  tg.stages = stages_env > 0 ? stages_env : (sizeof(T) == 2 ? 3 : 4);
   if (tg.stages > kMaxStages) tg.stages = kMaxStages;
-  while (tg.stages > 1 && (static_cast<size_t>(tg.stages) * tg.tile_bytes + box_smem) * ctas_per_sm > smem_budget) --tg.stages;
-  while (ctas_per_sm > 1 && (static_cast<size_t>(tg.stages) * tg.tile_bytes + box_smem) * ctas_per_sm > smem_budget) --ctas_per_sm;
-  // RTM_TMA_SMEM_PAD_KB: unused shared memory on top of the ring (experiments: caps how many scan CTAs - of this and of
-  // an overlapping scan - fit on an SM, i.e. how much room is left for another kernel's CTAs; 0 = none)
+  while (tg.stages > 1 && static_cast<size_t>(tg.stages) * tg.tile_bytes * ctas_per_sm > smem_budget) --tg.stages;
+  while (ctas_per_sm > 1 && static_cast<size_t>(tg.stages) * tg.tile_bytes * ctas_per_sm > smem_budget) --ctas_per_sm;
+  // RTM_TMA_SMEM_PAD_KB: unused shared memory on top of the ring (experiments: caps how many scan CTAs fit on an SM)
   static const int pad_env = env_int("RTM_TMA_SMEM_PAD_KB", 0);
-  const size_t smem = static_cast<size_t>(tg.stages) * tg.tile_bytes + box_smem + static_cast<size_t>(pad_env > 0 ? pad_env : 0) * 1024;
+  const size_t smem = static_cast<size_t>(tg.stages) * tg.tile_bytes + static_cast<size_t>(pad_env > 0 ? pad_env : 0) * 1024;
   if (smem > 220 * 1024) return 0;
-  static size_t configured = 0;
-  if (smem > configured) {
-    RTM_CUDA(cudaFuncSetAttribute(decode_tma_kernel<T, true, kTileW, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    RTM_CUDA(cudaFuncSetAttribute(decode_tma_kernel<T, false, kTileW, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    configured = smem;
-  }
+  if (int rc = rtm::ensure_dynamic_smem(reinterpret_cast<const void*>(decode_tma_kernel<T, true, kTileW>), smem)) return rc;
+  if (int rc = rtm::ensure_dynamic_smem(reinterpret_cast<const void*>(decode_tma_kernel<T, false, kTileW>), smem)) return rc;
   static const int grid_env = env_int("RTM_TMA_GRID", 0);  // experiments: any grid works with ticketed tiles
   const int grid = min(tg.total_tiles, grid_env > 0 ? grid_env : rtm::sm_count() * ctas_per_sm);
   {
     rtm::ProfileScope prof(RTM_K_DECODE, stream);
-    // Programmatic dependent launch: when the kernel in front of this one on the stream is the
-    // previous step's post kernel (which releases its dependents as soon as it starts), the scan
-    // of this step runs beside it - it reads nothing that kernel writes (other workspace half).
-    // Off while per-kernel profiling is on, so that each kernel is timed alone.
+    // Programmatic dependent launch ONLY on the library's own scan stream, where the launch in front of this one
+    // is always the library's previous scan: a dependent that does not execute griddepcontrol.wait has no ordering
+    // against its predecessor, so on a caller's stream (whose previous kernel may be the head producer, possibly
+    // one that releases its dependents early) the scan is an ordinary launch.
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(tma_threads(kTileW));
@@ -1319,12 +790,12 @@ int launch_decode_tma_w(const void* p3, const void* p4, const void* p5, const He
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = (rtm::pdl_enabled() && !rtm::g_profile_on) ? 1 : 0;
+    cfg.numAttrs = (own_stream && rtm::pdl_enabled() && !rtm::g_profile_on) ? 1 : 0;
     const float gate = logit_gate_for(prm.conf_thres);
     if (g.num_classes == 80)
-      RTM_CUDA(cudaLaunchKernelEx(&cfg, decode_tma_kernel<T, true, kTileW, SPLIT>, maps, tg, prm, gate, ws));
+      RTM_CUDA(cudaLaunchKernelEx(&cfg, decode_tma_kernel<T, true, kTileW>, maps, tg, prm, gate, ws));
     else
-      RTM_CUDA(cudaLaunchKernelEx(&cfg, decode_tma_kernel<T, false, kTileW, SPLIT>, maps, tg, prm, gate, ws));
+      RTM_CUDA(cudaLaunchKernelEx(&cfg, decode_tma_kernel<T, false, kTileW>, maps, tg, prm, gate, ws));
   }
   RTM_LAUNCH_CHECK("decode_tma_kernel");
   return 1;
@@ -1332,29 +803,23 @@ int launch_decode_tma_w(const void* p3, const void* p4, const void* p5, const He
 
 template <typename T>
 int try_launch_decode_tma(const void* p3, const void* p4, const void* p5, const HeadGeom& g, int B,
-                          const rtm_nms_params& prm, const Workspace& ws, cudaStream_t stream) {
+                          const rtm_nms_params& prm, const Workspace& ws, cudaStream_t stream, bool own_stream) {
   // anchors per tile (RTM_TMA_TILEW = 32 | 64 | 80 | 128 overrides): 80 when it divides every level
   // (640 x 640: 6400 / 1600 / 400; measured fastest, profiles/), else 64 / 32 with a masked tail
   static const int tile_env = env_int("RTM_TMA_TILEW", 0);
   bool div80 = true;
   for (int l = 0; l < 3; ++l) div80 = div80 && g.lv[l].hw % 80 == 0;
   const int tile_w = tile_env > 0 ? tile_env : (div80 ? 80 : (sizeof(T) == 2 ? 64 : 32));
-  // RTM_TMA_SPLIT=1: class-plane tiles + per-warp box sub-tiles (80-wide tiles only).  Reads 27 % fewer bytes on
-  // the bench workload but is slower there (37.4 vs 36.1 us alone: 40 % of the warp-tiles hold a candidate, and each
-  // sub-tile is 64 requests of one sector); meant for sparse scenes, off by default
-  static const int split_env = env_int("RTM_TMA_SPLIT", 0);
   switch (tile_w) {
     case 32:
-      return launch_decode_tma_w<T, 32, false>(p3, p4, p5, g, B, prm, ws, stream);
+      return launch_decode_tma_w<T, 32>(p3, p4, p5, g, B, prm, ws, stream, own_stream);
     case 64:
-      return launch_decode_tma_w<T, 64, false>(p3, p4, p5, g, B, prm, ws, stream);
+      return launch_decode_tma_w<T, 64>(p3, p4, p5, g, B, prm, ws, stream, own_stream);
     case 80:
-      for (int l = 0; l < 3; ++l)
-        if (g.lv[l].hw % 80 != 0) return 0;
-      if (split_env) return launch_decode_tma_w<T, 80, true>(p3, p4, p5, g, B, prm, ws, stream);
-      return launch_decode_tma_w<T, 80, false>(p3, p4, p5, g, B, prm, ws, stream);
+      if (!div80) return 0;
+      return launch_decode_tma_w<T, 80>(p3, p4, p5, g, B, prm, ws, stream, own_stream);
     case 128:
-      return launch_decode_tma_w<T, 128, false>(p3, p4, p5, g, B, prm, ws, stream);
+      return launch_decode_tma_w<T, 128>(p3, p4, p5, g, B, prm, ws, stream, own_stream);
     default:
       return 0;
   }
@@ -1373,13 +838,13 @@ int decode_impl() {
 
 template <typename T>
 int launch_decode(const void* p3, const void* p4, const void* p5, const HeadGeom& g, int B,
-                  const rtm_nms_params& prm, const Workspace& ws, cudaStream_t stream) {
+                  const rtm_nms_params& prm, const Workspace& ws, cudaStream_t stream, bool own_stream) {
   HeadPtrs<T> heads{{static_cast<const T*>(p3), static_cast<const T*>(p4), static_cast<const T*>(p5)}};
   for (int l = 0; l < 3; ++l)
     RTM_REQUIRE((reinterpret_cast<uintptr_t>(heads.p[l]) & 15) == 0, "head level %d must be 16-byte aligned", l);
   const int impl = decode_impl();
   if (impl == 1) {
-    const int tma = try_launch_decode_tma<T>(p3, p4, p5, g, B, prm, ws, stream);
+    const int tma = try_launch_decode_tma<T>(p3, p4, p5, g, B, prm, ws, stream, own_stream);
     if (tma != 0) return tma < 0 ? tma : RTM_OK;
   }
   const float gate = logit_gate_for(prm.conf_thres);
@@ -1404,18 +869,8 @@ int launch_decode(const void* p3, const void* p4, const void* p5, const HeadGeom
     cfg.gridDim = dim3((warps + kScanThreads / 32 - 1) / (kScanThreads / 32), B);
     cfg.blockDim = dim3(kScanThreads);
     cfg.dynamicSmemBytes = sizeof(ScanWarpSmem<T, BATCH>) * (kScanThreads / 32);
-    static bool configured = false;
-    if (!configured) {
-      RTM_CUDA(cudaFuncSetAttribute(decode_scan_kernel<T, BATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    static_cast<int>(cfg.dynamicSmemBytes)));
-      configured = true;
-    }
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = (rtm::pdl_enabled() && !rtm::g_profile_on) ? 1 : 0;
+    if (int rc = rtm::ensure_dynamic_smem(reinterpret_cast<const void*>(decode_scan_kernel<T, BATCH>), cfg.dynamicSmemBytes)) return rc;
+    cfg.stream = stream;  // an ordinary launch: ordered after whatever produced the head tensors on this stream
     RTM_CUDA(cudaLaunchKernelEx(&cfg, decode_scan_kernel<T, BATCH>, heads, g, prm, gate, ws));
   }
   RTM_LAUNCH_CHECK("decode_scan_kernel");
@@ -1430,21 +885,109 @@ extern "C" size_t rtm_nms_workspace_bytes(int32_t num_streams, int32_t num_ancho
 }
 
 namespace {
-std::unordered_map<const void*, int>& slot_table() {
-  static std::unordered_map<const void*, int> t;
+struct CtxKey {
+  int device;
+  const void* workspace;
+  bool operator==(const CtxKey& o) const { return device == o.device && workspace == o.workspace; }
+};
+struct CtxKeyHash {
+  size_t operator()(const CtxKey& k) const { return std::hash<const void*>()(k.workspace) ^ (static_cast<size_t>(k.device) << 1); }
+};
+std::unordered_map<CtxKey, rtm::WorkspaceCtx, CtxKeyHash>& ctx_table() {
+  static std::unordered_map<CtxKey, rtm::WorkspaceCtx, CtxKeyHash> t;
   return t;
 }
 }  // namespace
 
-int rtm::next_scan_slot(const void* workspace) {
-  const auto& t = slot_table();
-  const auto it = t.find(workspace);
-  return it == t.end() ? 0 : it->second;
+std::recursive_mutex& rtm::api_mutex() {
+  static std::recursive_mutex m;
+  return m;
 }
+
+size_t rtm::workspace_header_bytes(int num_streams) { return header_bytes(num_streams); }
+
+// Find or create the host bookkeeping of `workspace` on the current device.  The first time an address is seen
+// its header (ticket / completion counters, per-stream sequence numbers) is cleared, synchronously - not on the
+// per-frame path, and whichever stream uses the workspace first then finds it armed.  Callers hold api_mutex().
+int rtm::workspace_ctx(void* workspace, size_t workspace_bytes, int num_streams, cudaStream_t s, rtm::WorkspaceCtx** out) {
+  RTM_REQUIRE(workspace, "null workspace");
+  RTM_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
+  int dev = 0;
+  RTM_CUDA(cudaGetDevice(&dev));
+  auto& table = ctx_table();
+  auto it = table.find(CtxKey{dev, workspace});
+  if (it == table.end()) {
+    const size_t head = header_bytes(num_streams);
+    RTM_REQUIRE(workspace_bytes >= head, "workspace too small");
+    RTM_CUDA(cudaMemsetAsync(workspace, 0, head, s));
+    RTM_CUDA(cudaStreamSynchronize(s));
+    it = table.emplace(CtxKey{dev, workspace}, rtm::WorkspaceCtx()).first;
+    it->second.device = dev;
+    it->second.header_streams = num_streams;
+  } else if (num_streams > it->second.header_streams) {
+    // a larger batch on the same address: the per-stream part of the header grows - start it from zero again
+    rtm::WorkspaceCtx& c = it->second;
+    if (c.stream) RTM_CUDA(cudaStreamSynchronize(c.stream));
+    RTM_CUDA(cudaStreamSynchronize(s));
+    RTM_CUDA(cudaMemsetAsync(workspace, 0, header_bytes(num_streams), s));
+    RTM_CUDA(cudaStreamSynchronize(s));
+    c.reset_counters();
+    c.header_streams = num_streams;
+  }
+  *out = &it->second;
+  return RTM_OK;
+}
+
+int rtm::workspace_streams(rtm::WorkspaceCtx* c) {
+  if (c->stream) return RTM_OK;
+  RTM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < rtm::kCandSlots; ++i) {
+    RTM_CUDA(cudaEventCreateWithFlags(&c->scanned[i], cudaEventDisableTiming));
+    RTM_CUDA(cudaEventCreateWithFlags(&c->consumed[i], cudaEventDisableTiming));
+    RTM_CUDA(cudaEventCreateWithFlags(&c->done[i], cudaEventDisableTiming));
+  }
+  RTM_CUDA(cudaEventCreateWithFlags(&c->caller_mark, cudaEventDisableTiming));
+  return RTM_OK;
+}
+
+// Takes the next slot of the workspace's candidate ring and describes it in *ws.
+int rtm::take_scan_slot(rtm::WorkspaceCtx* c, void* workspace, size_t workspace_bytes, int num_streams, int num_anchors,
+                        Workspace* ws) {
+  const int slot = c->next_slot;
+  c->next_slot = (slot + 1) % kCandSlots;
+  const size_t need = workspace_layout(num_streams, num_anchors, static_cast<char*>(workspace), ws, slot);
+  RTM_REQUIRE(workspace_bytes >= need, "workspace has %zu bytes, %zu needed", workspace_bytes, need);
+  return RTM_OK;
+}
+
+extern "C" int rtm_workspace_release(void* workspace) {
+  std::lock_guard<std::recursive_mutex> lock(rtm::api_mutex());
+  int dev = 0;
+  RTM_CUDA(cudaGetDevice(&dev));
+  auto& table = ctx_table();
+  auto it = table.find(CtxKey{dev, workspace});
+  if (it == table.end()) return RTM_OK;
+  rtm::WorkspaceCtx& c = it->second;
+  if (c.stream) {
+    RTM_CUDA(cudaStreamSynchronize(c.stream));
+    for (int i = 0; i < rtm::kCandSlots; ++i) {
+      cudaEventDestroy(c.scanned[i]);
+      cudaEventDestroy(c.consumed[i]);
+      cudaEventDestroy(c.done[i]);
+    }
+    cudaEventDestroy(c.caller_mark);
+    cudaStreamDestroy(c.stream);
+  }
+  table.erase(it);
+  return RTM_OK;
+}
+
+int rtm::geometry_for(int img_h, int img_w, int num_classes, HeadGeom* g) { return make_geom(img_h, img_w, num_classes, g); }
 
 int rtm::launch_decode_stage(const void* head_p3, const void* head_p4, const void* head_p5, int head_dtype,
                              int num_streams, int img_h, int img_w, const rtm_nms_params* params, void* workspace,
-                             size_t workspace_bytes, Workspace* ws, cudaStream_t s) {
+                             size_t workspace_bytes, Workspace* ws, cudaStream_t s, rtm::WorkspaceCtx** out_ctx,
+                             cudaStream_t scan_stream) {
   RTM_REQUIRE(head_p3 && head_p4 && head_p5, "null head tensor");
   HeadGeom g;
   int rc = make_geom(img_h, img_w, params->num_classes, &g);
@@ -1453,29 +996,52 @@ int rtm::launch_decode_stage(const void* head_p3, const void* head_p4, const voi
   // that several stream batches, each with its own workspace and CUDA stream, can be interleaved).
   // The ticket counters must start at zero: the header is cleared the first time a workspace is seen;
   // afterwards every NMS stage leaves the counter of the slot it consumed at zero.
-  std::unordered_map<const void*, int>& next_slot = slot_table();
-  auto it = next_slot.find(workspace);
-  if (it == next_slot.end()) {
-    RTM_REQUIRE(workspace_bytes >= kWorkspaceHeader, "workspace too small");
-    RTM_CUDA(cudaMemsetAsync(workspace, 0, kWorkspaceHeader, s));
-    it = next_slot.emplace(workspace, 0).first;
-  }
-  const int half = it->second;
-  it->second = (half + 1) % kCandSlots;
-  const size_t need = workspace_layout(num_streams, g.num_anchors, static_cast<char*>(workspace), ws, half);
-  RTM_REQUIRE(workspace_bytes >= need, "workspace has %zu bytes, %zu needed", workspace_bytes, need);
-  RTM_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
+  std::lock_guard<std::recursive_mutex> lock(rtm::api_mutex());
+  rtm::WorkspaceCtx* ctx = nullptr;
+  rc = rtm::workspace_ctx(workspace, workspace_bytes, num_streams, s, &ctx);
+  if (rc) return rc;
+  if (out_ctx) *out_ctx = ctx;
+  rc = rtm::take_scan_slot(ctx, workspace, workspace_bytes, num_streams, g.num_anchors, ws);
+  if (rc) return rc;
+  const bool own = scan_stream != nullptr;
+  cudaStream_t ls = own ? scan_stream : s;
   switch (head_dtype) {
     case RTM_F32:
-      return launch_decode<float>(head_p3, head_p4, head_p5, g, num_streams, *params, *ws, s);
+      return launch_decode<float>(head_p3, head_p4, head_p5, g, num_streams, *params, *ws, ls, own);
     case RTM_F16:
-      return launch_decode<__half>(head_p3, head_p4, head_p5, g, num_streams, *params, *ws, s);
+      return launch_decode<__half>(head_p3, head_p4, head_p5, g, num_streams, *params, *ws, ls, own);
     case RTM_BF16:
-      return launch_decode<__nv_bfloat16>(head_p3, head_p4, head_p5, g, num_streams, *params, *ws, s);
+      return launch_decode<__nv_bfloat16>(head_p3, head_p4, head_p5, g, num_streams, *params, *ws, ls, own);
     default:
       RTM_REQUIRE(false, "unknown head_dtype %d", head_dtype);
   }
   return RTM_OK;
+}
+
+int rtm::plan_tma_scan80(const void* p3, const void* p4, const void* p5, int head_dtype, int num_streams, int img_h,
+                         int img_w, const rtm_nms_params* params, rtm::TmaScanPlan* plan) {
+  RTM_REQUIRE(p3 && p4 && p5, "null head tensor");
+  HeadGeom g;
+  int rc = make_geom(img_h, img_w, params->num_classes, &g);
+  if (rc) return rc;
+  for (const void* p : {p3, p4, p5})
+    RTM_REQUIRE((reinterpret_cast<uintptr_t>(p) & 15) == 0, "head tensors must be 16-byte aligned");
+  if (decode_impl() != 1 || env_int("RTM_TMA_TILEW", 80) != 80) return 0;
+  for (int l = 0; l < 3; ++l)
+    if (g.lv[l].hw % 80 != 0) return 0;
+  plan->logit_gate = logit_gate_for(params->conf_thres);
+  plan->nc80 = g.num_classes == 80;
+  switch (head_dtype) {
+    case RTM_F32:
+      return plan_tma_scan<float, 80>(p3, p4, p5, g, num_streams, &plan->maps, &plan->tg);
+    case RTM_F16:
+      return plan_tma_scan<__half, 80>(p3, p4, p5, g, num_streams, &plan->maps, &plan->tg);
+    case RTM_BF16:
+      return plan_tma_scan<__nv_bfloat16, 80>(p3, p4, p5, g, num_streams, &plan->maps, &plan->tg);
+    default:
+      RTM_REQUIRE(false, "unknown head_dtype %d", head_dtype);
+  }
+  return 0;
 }
 
 extern "C" int rtm_decode_nms(const void* head_p3, const void* head_p4, const void* head_p5,

@@ -14,13 +14,15 @@
 #include <float.h>
 #include <math.h>
 
+#include <mutex>
+
 #include "rtm_common.cuh"
 
 namespace rtm {
 
 constexpr float kMaxWh = 7680.f;    // ultralytics non_max_suppression max_wh
 #ifndef RTM_NMS_SMEM_CAND
-#define RTM_NMS_SMEM_CAND 2048
+#define RTM_NMS_SMEM_CAND 1024  // streams with more candidates take the spill arrays of the workspace
 #endif
 constexpr int kNmsSmemCand = RTM_NMS_SMEM_CAND;  // candidates handled entirely in shared memory
 constexpr int kIdxBits = 15;        // candidate rank (< 32768) in the low key bits
@@ -41,7 +43,8 @@ struct Workspace {
   uint32_t* alive;  // (B, 2, words)
   // tile ticket counter of the head scan that filled this candidate list; the NMS stage that
   // consumes the list zeroes it again (the workspace starts zero-filled)
-  int* tile_counter;
+  int* tile_counter;  // [1]: scan CTAs done, [2]: streams done reading the slot (one-launch step, post.cu)
+  int* sync;          // step kernel: [0] caller-stream mark, [64 + launch % 64] tile tickets, [128 + b] steps completed by stream b
   int num_anchors, words, cap_p2;
   int slot;  // which slot of the candidate ring this is (host-side bookkeeping)
 };
@@ -71,15 +74,50 @@ inline float iou_gate_for(double thr) {
 // (an event wait between two scans keeps the second from being launched ahead, ~1.6 us per step when measured).
 constexpr int kCandSlots = 8;
 constexpr int kSlotWaitEvery = 4;  // must divide kCandSlots; kCandSlots - kSlotWaitEvery steps of run-ahead remain
-// slot of the candidate ring the next scan of `workspace` will take (defined in nms.cu)
-int next_scan_slot(const void* workspace);
+constexpr int kSyncTicketRing = 64;   // ws.sync[kSyncTicketRing + (launch % 64)]: tile tickets of a step kernel launch
+constexpr int kSyncStreamSeq = 128;   // ws.sync[kSyncStreamSeq + b]: steps completed by stream b
 
+// Host bookkeeping of one workspace (nms.cu), keyed by (device, address); every entry point that touches it
+// holds api_mutex().  rtm_workspace_release drops the entry together with the stream and events it owns.
+struct WorkspaceCtx {
+  int device = 0;
+  int header_streams = 0;  // streams the cleared header was sized for
+  int next_slot = 0;       // slot of the candidate ring the next scan takes
+  cudaStream_t stream = nullptr;  // the library's own stream for this workspace (heads_ready steps)
+  // two-kernel pipeline: scan on `stream`, post kernel on the caller's stream
+  cudaEvent_t scanned[kCandSlots] = {};   // slot's candidate list is complete
+  cudaEvent_t consumed[kCandSlots] = {};  // slot's post kernel is done (recorded on the caller's stream)
+  bool consumed_valid[kCandSlots] = {};
+  int covered = 0;  // scans to come whose slots are already known to be free
+  // one-launch step
+  cudaEvent_t done[kCandSlots] = {};  // the step kernel that used the slot has finished
+  cudaEvent_t caller_mark = nullptr;
+  int tiles_done_target[kCandSlots] = {};  // value of the slot's "tiles done" counter once its current scan is over
+  int slot_free_target[kCandSlots] = {};   // value of the slot's "streams done" counter once its current readers are done
+  int post_ticket_base[kCandSlots] = {};   // value of the slot's post-ticket counter before its current launch
+  int seq = 0;            // step kernels launched so far
+  int chain_streams = 0;  // batch size of the step kernel last enqueued on `stream` (0: none a new launch could overlap)
+  int caller_seq = 0;     // caller-stream marks written so far
+  void reset_counters() {
+    for (int i = 0; i < kCandSlots; ++i) {
+      tiles_done_target[i] = slot_free_target[i] = post_ticket_base[i] = 0;
+      consumed_valid[i] = false;
+    }
+    seq = chain_streams = caller_seq = covered = 0;
+  }
+};
+std::recursive_mutex& api_mutex();
+size_t workspace_header_bytes(int num_streams);
+int workspace_ctx(void* workspace, size_t workspace_bytes, int num_streams, cudaStream_t s, WorkspaceCtx** out);
+int workspace_streams(WorkspaceCtx* c);  // creates the library's stream and events of the workspace if need be
+int take_scan_slot(WorkspaceCtx* c, void* workspace, size_t workspace_bytes, int num_streams, int num_anchors, Workspace* ws);
 
 // D1 + N1 only (defined in nms.cu): scans the head tensors and leaves the candidate list of every
-// stream in `workspace`; *ws describes it for the NMS stage.
+// stream in `workspace`; *ws describes it for the NMS stage.  scan_stream != null: the scan goes to that
+// stream (the library's own) instead of `stream`.
 int launch_decode_stage(const void* head_p3, const void* head_p4, const void* head_p5, int head_dtype, int num_streams,
                         int img_h, int img_w, const rtm_nms_params* params, void* workspace, size_t workspace_bytes,
-                        Workspace* ws, cudaStream_t stream);
+                        Workspace* ws, cudaStream_t stream, WorkspaceCtx** ctx = nullptr, cudaStream_t scan_stream = nullptr);
 
 // bytes of dynamic shared memory nms_stream needs
 constexpr size_t kNmsSmemBytes = (sizeof(uint64_t) + 2 * sizeof(float4) + sizeof(float) + sizeof(int32_t)) * kNmsSmemCand +
@@ -194,7 +232,7 @@ __device__ __forceinline__ bool bucket_sort_keys(uint64_t* keys, const int n, ui
   const int c0 = cnt[4 * tid], c1 = cnt[4 * tid + 1], c2 = cnt[4 * tid + 2], c3 = cnt[4 * tid + 3];
   if (__syncthreads_or(max(max(c0, c1), max(c2, c3)) > kSortBucketMax)) return false;
   int tot;
-  const int base = block_exclusive_sum(c0 + c1 + c2 + c3, s_scan, &tot);
+  const int base = block_exclusive_sum<THREADS>(c0 + c1 + c2 + c3, s_scan, &tot);
   cnt[4 * tid] = base;
   cnt[4 * tid + 1] = base + c0;
   cnt[4 * tid + 2] = base + c0 + c1;
@@ -618,7 +656,7 @@ __device__ __forceinline__ int nms_run(const Workspace& ws, const rtm_nms_params
       const int w = w0 + tid;
       uint32_t m = w < words ? kmask[w] : 0u;
       int tot;
-      int r = K + block_exclusive_sum(__popc(m), s_scan, &tot);
+      int r = K + block_exclusive_sum<THREADS>(__popc(m), s_scan, &tot);
       while (m) {
         const int pos = (w << 5) + __ffs(m) - 1;
         m &= m - 1;
@@ -717,7 +755,7 @@ __device__ __forceinline__ int nms_stream(const Workspace& ws, const rtm_nms_par
   const int tid = threadIdx.x;
   const int A = ws.num_anchors, W = ws.words;
   const uint32_t* mask = ws.mask + static_cast<size_t>(b) * W;
-  if (b == 0 && tid == 0) *ws.tile_counter = 0;  // the scan that filled this list is over: re-arm its tickets
+  if (ws.tile_counter && b == 0 && tid == 0) *ws.tile_counter = 0;  // the scan that filled this list is over: re-arm its tickets
   // ---- one pass over the stream's candidate mask: words stay in registers, ranks by block scan ----
   constexpr int kIters = (kMaxAnchors / 32 + THREADS - 1) / THREADS;
   uint32_t mw[kIters];
@@ -738,7 +776,7 @@ __device__ __forceinline__ int nms_stream(const Workspace& ws, const rtm_nms_par
       const int valid = A - (w << 5);
       if (w < W && valid < 32) m &= (1u << valid) - 1u;
       int tot;
-      rb[it] = n + block_exclusive_sum(__popc(m), s_scan, &tot);
+      rb[it] = n + block_exclusive_sum<THREADS>(__popc(m), s_scan, &tot);
       mw[it] = m;
       n += tot;
     }

@@ -40,6 +40,8 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 int sm_count();  // cached multiProcessorCount of the current device
+// raises a kernel's dynamic shared-memory limit when `bytes` exceeds what was set for it on the current device
+int ensure_dynamic_smem(const void* func, size_t bytes);
 bool pdl_enabled();  // programmatic dependent launch of the step kernels (RTM_PDL=0 turns it off)
 
 // Brackets a kernel launch with CUDA events while rtm_profile_enable(1) is in effect.
@@ -79,9 +81,11 @@ constexpr unsigned kFull = 0xffffffffu;
 
 // Order-preserving compaction support: exclusive prefix of `flag` over the threads of the
 // block (thread order), plus the block total.  `scratch` holds 33 ints.
-// All threads of the block must call it; contains three __syncthreads().
+// The block's first THREADS threads - all that are still running - must call it; contains three __syncthreads().
+template <int THREADS>
 __device__ __forceinline__ int block_exclusive_count(bool flag, int* scratch, int* total) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int nwarp = (THREADS + 31) >> 5;  // the threads that take part (a block may hold more: they have left by then)
   const unsigned bal = __ballot_sync(kFull, flag);
   const int within = __popc(bal & ((1u << lane) - 1u));
   if (lane == 0) scratch[warp] = __popc(bal);
@@ -107,8 +111,10 @@ __device__ __forceinline__ int block_exclusive_count(bool flag, int* scratch, in
 
 // Exclusive prefix sum of `v` over the threads of the block (thread order) plus the block
 // total.  `scratch` holds 33 ints.  All threads must call it; three __syncthreads().
+template <int THREADS>
 __device__ __forceinline__ int block_exclusive_sum(int v, int* scratch, int* total) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int nwarp = (THREADS + 31) >> 5;
   int incl = v;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {

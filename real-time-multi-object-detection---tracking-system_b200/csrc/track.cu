@@ -37,12 +37,8 @@ int launch_track(const TrackArgs& a, cudaStream_t stream) {
   const size_t smem = track_smem_bytes(a.det_stride, a.tin.capacity, a.assignment == RTM_ASSIGN_OPTIMAL);
   RTM_REQUIRE(smem + sizeof(rtm::TrackPrefetch) <= 226 * 1024, "rtm_track_step: det_stride %d / capacity %d need %zu B of shared memory (> 227 KB)",
               a.det_stride, a.tin.capacity, smem);
-  static size_t configured = 0;
-  if (smem + sizeof(rtm::TrackPrefetch) > 40 * 1024 && smem > configured) {  // static + dynamic beyond the default limit
-    RTM_CUDA(cudaFuncSetAttribute(track_step_kernel<THREADS>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    configured = smem;
-  }
+  if (smem + sizeof(rtm::TrackPrefetch) > 40 * 1024)  // static + dynamic beyond the default limit
+    if (int rc = rtm::ensure_dynamic_smem(reinterpret_cast<const void*>(track_step_kernel<THREADS>), smem)) return rc;
   {
     rtm::ProfileScope prof(RTM_K_TRACK, stream);
     track_step_kernel<THREADS><<<a.tin.num_streams, THREADS, smem, stream>>>(a);

@@ -154,7 +154,7 @@ __device__ __forceinline__ float box_area(const float4 b) {
 // The head of a stream's input table, staged in shared memory ahead of use: the fused kernel
 // issues these loads before the NMS stage so that their latency is off the critical path.
 #ifndef RTM_TRACK_PREF_ROWS
-#define RTM_TRACK_PREF_ROWS 512
+#define RTM_TRACK_PREF_ROWS 256
 #endif
 constexpr int kTrackPrefRows = RTM_TRACK_PREF_ROWS;
 struct TrackPrefetch {
@@ -553,7 +553,7 @@ __device__ __forceinline__ void track_stream(const TrackArgs& a, const int b, un
       if (a.det_kind) a.det_kind[det0 + d] = RTM_DET_NONE;
     }
     int tot;
-    const int p = block_exclusive_count(hi, s_scan, &tot);
+    const int p = block_exclusive_count<THREADS>(hi, s_scan, &tot);
     if (hi) s_hi[H + p] = d;
     if (valid && !hi) s_lo[L + (tid - p)] = d;
     const int in_round = min(THREADS, n - r0);
@@ -599,7 +599,7 @@ __device__ __forceinline__ void track_stream(const TrackArgs& a, const int b, un
     const int j = r0 + tid;
     const bool born = j < H && s_born[j];
     int tot;
-    const int p = block_exclusive_count(born, s_scan, &tot);
+    const int p = block_exclusive_count<THREADS>(born, s_scan, &tot);
     if (born) s_birth[NB + p] = s_hi[j];
     NB += tot;
   }
@@ -659,7 +659,7 @@ __device__ __forceinline__ void track_stream(const TrackArgs& a, const int b, un
       if (a.det_kind) a.det_kind[det0 + det] = kind;
     }
     int tot;
-    const int p = kept + block_exclusive_count(keep, s_scan, &tot);
+    const int p = kept + block_exclusive_count<THREADS>(keep, s_scan, &tot);
     if (keep && p < cap) {
       a.tout.track_id[row0 + p] = id;
       out_box[p] = box;

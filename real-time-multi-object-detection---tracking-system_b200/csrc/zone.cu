@@ -49,11 +49,8 @@ extern "C" int rtm_zone_step(const rtm_zone_set* zones, const rtm_track_table* t
              events, event_stride, event_count, status};
   const size_t smem = rtm::zone_smem_bytes(event_stride);
   RTM_REQUIRE(smem + sizeof(rtm::ZonePrefetch) <= 226 * 1024, "rtm_zone_step: %zu B of shared memory needed", smem);
-  static size_t configured = 0;
-  if (smem > 24 * 1024 && smem > configured) {
-    RTM_CUDA(cudaFuncSetAttribute(zone_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    configured = smem;
-  }
+  if (smem > 24 * 1024)
+    if (int rc = rtm::ensure_dynamic_smem(reinterpret_cast<const void*>(zone_step_kernel), smem)) return rc;
   {
     rtm::ProfileScope prof(RTM_K_ZONE, static_cast<cudaStream_t>(stream));
     zone_step_kernel<<<tracks->num_streams, kZoneThreads, smem, static_cast<cudaStream_t>(stream)>>>(a);

@@ -51,7 +51,7 @@ __device__ __forceinline__ int point_in_polygon(const int2* __restrict__ poly, i
 // issues these loads before the NMS stage).  kZonePrefVertices vertices are staged; streams with
 // more read their polygons from global memory.
 #ifndef RTM_ZONE_PREF_VERTICES
-#define RTM_ZONE_PREF_VERTICES 2048
+#define RTM_ZONE_PREF_VERTICES 512
 #endif
 constexpr int kZonePrefVertices = RTM_ZONE_PREF_VERTICES;
 struct ZonePrefetch {
@@ -125,8 +125,12 @@ __device__ __forceinline__ void zone_stream(const ZoneArgs& a, const int b, unsi
   rtm_zone_event* ev_out = a.events + static_cast<size_t>(b) * a.event_stride;
 
   // ---- pass 1: (column, row) pairs, column-major so that state accesses coalesce over rows ----
+  // (the lanes of a warp are brought back together after every pair: their polygon walks take different turns, and
+  // without the barrier the warp drifts apart for the rest of the loop - ncu showed 4 of 32 lanes active, 7x the time)
   const int pairs = T * C;
-  for (int q = tid; q < pairs; q += THREADS) {
+  for (int q0 = 0; q0 < pairs; q0 += THREADS, __syncwarp()) {
+    const int q = q0 + tid;
+    if (q >= pairs) continue;
     const int c = q / T, r = q - c * T;
     const int src = a.src_row ? a.src_row[row0 + r] : r;
     const bool active = a.trk.time_since_update[row0 + r] == 1;

@@ -53,13 +53,15 @@ class Detector:
                  input_size: tuple = (640, 640), confidence: float = 0.35, iou: float = 0.45,
                  classes: Optional[list] = None, half: bool = True, device: str = "cuda:0",
                  max_det: int = 100, agnostic_nms: bool = False, *, model=None, names=None,
-                 num_classes: int = 80, warmup: bool = True, auto: bool = False) -> None:
+                 num_classes: int = 80, warmup: bool = True, auto: Optional[bool] = None) -> None:
         import torch
         from .yolov8s import COCO_NAMES, YOLOv8s
         self.input_size = tuple(input_size)
         # auto=True: LetterBox pads only to the next multiple of 32 (what ultralytics does for .pt models:
-        # 1080p -> 384 x 640, 5040 anchors); False: the square input the BASELINE configs fix (8400 anchors)
-        self.auto = bool(auto)
+        # 1080p -> 384 x 640, 5040 anchors); False: a fixed square input (exported engines; the BASELINE configs:
+        # 8400 anchors).  None (default) follows ultralytics' own rule, `auto = model is a .pt file`
+        # (detector.py:84-87 loads either an engine or the .pt fallback); a module passed in is taken as fixed-shape.
+        self.auto = auto
         self.confidence, self.iou, self.classes = confidence, iou, classes
         self.half = half and torch.cuda.is_available()
         self.device, self.max_det, self.agnostic_nms = device, max_det, agnostic_nms
@@ -79,9 +81,12 @@ class Detector:
                 chosen = Path(fallback_model)
             else:
                 raise FileNotFoundError(f"No model found at {model_path} or {fallback_model}")
+            if self.auto is None:
+                self.auto = chosen.suffix == ".pt"
             net = YOLOv8s(self.nc)
             state = torch.load(str(chosen), map_location="cpu", weights_only=True)
             net.load_state_dict(state)
+        self.auto = bool(self.auto)
         self.model = net.to(self._dev).to(self._dtype).eval()
         self._params = _lib.make_nms_params(confidence, iou, max_det, agnostic_nms, classes, self.nc)
         self._bufs = {}
@@ -108,13 +113,14 @@ class Detector:
                 count=torch.zeros(B, dtype=torch.int32, device=dev),
                 status=torch.zeros(B, dtype=torch.int32, device=dev),
                 ws=torch.zeros(self._lib.rtm_nms_workspace_bytes(B, A), dtype=torch.uint8, device=dev))}
+            self._lib.rtm_workspace_release(self._bufs[key]["ws"].data_ptr())   # a recycled address starts afresh
         return self._bufs[key]
 
     def _geometry(self, src_hw):
         """LetterBox.__call__ (scaleup=True, center=True): network input (H, W) and where the resized
         source goes in it: (new_h, new_w, top, left)."""
         h0, w0 = src_hw
-        Hf, Wf = self.input_size[1], self.input_size[0]            # input_size is (w, h) like imgsz pairs
+        Hf = Wf = int(self.input_size[0])          # detector.py:102 passes imgsz=self.input_size[0]: a square target
         r = min(Hf / h0, Wf / w0)
         new_w, new_h = int(round(w0 * r)), int(round(h0 * r))
         dw, dh = Wf - new_w, Hf - new_h
@@ -148,7 +154,10 @@ class Detector:
                 buf["conf"].data_ptr(), buf["cls"].data_ptr(), None, None, buf["count"].data_ptr(),
                 self.max_det, buf["status"].data_ptr(), buf["ws"].data_ptr(), buf["ws"].numel(), st))
             n = buf["count"].cpu().numpy()
-            _lib.raise_on_status(buf["status"].cpu().numpy(), "Detector")
+            status = buf["status"].cpu().numpy()
+            if status.any():
+                buf["status"].zero_()
+            _lib.raise_on_status(status, "Detector")
             xyxy, conf, cls = buf["xyxy"].cpu().numpy(), buf["conf"].cpu().numpy(), buf["cls"].cpu().numpy()
         return [self._parse(xyxy[b, :n[b]], conf[b, :n[b]], cls[b, :n[b]]) for b in range(B)]
 

@@ -30,28 +30,45 @@ def owner_of(stream: int, total_streams: int, world_size: int) -> int:
     raise ValueError(f"stream {stream} outside 0..{total_streams - 1}")
 
 
-def reduce_summary(counters: Sequence[int], events_per_stream, device="cpu"):
-    """Sum ``counters`` over ranks and gather every rank's per-stream event counts.
+def reduce_summary(counters: Sequence[int], events, device="cpu", first_stream: int = 0):
+    """Sum ``counters`` over ranks and gather every rank's zone events of the closing step.
 
-    Returns ``(totals list[int], per_stream_events list[int] in global stream order)``.  With no
-    process group initialised it is the identity (single-GPU runs).
+    ``events``: this rank's 64-byte ``rtm_zone_event`` records (a NumPy structured array of
+    ``_lib.EVENT_DTYPE``, e.g. :meth:`StreamBatch.event_records`), streams numbered within the rank;
+    ``first_stream`` is the global id of the rank's stream 0.  Returns ``(totals list[int], records)``:
+    all ranks' records in global stream order with the ``stream`` field made global.  The exchange is
+    the one SURVEY section 8e specifies: ``all_reduce(SUM)`` of the counter vector, an ``all_gather``
+    of the record counts, and an ``all_gather`` of the records padded to the largest count - a few KB,
+    once per run.  A plain sequence of integers is accepted in place of records and gathered the same
+    way (returned as a flat list).  With no process group initialised it is the identity.
     """
+    import numpy as np
     import torch
     import torch.distributed as dist
+    from . import _lib
     c = torch.tensor(list(counters), dtype=torch.int64, device=device)
-    ev = torch.as_tensor(events_per_stream, dtype=torch.int64).to(device).reshape(-1)
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-        return c.tolist(), ev.tolist()
-    world = dist.get_world_size()
-    dist.all_reduce(c, op=dist.ReduceOp.SUM)
-    sizes = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
-    dist.all_gather(sizes, torch.tensor([ev.numel()], dtype=torch.int64, device=device))
-    width = int(max(int(s.item()) for s in sizes))
-    padded = torch.zeros(width, dtype=torch.int64, device=device)
-    padded[: ev.numel()] = ev
-    gathered = [torch.zeros(width, dtype=torch.int64, device=device) for _ in range(world)]
-    dist.all_gather(gathered, padded)
-    flat = []
-    for g, s in zip(gathered, sizes):
-        flat += g[: int(s.item())].tolist()
-    return c.tolist(), flat
+    is_records = isinstance(events, np.ndarray) and events.dtype.names is not None
+    if is_records:
+        rec = np.ascontiguousarray(events).copy()
+        rec["stream"] += np.int32(first_stream)
+        payload = torch.from_numpy(rec.view(np.uint8).reshape(-1)).to(device)
+        unit = rec.dtype.itemsize
+    else:
+        payload = torch.as_tensor(list(events), dtype=torch.int64).reshape(-1).to(device)
+        unit = 1
+    distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    if distributed:
+        world = dist.get_world_size()
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        sizes = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+        dist.all_gather(sizes, torch.tensor([payload.numel()], dtype=torch.int64, device=device))
+        width = max(int(max(int(s.item()) for s in sizes)), 1)
+        padded = torch.zeros(width, dtype=payload.dtype, device=device)
+        padded[: payload.numel()] = payload
+        parts = [torch.zeros(width, dtype=payload.dtype, device=device) for _ in range(world)]
+        dist.all_gather(parts, padded)
+        payload = torch.cat([g[: int(s.item())] for g, s in zip(parts, sizes)])
+    if is_records:
+        flat = payload.cpu().numpy().reshape(-1, unit).view(np.dtype(_lib.EVENT_DTYPE)).reshape(-1)
+        return c.tolist(), flat
+    return c.tolist(), payload.tolist()

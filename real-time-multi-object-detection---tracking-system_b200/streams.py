@@ -181,9 +181,22 @@ class ZoneTables:
             la = torch.zeros((B, ncol, self.capacity), dtype=torch.float64, device=device)
             self._state.append((fs, la, _lib.ZoneState(fs.data_ptr(), la.data_ptr())))
         self.cur = 0
-        self.event_stride = int(max_events or max(16, min(self.capacity * self.max_zones, 256)))
-        self.events = torch.zeros((B, self.event_stride, 64), dtype=torch.uint8, device=device)
-        self.event_count = torch.zeros(B, dtype=torch.int32, device=device)
+        # every (track row, zone) pair of a stream may fire in one step - a crowd whose dwell timers run out on the same
+        # frame does just that - up to what the kernel can stage per stream and step (kZoneStepEvents)
+        self.event_stride = int(max_events or max(16, min(self.capacity * self.max_zones, _lib.ZONE_STEP_EVENTS)))
+        # event slabs alternate with the state tables: the set written by a step is not the one the caller may
+        # still be reading from the step before (rtm_step_io.results_alternate)
+        self._events = [torch.zeros((B, self.event_stride, 64), dtype=torch.uint8, device=device) for _ in range(2)]
+        self._event_count = [torch.zeros(B, dtype=torch.int32, device=device) for _ in range(2)]
+
+    @property
+    def events(self):
+        """Event slabs of the last step (the set that goes with the current state)."""
+        return self._events[self.cur]
+
+    @property
+    def event_count(self):
+        return self._event_count[self.cur]
 
     def state_in(self):
         return self._state[self.cur]
@@ -246,19 +259,19 @@ class StreamBatch:
             i32 = dict(dtype=torch.int32, device=self.device)
             f32 = dict(dtype=torch.float32, device=self.device)
             D = self.det_stride
-            self.det_xyxy = torch.zeros(B, D, 4, **f32)
-            self.det_conf = torch.zeros(B, D, **f32)
-            self.det_cls = torch.zeros(B, D, **i32)
-            self.det_anchor = torch.zeros(B, D, **i32)
-            self.det_keep = torch.zeros(B, D, **i32)
-            self.det_count = torch.zeros(B, **i32)
-            self.det_track_id = torch.zeros(B, D, **i32)
-            self.det_kind = torch.zeros(B, D, **i32)
+            # two sets of result buffers, alternating like the track tables: a step never overwrites what the
+            # caller may still be reading from the step before it (rtm_step_io.results_alternate)
+            self._res = [dict(det_xyxy=torch.zeros(B, D, 4, **f32), det_conf=torch.zeros(B, D, **f32),
+                              det_cls=torch.zeros(B, D, **i32), det_anchor=torch.zeros(B, D, **i32),
+                              det_keep=torch.zeros(B, D, **i32), det_count=torch.zeros(B, **i32),
+                              det_track_id=torch.zeros(B, D, **i32), det_kind=torch.zeros(B, D, **i32)) for _ in range(2)]
             self.status = torch.zeros(B, **i32)
             gain, px, py = scale_params(self.src_hw, self.imgsz)
             self.scale = torch.tensor([[gain, px, py, self.src_hw[1], self.src_hw[0]]] * B, **f32)
             ws_bytes = self.lib.rtm_nms_workspace_bytes(B, self.num_anchors)
             self.workspace = torch.zeros(ws_bytes, dtype=torch.uint8, device=self.device)
+            # the allocator may hand out an address the library has seen before: start its bookkeeping afresh
+            _lib.check(self.lib.rtm_workspace_release(self.workspace.data_ptr()))
             # use_kalman: opt-in motion model the reference does not have (rtm_track_step_ex); off = reference
             self.use_kalman = bool(use_kalman)
             # assignment: "greedy" = what the reference runs without `lap` (and here); "lapjv" = its lap branch
@@ -276,7 +289,28 @@ class StreamBatch:
         self._host = None
         self._io_cache, self._head_cache = {}, {}
 
+    def close(self) -> None:
+        """Give the library's per-workspace bookkeeping (its stream and events) back; the batch is unusable after."""
+        ws, self.workspace = getattr(self, "workspace", None), None
+        if ws is not None:
+            import torch
+            with torch.cuda.device(self.device):
+                torch.cuda.synchronize(self.device)
+                self.lib.rtm_workspace_release(ws.data_ptr())
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
     # -- state views -------------------------------------------------------
+    def __getattr__(self, name):
+        # det_xyxy, det_conf, ... : the result buffers of the last step (the set that goes with the current table)
+        if name.startswith("det_") and "_res" in self.__dict__ and name in self._res[0]:
+            return self._res[self.cur][name]
+        raise AttributeError(name)
+
     @property
     def table(self) -> DeviceTrackTable:
         """The table holding the current state (after the last step)."""
@@ -310,20 +344,21 @@ class StreamBatch:
         io = _lib.StepIO()
         io.img_h, io.img_w = self.imgsz
         io.scale = self.scale.data_ptr()
-        io.det_xyxy, io.det_conf, io.det_cls = self.det_xyxy.data_ptr(), self.det_conf.data_ptr(), self.det_cls.data_ptr()
-        io.det_anchor, io.det_keep, io.det_count = self.det_anchor.data_ptr(), self.det_keep.data_ptr(), self.det_count.data_ptr()
+        res = self._res[self.cur ^ 1]                           # the set that goes with table_out
+        io.det_xyxy, io.det_conf, io.det_cls = res["det_xyxy"].data_ptr(), res["det_conf"].data_ptr(), res["det_cls"].data_ptr()
+        io.det_anchor, io.det_keep, io.det_count = res["det_anchor"].data_ptr(), res["det_keep"].data_ptr(), res["det_count"].data_ptr()
         io.det_stride = self.det_stride
         io.workspace, io.workspace_bytes = self.workspace.data_ptr(), self.workspace.numel()
         io.table_in = C.pointer(self.tables[self.cur].struct)
         io.table_out = C.pointer(self.tables[self.cur ^ 1].struct)
         io.track_thresh, io.match_thresh, io.track_buffer = self.track_thresh, self.match_thresh, self.track_buffer
-        io.det_track_id, io.det_kind, io.src_row = self.det_track_id.data_ptr(), self.det_kind.data_ptr(), self.src_row.data_ptr()
+        io.det_track_id, io.det_kind, io.src_row = res["det_track_id"].data_ptr(), res["det_kind"].data_ptr(), self.src_row.data_ptr()
         if self.zones is not None:
             io.zones = C.pointer(self.zones.zone_set)
             io.state_in = C.pointer(self.zones.state_in()[2])
             io.state_out = C.pointer(self.zones.state_out()[2])
-            io.events, io.event_stride = self.zones.events.data_ptr(), self.zones.event_stride
-            io.event_count = self.zones.event_count.data_ptr()
+            io.events, io.event_stride = self.zones._events[self.zones.cur ^ 1].data_ptr(), self.zones.event_stride
+            io.event_count = self.zones._event_count[self.zones.cur ^ 1].data_ptr()
         io.status = self.status.data_ptr()
         if self.use_kalman:
             io.kalman_in = C.pointer(self.tables[self.cur].kalman)
@@ -353,9 +388,9 @@ class StreamBatch:
         fid = self.frame_id if frame_id is None else frame_id
         io = self._io(heads, now, fid)
         if heads_ready is None:
-            io.scan_async, io.heads_ready_event = 0, None
+            io.scan_async, io.heads_ready_event, io.results_alternate = 0, None, 0
         else:
-            io.scan_async = 1
+            io.scan_async, io.results_alternate = 1, 1           # the result buffers alternate with the tables
             io.heads_ready_event = None if heads_ready is True else heads_ready.cuda_event
         if torch.cuda.current_device() == self.device.index:
             rc = self.lib.rtm_post_backbone_step(C.byref(io), C.byref(self.params), torch.cuda.current_stream().cuda_stream)
@@ -377,36 +412,72 @@ class StreamBatch:
         with torch.cuda.device(self.device):
             st = _lib.cuda_stream()
             tin, tout = self.tables[self.cur], self.tables[self.cur ^ 1]
+            res = self._res[self.cur ^ 1]
             want_assign = S == self.det_stride
             opt = _lib.track_options(self.track_thresh, self.match_thresh, self.track_buffer, self.assignment,
                                      tin.kalman if self.use_kalman else None, tout.kalman if self.use_kalman else None)
             _lib.check(self.lib.rtm_track_step_ex(
                 C.byref(tin.struct), C.byref(tout.struct), det_xyxy.data_ptr(), det_conf.data_ptr(),
                 det_cls.data_ptr(), det_count.data_ptr(), S, C.byref(opt),
-                self.det_track_id.data_ptr() if want_assign else None,
-                self.det_kind.data_ptr() if want_assign else None, self.src_row.data_ptr(),
+                res["det_track_id"].data_ptr() if want_assign else None,
+                res["det_kind"].data_ptr() if want_assign else None, self.src_row.data_ptr(),
                 self.status.data_ptr(), st))
             if self.zones is not None:
                 z = self.zones
                 _lib.check(self.lib.rtm_zone_step(
                     C.byref(z.zone_set), C.byref(tout.struct), self.src_row.data_ptr(),
                     C.byref(z.state_in()[2]), C.byref(z.state_out()[2]), float(now), None, int(fid),
-                    z.events.data_ptr(), z.event_stride, z.event_count.data_ptr(),
+                    z._events[z.cur ^ 1].data_ptr(), z.event_stride, z._event_count[z.cur ^ 1].data_ptr(),
                     self.status.data_ptr(), st))
         self._advance()
 
     # -- results -----------------------------------------------------------
     def check_status(self) -> None:
-        _lib.raise_on_status(self.status.cpu().numpy(), "StreamBatch")
+        st = self.status.cpu().numpy()
+        if st.any():
+            self.status.zero_()                       # reported once: later steps start from a clean word
+        _lib.raise_on_status(st, "StreamBatch")
 
     def read_events(self, class_names=None):
         """Per-stream lists of ZoneEvent of the last step (synchronises the device)."""
         if self.zones is None:
             return [[] for _ in range(self.B)]
         self.check_status()
-        ev = self.zones.events.cpu().numpy()
         cnt = self.zones.event_count.cpu().numpy()
+        ev = self.zones.events[:, :max(int(cnt.max()), 1)].cpu().numpy()     # only the filled part of the slabs
         return self.zones.decode_events(ev, cnt, class_names)
+
+    def event_records(self) -> np.ndarray:
+        """The raw 64-byte ``rtm_zone_event`` records of the last step, all streams concatenated in stream
+        order (a NumPy structured array of ``_lib.EVENT_DTYPE``; ``stream`` numbers the batch's streams)."""
+        if self.zones is None:
+            return np.zeros(0, np.dtype(_lib.EVENT_DTYPE))
+        self.check_status()
+        cnt = self.zones.event_count.cpu().numpy()
+        ev = self.zones.events[:, :max(int(cnt.max()), 1)].cpu().numpy()
+        recs = ev.view(np.dtype(_lib.EVENT_DTYPE)).reshape(self.B, -1)
+        return np.concatenate([recs[b, :int(cnt[b])] for b in range(self.B)]) if self.B else recs.reshape(-1)
+
+    def write_events(self, log_path, class_names=None, stream_names=None) -> int:
+        """The event sink of the batch: the last step's events of ALL streams as JSONL, the reference's
+        ``ZoneEvent.to_json()`` line per event (zone_engine.py:44-45), in (stream, track, zone) order, with ONE
+        append for the whole step (the reference opens the file once per event, zone_engine.py:153-155).
+        ``stream_names``: optional per-stream value stored under ``metadata["stream"]`` (the reference's
+        ``metadata`` is ``{}``: omitted when None, so that a single-stream log is byte-identical to the
+        reference's apart from ``timestamp_utc``).  Returns the number of lines written."""
+        from pathlib import Path
+        lines = []
+        for b, evs in enumerate(self.read_events(class_names)):
+            for e in evs:
+                if stream_names is not None:
+                    e.metadata = {"stream": stream_names[b]}
+                lines.append(e.to_json() + "\n")
+        if lines:
+            path = Path(log_path)
+            path.parent.mkdir(parents=True, exist_ok=True)
+            with open(path, "a") as f:
+                f.write("".join(lines))
+        return len(lines)
 
     def read_detections(self):
         """Per-stream dict(xyxy, confidence, class_id, anchor, keep, track_id, kind) of the last step."""
@@ -456,7 +527,11 @@ class StepResult:
         z = self._feeder.batch.zones
         if z is None:
             return [[] for _ in range(self._feeder.batch.B)]
-        return z.decode_events(self._slot["events"].numpy(), self._slot["event_count"].numpy(), class_names)
+        cnt = self._slot["event_count"].numpy()
+        if int(cnt.max()) > self._feeder.event_prefix:
+            raise _lib.RtmError(f"HostFeeder: a stream emitted {int(cnt.max())} events in one step, only the first "
+                                f"{self._feeder.event_prefix} are copied to the host (raise event_prefix)")
+        return z.decode_events(self._slot["events"].numpy(), cnt, class_names)
 
 
 class HostFeeder:
@@ -469,9 +544,11 @@ class HostFeeder:
     (detections with track ids, events, status) come back to pinned host memory.
     """
 
-    def __init__(self, batch: StreamBatch, head_dtype, depth: int = 2) -> None:
+    def __init__(self, batch: StreamBatch, head_dtype, depth: int = 2, event_prefix: int = 64) -> None:
         import torch
         self.batch, self.depth = batch, int(depth)
+        # events copied back per stream and step; a stream that emits more in one step raises (nothing is dropped silently)
+        self.event_prefix = min(int(event_prefix), batch.zones.event_stride) if batch.zones is not None else 1
         self.lib = batch.lib
         B, D, dev = batch.B, batch.det_stride, batch.device
         shapes = [(B, 64 + batch.nc, batch.imgsz[0] // s, batch.imgsz[1] // s) for s in (8, 16, 32)]
@@ -494,7 +571,7 @@ class HostFeeder:
                 stream = torch.cuda.Stream(device=dev)
                 done = torch.cuda.Event()
                 done.record(stream)                          # materialise the cudaEvent_t handle
-                ev_stride = batch.zones.event_stride if batch.zones is not None else 1
+                ev_stride = self.event_prefix
                 self.slots.append(dict(
                     stream=stream, done=done,
                     host_heads=views(pin((total,), head_dtype)),
@@ -547,7 +624,7 @@ class HostFeeder:
         now = time.time() if now is None else now
         fid = b.frame_id if frame_id is None else frame_id
         io = b._io(None, now, fid)
-        io.scan_async, io.heads_ready_event = 0, None          # the copy and the kernels share the slot's stream
+        io.scan_async, io.heads_ready_event, io.results_alternate = 0, None, 0   # the copy and the kernels share the slot's stream
         io.head_p3, io.head_p4, io.head_p5 = (t.data_ptr() for t in slot["dev_heads"])
         io.head_dtype = _lib.dtype_code(slot["dev_heads"][0].dtype)
         h = _lib.StepHostIO()
@@ -557,6 +634,7 @@ class HostFeeder:
         h.host_det_xyxy, h.host_det_conf = slot["det_xyxy"].data_ptr(), slot["det_conf"].data_ptr()
         h.host_det_cls, h.host_det_track_id = slot["det_cls"].data_ptr(), slot["det_track_id"].data_ptr()
         h.host_det_count, h.host_status = slot["det_count"].data_ptr(), slot["status"].data_ptr()
+        h.host_event_stride = self.event_prefix
         h.wait_event = prev["done"].cuda_event if self.k > 0 and self.depth > 1 else None
         h.done_event = slot["done"].cuda_event
         with torch.cuda.device(b.device):

@@ -103,7 +103,10 @@ class _ByteTrackCore:
                 self._src_row.data_ptr(), self._status.data_ptr(), _lib.cuda_stream()))
             self._cur ^= 1
             self._last_n = n
-        _lib.raise_on_status(self._status.cpu().numpy(), "MultiObjectTracker")
+        st = self._status.cpu().numpy()
+        if st.any():
+            self._status.zero_()
+        _lib.raise_on_status(st, "MultiObjectTracker")
         # the reference filters on time_since_update == 0 AFTER ageing every track, so nothing
         # ever qualifies (tracker.py:141, 144-147)
         return []
@@ -131,10 +134,13 @@ class MultiObjectTracker:
             raise ValueError(f"Unknown tracker: {self.algorithm}")
         self._trail_map = defaultdict(list)
         self._trail_maxlen = 30
+        self._frame = 0                    # update() calls so far
+        self._trail_frame = {}             # track id -> frame its trail was last extended in
 
     def update(self, detections) -> list:
         """``detections`` needs ``.xyxy``, ``.confidence``, ``.class_id`` (tracker.py:234-238)."""
         raw = self._core.update(detections.xyxy, detections.confidence, detections.class_id)
+        self._frame += 1
         return self._wrap(raw)
 
     def active_tracks(self) -> list:
@@ -149,9 +155,11 @@ class MultiObjectTracker:
             cx = int((r["xyxy"][0] + r["xyxy"][2]) / 2)
             cy = int((r["xyxy"][1] + r["xyxy"][3]) / 2)
             trail = self._trail_map[tid]
-            trail.append((cx, cy))
-            if len(trail) > self._trail_maxlen:
-                trail.pop(0)
+            if self._trail_frame.get(tid) != self._frame:         # one point per frame, however often the view is read
+                self._trail_frame[tid] = self._frame
+                trail.append((cx, cy))
+                if len(trail) > self._trail_maxlen:
+                    trail.pop(0)
             tracks.append(Track(track_id=tid, xyxy=r["xyxy"], confidence=r["confidence"],
                                 class_id=r["class_id"], age=r["age"],
                                 time_since_update=r["time_since_update"], trail=list(trail)))

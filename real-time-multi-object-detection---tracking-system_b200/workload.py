@@ -1,7 +1,10 @@
 """The benchmark workload of BASELINE.json configs 3 / 4: S synthetic 1080p streams, a cycle of F
 frames of planted YOLOv8 head tensors per stream (8400 anchors x (64 + 80) channels) and 4 zones
-per stream.  Planted cells come from NumPy (seeded per stream, identical wherever they are
-generated); the background noise is drawn with torch on the device that holds the tensors.
+per stream.  Every stream's tensors are a function of its GLOBAL stream id and the frame only:
+planted cells come from NumPy generators seeded per (stream, frame), the background noise from a
+counter-based integer hash evaluated with exact integer arithmetic (the same bits on the CPU and on
+any GPU) - so a stream's head tensor does not depend on how streams are sharded over ranks, nor on
+which arm of the bench generates it ("identical head tensors").
 Used by bench.py (both arms) and by the tests; touches neither the CUDA library nor the oracle.
 """
 
@@ -10,6 +13,22 @@ from __future__ import annotations
 import numpy as np
 
 from . import synth
+
+
+def hashed_noise(stream_ids, frame: int, level: int, numel: int, device):
+    """(len(stream_ids), numel) float32 noise, mean 0, std 1.155 (sum of the four bytes of a 32-bit hash of
+    (stream, frame, level, element), centred and divided by 128): integer arithmetic below 2^63 and an exact
+    conversion, hence bit-identical on the CPU and on any GPU."""
+    import torch
+    idx = torch.arange(numel, dtype=torch.int64, device=device)[None]
+    seed = torch.tensor([(sid * 1_000_003 + frame * 7_919 + level * 104_729 + 12_345) & 0x7FFFFFFF for sid in stream_ids],
+                        dtype=torch.int64, device=device)[:, None]
+    x = (idx * 2_654_435_761 + seed) & 0xFFFFFFFF
+    x = (((x >> 16) ^ x) * 0x45D9F3B) & 0xFFFFFFFF
+    x = (((x >> 16) ^ x) * 0x45D9F3B) & 0xFFFFFFFF
+    x = (x >> 16) ^ x
+    s = (x & 255) + ((x >> 8) & 255) + ((x >> 16) & 255) + (x >> 24)
+    return (s - 510).to(torch.float32) / 128.0
 
 
 class PostBackboneWorkload:
@@ -32,22 +51,21 @@ class PostBackboneWorkload:
 
     def _make_frame(self, f: int):
         import torch
-        boxes, cls, logit, owner = [], [], [], []
-        for s, o in enumerate(self.objects):
+        cells = None
+        for s, (sid, o) in enumerate(zip(self.stream_ids, self.objects)):
             keep = o["present"][f]
-            boxes.append(o["boxes"][f][keep])
-            cls.append(o["cls"][keep])
-            logit.append(o["logit"][f][keep])
-            owner.append(np.full(int(keep.sum()), s, np.int64))
-        rng = np.random.default_rng(77_000 + 131 * self.stream_ids[0] + f)
-        cells = synth.plant_cells(np.concatenate(boxes), np.concatenate(cls), np.concatenate(logit),
-                                  np.concatenate(owner), rng, self.imgsz)
-        gen = torch.Generator(device=self.device)
-        gen.manual_seed(5_000_011 * (self.stream_ids[0] + 1) + f)
+            n = int(keep.sum())
+            rng = np.random.default_rng([77, sid, f])                      # per (global stream, frame)
+            c = synth.plant_cells(o["boxes"][f][keep], o["cls"][keep], o["logit"][f][keep],
+                                  np.full(n, s, np.int64), rng, self.imgsz)
+            cells = c if cells is None else [{k: np.concatenate([a[k], b[k]]) for k in a} for a, b in zip(cells, c)]
         out = []
-        for (h, w), c in zip(synth.head_shapes(self.imgsz), cells):
-            t = torch.randn((self.S, synth.NUM_OUT, h, w), generator=gen, device=self.device, dtype=torch.float32)
-            t[:, 4 * synth.REG_MAX:] -= 6.0                               # background class logits ~ N(-6, 1)
+        for level, ((h, w), c) in enumerate(zip(synth.head_shapes(self.imgsz), cells)):
+            t = torch.empty((self.S, synth.NUM_OUT, h, w), device=self.device, dtype=torch.float32)
+            for s0 in range(0, self.S, 16):
+                ids = self.stream_ids[s0:s0 + 16]
+                t[s0:s0 + len(ids)] = hashed_noise(ids, f, level, synth.NUM_OUT * h * w, self.device).view(len(ids), synth.NUM_OUT, h, w)
+            t[:, 4 * synth.REG_MAX:] -= 6.0                               # background class logits ~ (-6, 1.15)
             synth.scatter_cells(t, c)
             out.append(t.to(self.dtype).contiguous())
         return out

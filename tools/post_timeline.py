@@ -24,6 +24,7 @@ if "--build" in sys.argv:
     sys.exit(0)
 
 os.environ["RTM_LIB_PATH"] = TL_LIB
+os.environ["RTM_STEP_FUSED"] = "0"      # the stage stamps are indexed by blockIdx = stream: the two-launch post kernel
 import ctypes as C
 import numpy as np
 import torch
