@@ -577,15 +577,19 @@ def parity_leg(pkg, wl, new_batch, args, rank, world, my_streams, total_streams,
     return out
 
 
-def e2e_bench(pkg, wl, sb, f0, K, W, total_streams, world, dev):
-    """Same metric through rtm_post_backbone_step_host: pinned host heads -> H2D -> kernels -> D2H."""
+def e2e_bench(pkg, wl, sb, f0, K, W, total_streams, world, dev, pinned_frames=4):
+    """Same metric through rtm_post_backbone_step_host: pinned host heads -> H2D -> kernel -> D2H.  The step is bound by
+    the host -> device copy of its inputs, so the bare copy ceiling of the same buffers is measured in the same run,
+    all ranks copying at once like they do in the timed region (`h2d_ceiling_gbs`)."""
     import torch
     import torch.distributed as dist
     feeder = pkg.HostFeeder(sb, wl.dtype)
+    n_pin = min(pinned_frames, wl.F)
+    order = list(range(n_pin)) + list(range(n_pin - 2, 0, -1))     # forward, then back: every step continues the last
     pinned = []
-    for frame in wl.heads:                                   # every frame of the cycle in page-locked host memory
+    for f in range(n_pin):                                    # frames of the cycle in page-locked host memory
         host = feeder.alloc_pinned_heads()
-        for dst, src in zip(host, frame):
+        for dst, src in zip(host, wl.heads[f]):
             dst.copy_(src)
         pinned.append(host)
     torch.cuda.synchronize(dev)
@@ -593,12 +597,18 @@ def e2e_bench(pkg, wl, sb, f0, K, W, total_streams, world, dev):
 
     def go(first, n):
         for f in range(first, first + n):
-            res = feeder.step_pinned(pinned[f % wl.F], now=T0 + f / FPS, frame_id=f)
+            res = feeder.step_pinned(pinned[order[f % len(order)]], now=T0 + f / FPS, frame_id=f)
             results.append(res)
             if len(results) > 2:
                 results.pop(0).wait()                     # consume the results of step k-2 on the host
         while results:
             results.pop(0).wait()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     go(f0, W)
     if world > 1:
@@ -607,13 +617,34 @@ def e2e_bench(pkg, wl, sb, f0, K, W, total_streams, world, dev):
     t0 = time.perf_counter()
     go(f0 + W, K)
     torch.cuda.synchronize(dev)
-    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    dt = max_over_ranks(time.perf_counter() - t0)
+    # the bare copies: K times the same pinned buffers into the same device buffers, nothing else
+    dev_heads = feeder.slots[0]["dev_heads"]
+    copy_stream = torch.cuda.Stream(device=dev)
+    def copies(n):
+        with torch.cuda.stream(copy_stream):
+            for i in range(n):
+                host = pinned[i % n_pin]
+                if dev_heads[0]._base is not None and host[0]._base is not None:   # the three levels are one buffer on both sides
+                    dev_heads[0]._base.copy_(host[0]._base, non_blocking=True)
+                else:
+                    for d, h in zip(dev_heads, host):
+                        d.copy_(h, non_blocking=True)
+        copy_stream.synchronize()
+    copies(2)
     if world > 1:
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    dt = float(dt.item())
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    copies(K)
+    dc = max_over_ranks(time.perf_counter() - t0)
+    gbs, ceil_gbs = feeder.h2d_bytes * K / dt / 1e9, feeder.h2d_bytes * K / dc / 1e9
     return {"value": total_streams * K / dt, "unit": UNIT, "h2d_bytes_per_step": feeder.h2d_bytes,
             "d2h_bytes_per_step": feeder.d2h_bytes, "ms_per_step": 1e3 * dt / K,
-            "h2d_gbs": feeder.h2d_bytes * K / dt / 1e9,
+            "h2d_gbs": gbs, "h2d_ceiling_gbs": ceil_gbs, "frac_of_copy_ceiling": gbs / ceil_gbs,
+            "ceiling_note": "bare cudaMemcpyAsync of the same pinned head buffers, same count, every rank at once (max over ranks): "
+                            "what the host memory system and the PCIe links of this box give the run",
+            "pinned_frames": n_pin,
             "api": "HostFeeder.step_pinned -> rtm_post_backbone_step_host (2 CUDA streams, H2D of step k+1 overlaps step k)"}
 
 
@@ -639,15 +670,17 @@ def modes_bench(pkg, wl, dev, S, F, steps=100):
     return out
 
 
-def dense_crowd_bench(pkg, dev, streams=128, objects=1000, zones=16, distinct=4, frames=8, steps=48):
+def dense_crowd_bench(pkg, dev, hbm_peak, streams=128, objects=1000, zones=16, distinct=8, frames=16, steps=48):
     """BASELINE.json configs[4] as a side measurement: 128 streams x 1000 scripted objects (MOT20-like
     motion) x 16 zone polygons (K in 4..12), tracker + zones only (the detector cannot emit 1000 boxes:
     max_det = 100).  `distinct` different streams are generated and repeated to fill the batch (streams
     are independent, so repetition changes nothing about the work); the clip runs forward then back.
-    The first frames of one stream are checked against the oracle."""
+    Every distinct stream is checked against the oracle on every frame of the clip; the two kernels are
+    timed alone as well and held against what bounds them (algorithmic bytes; the pair tests)."""
     import numpy as np
     import torch
     from oracle import tracker_ref, zone_ref
+    from rtmodt_b200 import _lib
     slots = 1024
     xyxy, conf, cls, count = pkg.synth.scripted_batch(distinct, frames, slots, seed=900, **pkg.synth.dense_crowd_kwargs(objects))
     rep = streams // distinct
@@ -659,22 +692,30 @@ def dense_crowd_bench(pkg, dev, streams=128, objects=1000, zones=16, distinct=4,
     def fresh():
         return pkg.StreamBatch(streams, zcfg, src_hw=(1080, 1920), max_det=slots, max_tracks=4096, max_events=4096, device=dev)
 
-    # parity: stream 0, first frames, against the oracle
+    # parity: every distinct stream, every frame of the clip, against the oracle (tracker pinned to the reference)
     sb = fresh()
-    trk, zon = tracker_ref.TrackerOracle(), zone_ref.ZoneOracle(zcfg[0])
-    ok = True
-    for f in range(3):
+    trk = [tracker_ref.TrackerOracle() for _ in range(distinct)]
+    zon = [zone_ref.ZoneOracle(zcfg[b]) for b in range(distinct)]
+    bad = checked = 0
+    for f in range(frames):
         now = T0 + f / FPS
         sb.track_only(d_xyxy[f], d_conf[f], d_cls[f], d_count[f], now=now, frame_id=f)
-        n = int(count[f, 0])
-        trk.step(xyxy[f, 0, :n], conf[f, 0, :n], cls[f, 0, :n])
         tracks, next_id = sb.read_tracks()
-        ok &= [t["track_id"] for t in tracks[0]] == trk.track_id.tolist() and int(next_id[0]) == trk.next_id
-        act = trk.active_rows()
-        exp = zon.process(zip(trk.track_id[act], trk.xyxy[act], trk.cls[act]), f, now)
-        got = sb.read_events()[0]
-        ok &= [(e.track_id, e.zone_name, e.centroid) for e in got] == [(e.track_id, e.zone_name, e.centroid) for e in exp]
+        got = sb.read_events()
+        for b in range(distinct):
+            n = int(count[f, b])
+            trk[b].step(xyxy[f, b, :n], conf[f, b, :n], cls[f, b, :n])
+            ok = [t["track_id"] for t in tracks[b]] == trk[b].track_id.tolist() and int(next_id[b]) == trk[b].next_id
+            ok = ok and [t["time_since_update"] for t in tracks[b]] == trk[b].tsu.tolist()
+            ok = ok and np.array_equal(np.asarray([t["xyxy"] for t in tracks[b]], np.float32).reshape(-1, 4), trk[b].xyxy)
+            act = trk[b].active_rows()
+            exp = zon[b].process(zip(trk[b].track_id[act], trk[b].xyxy[act], trk[b].cls[act]), f, now)
+            ok = ok and [(e.track_id, e.zone_name, e.centroid, e.dwell_time_sec) for e in got[b]] == \
+                [(e.track_id, e.zone_name, e.centroid, e.dwell_time_sec) for e in exp]
+            bad += int(not ok)
+            checked += 1
     sb.check_status()
+    sb.close()
     # timing
     sb = fresh()
     k = 0
@@ -684,7 +725,7 @@ def dense_crowd_bench(pkg, dev, streams=128, objects=1000, zones=16, distinct=4,
             f = order[k % len(order)]
             sb.track_only(d_xyxy[f], d_conf[f], d_cls[f], d_count[f], now=T0 + k / FPS, frame_id=k)
             k += 1
-    go(8)
+    go(len(order))
     torch.cuda.synchronize(dev)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
@@ -692,11 +733,74 @@ def dense_crowd_bench(pkg, dev, streams=128, objects=1000, zones=16, distinct=4,
     b.record()
     b.synchronize()
     ms = a.elapsed_time(b) / steps
+    sb.lib.rtm_profile_enable(1)
+    _lib.profile_read()
+    go(steps)
+    torch.cuda.synchronize(dev)
+    prof = _lib.profile_read()
+    sb.lib.rtm_profile_enable(0)
     sb.check_status()
     tracks, _ = sb.read_tracks()
-    return {"config": f"BASELINE.json configs[4]: {streams} streams x {objects} scripted objects, {zones} zones (K 4..12), tracker + zones "
-                      f"({distinct} distinct streams repeated)", "frames_per_s": streams / (ms * 1e-3), "ms_per_step": ms,
-            "live_tracks_per_stream": float(np.mean([len(t) for t in tracks])), "parity_ok": bool(ok), "steps": steps}
+    T = float(np.mean([len(t) for t in tracks]))
+    N = float(count.mean())
+    kern = {n: 1e3 * v[0] / v[1] for n, v in prof.items()}
+    # track step 36 (T_in + T_out) + 24 N bytes, zone step 24 T + 8 Z K + 2 * 16 T Z bytes per stream-frame
+    alg_track = streams * (36 * 2 * T + 24 * N)
+    alg_zone = streams * (24 * T + 8 * zones * 8 + 32 * T * zones)
+    pair_tests = streams * T * N                           # IoU pairs of stage 1 (stage 2 adds the unmatched rest)
+    out = {"config": f"BASELINE.json configs[4]: {streams} streams x {objects} scripted objects, {zones} zones (K 4..12), tracker + zones "
+                     f"({distinct} distinct streams repeated)", "frames_per_s": streams / (ms * 1e-3), "ms_per_step": ms,
+           "live_tracks_per_stream": T, "detections_per_stream": N,
+           "parity_ok": bad == 0, "parity": {"stream_frames_checked": checked, "mismatches": bad, "frames": frames, "streams": distinct},
+           "steps": steps, "kernels_alone_us": kern,
+           "roofline": {"bound": "hbm (algorithmic bytes, SURVEY 8d) - the kernels are nowhere near it: the step is pair tests and per-row "
+                                 "serial logic, not bytes",
+                        "algorithmic_bytes_per_step": alg_track + alg_zone,
+                        "achieved_gbs": (alg_track + alg_zone) / (ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                        "frac": (alg_track + alg_zone) / (ms * 1e-3) / 1e9 / hbm_peak,
+                        "iou_pair_tests_per_step": pair_tests,
+                        "pair_tests_per_s": pair_tests / (kern.get("track", ms * 1e3) * 1e-6)}}
+    sb.close()
+    return out
+
+
+def single_stream_bench(pkg, dev, steps=300):
+    """BASELINE.json configs[1]: ONE stream, batch 1 - the YOLOv8s stand-in's conv forward on a 640 x 640 bf16 frame
+    (random init, not a parity subject: its heads score nothing above 0.35), then decode + NMS + tracker + zones on a
+    planted head tensor of the same shape.  What the reference's loop does per frame
+    (tools/run_pipeline.py:131-146), one frame at a time, latency of each part by CUDA events."""
+    import numpy as np
+    import torch
+    from rtmodt_b200.detection.yolov8s import YOLOv8s
+    from rtmodt_b200.workload import PostBackboneWorkload
+    torch.manual_seed(0)
+    net = YOLOv8s().to(dev).to(torch.bfloat16).eval()
+    frame = torch.rand(1, 3, 640, 640, device=dev).to(torch.bfloat16)
+    wl = PostBackboneWorkload(1, 8, first_stream=0, device=dev, dtype=torch.bfloat16)
+    sb = pkg.StreamBatch(1, wl.zones, src_hw=(1080, 1920), classes=WANTED, max_tracks=512, device=dev)
+    t_net, t_post = [], []
+    with torch.no_grad():
+        for i in range(20 + steps):
+            a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            a.record()
+            heads = net(frame)
+            b.record()
+            sb.step(wl.heads[i % 8], now=T0 + i / FPS, frame_id=i)
+            c.record()
+            c.synchronize()
+            if i >= 20:
+                t_net.append(a.elapsed_time(b))
+                t_post.append(b.elapsed_time(c))
+    sb.check_status()
+    dets = int(sb.det_count.sum().item())
+    sb.close()
+    assert [tuple(h.shape) for h in heads] == [(1, 144, 80, 80), (1, 144, 40, 40), (1, 144, 20, 20)]
+    pct = lambda v, q: float(np.percentile(np.asarray(v), q))
+    return {"config": "BASELINE.json configs[1]: YOLOv8s stand-in (random init) 640x640 batch 1, one stream: conv forward (PyTorch, "
+                      "not timed against anything), then decode + NMS + ByteTrack + 4 zones on a planted head tensor",
+            "post_backbone_ms": {"p50": pct(t_post, 50), "p99": pct(t_post, 99)},
+            "conv_forward_ms": {"p50": pct(t_net, 50), "p99": pct(t_net, 99)},
+            "frames_per_s_post_backbone": 1e3 / pct(t_post, 50), "steps": steps, "detections_last_frame": dets}
 
 
 def letterbox_bench(pkg, lib, dev, S, hbm_peak, iters=20):

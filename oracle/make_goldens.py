@@ -94,7 +94,12 @@ def run_reference_clip(ref_tracker, ref_zones, clip, zone_cfgs, fps=30.0, tracke
             ev_rows.append((f, e.track_id, zi, e.class_id, e.centroid[0], e.centroid[1],
                             e.dwell_time_sec, *e.bbox_xyxy))
     ev = np.array(ev_rows, np.float64).reshape(-1, 11)
+    # the event sink's wire format: the very lines ZoneEventEngine._write appended (zone_engine.py:153-157);
+    # `timestamp_utc` in them is the wall clock of this run (time.gmtime), everything else is deterministic
+    log = os.path.join(tmp, "events.jsonl")
+    jsonl = open(log, "rb").read() if os.path.exists(log) else b""
     out = pack_states(states)
+    out["jsonl"] = np.frombuffer(jsonl, np.uint8).copy()
     out.update(pack_clip(clip))
     out.update(next_id=np.array(next_ids, np.int64), returned=np.array(returned, np.int64),
                events=ev, fps=np.float64(fps), t0=np.float64(1_700_000_000.0))

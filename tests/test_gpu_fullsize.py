@@ -1,5 +1,6 @@
-"""BASELINE.json configs[2] at its full size (64 streams x 8400 anchors x 80 classes, 4 zones) through
-size-independent properties - the oracle chain would need minutes for this many stream-frames:
+"""BASELINE.json configs[2] at its full size (64 streams x 8400 anchors x 80 classes, 4 zones): every stream and
+every frame of the bench's 16-frame cycle against the oracle chain (a few seconds of CPU), in both step modes, and
+size-independent properties on top:
 
 * every stream's detections are what ultralytics' post-process can emit: at most max_det, score order,
   above the confidence threshold, wanted classes only, inside the source frame, `keep` indices strictly
@@ -123,3 +124,23 @@ def test_results_do_not_depend_on_the_batching(pkg, full, heads_ready):
             for th, tw in zip(tracks_h[b], tracks_w[off + b]):
                 assert th["track_id"] == tw["track_id"] and th["age"] == tw["age"]
                 np.testing.assert_array_equal(th["xyxy"], tw["xyxy"])
+
+
+@pytest.mark.parametrize("heads_ready", [None, True])
+def test_every_stream_and_frame_matches_the_oracle_chain(pkg, heads_ready):
+    """All 64 streams x 16 frames of configs[2] (the bench workload itself): detections (keep sets, boxes within
+    1e-4), per-detection track ids, whole track tables, next ids and event lists, frame by frame."""
+    import torch
+    from oracle import chain
+    from rtmodt_b200.workload import PostBackboneWorkload
+    dev = torch.device("cuda", 0)
+    frames = 16
+    wl = PostBackboneWorkload(S, frames, first_stream=0, device=dev, dtype=torch.bfloat16)
+    sb = pkg.StreamBatch(S, wl.zones, src_hw=(SRC_H, SRC_W), classes=WANTED, max_tracks=512, device=dev)
+    res = chain.run_chain_parity(sb, lambda f: wl.heads[f], lambda f: wl.host_frame(f), wl.zones, frames,
+                                 src_hw=(SRC_H, SRC_W), classes=WANTED, heads_ready=heads_ready)
+    sb.close()
+    assert res["streams"] == S and res["frames"] == frames
+    assert res["detections_checked"] > S * frames * 10 and res["events_checked"] > 0
+    bad = {k: res[k] for k in ("nms_index_flips", "box_mismatch", "track_id_mismatch", "track_table_mismatch", "event_mismatch")}
+    assert res["ok"], bad

@@ -237,3 +237,88 @@ def test_async_scan_steps_equal_synchronised_steps(pkg, mode):
         assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and np.array_equal(got[4], want[4])
         for a, b in zip(got[2] + got[3] + got[5], want[2] + want[3] + want[5]):
             np.testing.assert_array_equal(a, b)
+
+
+def test_heads_produced_right_before_the_step_are_seen_whole(pkg):
+    """Default mode: the head tensors are ordered on the current stream like any other input - also when the kernel
+    in front of the step is their producer (a conv stack here, plus an elementwise tail), with no synchronisation in
+    between.  (The scan used to be a programmatic dependent launch on the caller's stream, which has no ordering
+    against a producer that releases its dependents early: ADVICE r1.)"""
+    import torch
+    B, F = 3, 6
+    dev = torch.device("cuda", 0)
+    frames = moving_heads(pkg, B, F, seed=21)
+    convs = [torch.nn.Conv2d(144, 144, 1, bias=False).to(dev).to(torch.bfloat16) for _ in range(3)]
+    for c in convs:
+        with torch.no_grad():
+            c.weight.copy_(torch.eye(144).reshape(144, 144, 1, 1))         # identity: the producer is real, the values known
+    zones = [pkg.synth.make_zones(seed=b, num_zones=3, width=1920, height=1080, dwell_time_sec=0.0, cooldown_sec=0.1) for b in range(B)]
+
+    def run(sync_between):
+        sb = pkg.StreamBatch(B, zones, src_hw=(1080, 1920), classes=WANTED, max_tracks=256)
+        out = []
+        for f, heads in enumerate(frames):
+            src = [torch.from_numpy(h).to(torch.bfloat16).to(dev) for h in heads]
+            torch.cuda.synchronize()
+            with torch.no_grad():
+                produced = [(c(s) * 1.0).contiguous() for c, s in zip(convs, src)]   # enqueued right in front of the step
+            if sync_between:
+                torch.cuda.synchronize()
+            sb.step(produced, now=9.0 + f / 30.0, frame_id=f)
+            torch.cuda.synchronize()
+            out.append((sb.read_detections(), sb.read_tracks()[1].tolist(), [len(e) for e in sb.read_events()]))
+        sb.close()
+        return out
+
+    ref, got = run(True), run(False)
+    for (d0, n0, e0), (d1, n1, e1) in zip(ref, got):
+        assert n0 == n1 and e0 == e1
+        for a, b in zip(d0, d1):
+            for k in ("xyxy", "confidence", "class_id", "anchor", "track_id"):
+                np.testing.assert_array_equal(a[k], b[k])
+    assert sum(len(d["confidence"]) for d in ref[-1][0]) > 10
+
+
+def test_recycled_workspace_addresses_start_afresh(pkg):
+    """Batches are created and dropped in a loop: the allocator hands the workspace address out again, and the library's
+    per-workspace bookkeeping (slot, counters, its own stream) must not survive into the next owner - in both step modes."""
+    import torch
+    B, F = 4, 5
+    frames = moving_heads(pkg, B, F, seed=8)
+    dev = torch.device("cuda", 0)
+    heads = [[torch.from_numpy(h).to(torch.bfloat16).to(dev).contiguous() for h in fr] for fr in frames]
+    seen, ptrs = [], set()
+    for rep in range(6):
+        sb = pkg.StreamBatch(B, None, src_hw=(1080, 1920), classes=WANTED, max_tracks=128)
+        ptrs.add(sb.workspace.data_ptr())
+        for f in range(F + rep % 3):                                 # a different number of steps each time: slots differ
+            sb.step(heads[f % F], now=1.0 + f, frame_id=f, heads_ready=True if rep % 2 else None)
+        torch.cuda.synchronize()
+        if rep % 3 == 0:
+            seen.append((sb.read_tracks()[1].tolist(), [d["anchor"].tolist() for d in sb.read_detections()]))
+        sb.close()
+        del sb
+    assert seen[0] == seen[1]
+
+
+def test_host_feeder_copies_event_heads_only_and_says_so(pkg):
+    """The host-fed step copies the first `event_prefix` events of every stream back; a stream that emits more raises
+    instead of dropping them, and the device buffers are sized for a whole crowd firing at once."""
+    import torch
+    B, n_obj = 2, 12
+    frames = moving_heads(pkg, B, 3, seed=3, n_obj=n_obj)
+    everywhere = [[dict(name=f"z{k}", polygon=[[0, 0], [1920, 0], [1920, 1080], [0, 1080]], dwell_time_sec=0.0, cooldown_sec=0.0)
+                   for k in range(3)] for _ in range(B)]
+    sb = pkg.StreamBatch(B, everywhere, src_hw=(1080, 1920), classes=WANTED, max_tracks=64)
+    assert sb.zones.event_stride == 64 * 3
+    feeder = pkg.HostFeeder(sb, torch.bfloat16, event_prefix=8)
+    res = None
+    for f, heads in enumerate(frames):
+        res = feeder.step([torch.from_numpy(h).to(torch.bfloat16) for h in heads], now=5.0 + f, frame_id=f)
+    res.wait()
+    with pytest.raises(pkg.RtmError):
+        res.events()                                               # 3 zones x ~12 tracks > 8 per stream
+    assert len(sb.read_events()[0]) > 8                            # all of them are on the device
+    feeder = pkg.HostFeeder(sb, torch.bfloat16, event_prefix=64)
+    res = feeder.step([torch.from_numpy(h).to(torch.bfloat16) for h in frames[-1]], now=9.0, frame_id=9)
+    assert [len(e) for e in res.events()] == [len(e) for e in sb.read_events()]

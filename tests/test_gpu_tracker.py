@@ -212,3 +212,15 @@ def test_tracker_modes_soak(pkg, seed, assignment, kalman):
     run_batch_against_oracle(pkg, B=3, F=25, slots=256, clip_kw=kw, max_tracks=2048, seed=700 + seed,
                              track_kw=dict(assignment=assignment, use_kalman=kalman),
                              oracle_kw=dict(assign=assign, use_kalman=kalman))
+
+
+def test_active_tracks_is_a_view_not_a_step(pkg):
+    """Reading the active view twice in a frame leaves the trails alone (one point per update, tracker.py:241-258)."""
+    import types
+    trk = pkg.MultiObjectTracker()
+    for f in range(4):
+        box = np.array([[10 + f, 10, 60 + f, 80]], np.float32)
+        trk.update(types.SimpleNamespace(xyxy=box, confidence=np.array([0.9], np.float32), class_id=np.array([2], np.int32)))
+        a = trk.active_tracks()
+        b = trk.active_tracks()
+        assert len(a) == len(b) == 1 and a[0].trail == b[0].trail and len(a[0].trail) == f + 1

@@ -124,3 +124,82 @@ def test_reference_dwell_cooldown_schedule(pkg, tmp_path):
         for e in eng.process(trk, f):
             fired.append((f, e.dwell_time_sec))
     assert fired == [(60, 2.0), (360, 12.0), (660, 22.0)]
+
+
+def strip_stamp(line: str) -> str:
+    import re
+    return re.sub(r'"timestamp_utc": "[^"]*"', '"timestamp_utc": ""', line)
+
+
+@pytest.mark.parametrize("name", ["cfg1_clip.npz", "crowd_clip.npz", "churn_clip.npz"])
+def test_event_sink_lines_are_the_references_bytes(pkg, name, tmp_path):
+    """The event sink (zone_engine.py:44-45, 153-157): StreamBatch.write_events appends, once per step, the lines
+    the UNMODIFIED reference wrote to its own events.jsonl for the same clip (captured by make_goldens.py) -
+    byte for byte, apart from `timestamp_utc`, which is the wall clock of the run that wrote them."""
+    import torch
+    g = load_golden(name)
+    zones = zones_for(name)
+    want = bytes(g["jsonl"]).decode().splitlines()
+    assert len(want) == len(g["events"]) > 0
+    slots = 128
+    sb = pkg.StreamBatch(1, [zones], max_det=slots, max_tracks=512, src_hw=(720, 1280), **tracker_params(g))
+    log = tmp_path / "logs" / "events.jsonl"
+    written = 0
+    for f, (xyxy, conf, cls) in enumerate(golden_clip(g)):
+        n = len(conf)
+        bx = np.zeros((1, slots, 4), np.float32); bx[0, :n] = xyxy
+        cf = np.zeros((1, slots), np.float32); cf[0, :n] = conf
+        cl = np.zeros((1, slots), np.int32); cl[0, :n] = cls
+        t = lambda a: torch.from_numpy(a).to(sb.device)
+        sb.track_only(t(bx), t(cf), t(cl), t(np.array([n], np.int32)), now=float(g["t0"]) + f / float(g["fps"]), frame_id=f)
+        written += sb.write_events(log)
+    got = open(log).read().splitlines()
+    assert written == len(got) == len(want)
+    assert [strip_stamp(l) for l in got] == [strip_stamp(l) for l in want]
+
+
+def test_facade_event_log_is_the_references_bytes(pkg, tmp_path):
+    """The same for the single-stream drop-in: ZoneEventEngine.process fed the reference's own active-track
+    lists writes the reference's lines."""
+    g = load_golden("cfg1_clip.npz")
+    zones = zones_for("cfg1_clip.npz")
+    want = bytes(g["jsonl"]).decode().splitlines()
+    clock = {"t": 0.0}
+    eng = pkg.ZoneEventEngine(zones, log_path=str(tmp_path / "events.jsonl"), clock=lambda: clock["t"])
+    from conftest import golden_state
+    for f in range(len(g["next_id"])):
+        st = golden_state(g, f)
+        act = np.flatnonzero(st["tsu"] == 1)
+        clock["t"] = float(g["t0"]) + f / float(g["fps"])
+        eng.process([types.SimpleNamespace(track_id=int(st["track_id"][r]), xyxy=st["xyxy"][r], class_id=int(st["cls"][r])) for r in act], f)
+    got = open(tmp_path / "events.jsonl").read().splitlines()
+    assert [strip_stamp(l) for l in got] == [strip_stamp(l) for l in want]
+
+
+def test_facade_does_work_proportional_to_the_call_and_handles_repeated_ids(pkg, tmp_path):
+    """Thousands of ids come and go: the device table stays as small as the largest call (the reference keeps dicts;
+    so does the facade).  An id passed twice in one call is evaluated one after the other, as the reference's loop does."""
+    rng = np.random.default_rng(5)
+    zones = pkg.synth.make_zones(seed=2, num_zones=5, width=640, height=480, kmin=3, kmax=8, dwell_time_sec=0.1, cooldown_sec=0.3)
+    clock = {"t": 10.0}
+    eng = pkg.ZoneEventEngine(zones, log_path=str(tmp_path / "ev.jsonl"), clock=lambda: clock["t"], initial_rows=8)
+    orc = zone_ref.ZoneOracle(zones)
+    total = 0
+    for f in range(150):
+        clock["t"] = 10.0 + f * 0.05
+        base = 1 + 20 * (f // 10)                                   # the id range moves on: 300+ ids over the run
+        ids = base + rng.permutation(30)[: int(rng.integers(1, 25))]
+        if f % 7 == 3:
+            ids = np.concatenate([ids, ids[:2]])                    # the same ids again, later in the same call
+        tracks = []
+        for k, i in enumerate(ids):
+            c = np.array([(37 * int(i) + 3 * f + 11 * k) % 640, (53 * int(i) + 2 * f) % 480], np.float32)
+            tracks.append(types.SimpleNamespace(track_id=int(i), xyxy=np.array([c[0] - 6, c[1] - 8, c[0] + 6, c[1] + 8], np.float32),
+                                                class_id=int(i) % 3))
+        got = eng.process(tracks, f)
+        exp = orc.process([(t.track_id, t.xyxy, t.class_id) for t in tracks], f, clock["t"])
+        assert [(e.track_id, e.zone_name, e.centroid, e.dwell_time_sec, e.frame_id) for e in got] == \
+               [(e.track_id, e.zone_name, e.centroid, e.dwell_time_sec, e.frame_id) for e in exp]
+        total += len(got)
+    assert total > 30
+    assert eng._tables.capacity <= 32 and len(eng._cooldown) > 40     # state on the host, a small table on the device

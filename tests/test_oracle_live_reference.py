@@ -76,3 +76,29 @@ def test_oracle_reproduces_the_live_reference(ref, seed):
             rows.append((f, e.track_id, e.zone_index, e.class_id, *e.centroid, e.dwell_time_sec, *e.bbox_xyxy))
     np.testing.assert_array_equal(np.array(rows, np.float64).reshape(-1, 11), g["events"])
     assert g["returned"].sum() == 0
+
+
+def test_oracle_reproduces_the_live_reference_on_a_dense_crowd(ref):
+    """BASELINE.json configs[4] scale: 1000 objects per frame (MOT20-like), 16 zones - the reference's own
+    `_ByteTrackCore.update` at T = N = 1000 (tracker.py:58-141) and its zone engine, live, against the oracle."""
+    mg, (ref_tracker, ref_zones) = ref
+    synth = importlib.import_module("rtmodt_b200").synth
+    clip = synth.scripted_clip(seed=900, num_frames=12, **synth.dense_crowd_kwargs(1000))
+    zones = synth.make_zones(seed=0, num_zones=16, width=1920, height=1080, kmin=4, kmax=12, dwell_time_sec=0.1, cooldown_sec=0.2)
+    g = mg.run_reference_clip(ref_tracker, ref_zones, clip, zones, tracker_kwargs=dict(bytetrack=dict(mot20=False)))
+    trk, eng = tracker_ref.TrackerOracle(), zone_ref.ZoneOracle(zones)
+    rows = []
+    for f, (xyxy, conf, cls) in enumerate(golden_clip(g)):
+        trk.step(xyxy, conf, cls)
+        want = golden_state(g, f)
+        assert trk.next_id == g["next_id"][f] and len(trk) >= 700
+        np.testing.assert_array_equal(trk.track_id, want["track_id"])
+        np.testing.assert_array_equal(trk.xyxy, want["xyxy"])
+        np.testing.assert_array_equal(trk.age, want["age"])
+        np.testing.assert_array_equal(trk.tsu, want["tsu"])
+        act = trk.active_rows()
+        now = float(g["t0"]) + f / float(g["fps"])
+        for e in eng.process(zip(trk.track_id[act], trk.xyxy[act], trk.cls[act]), f, now):
+            rows.append((f, e.track_id, e.zone_index, e.class_id, *e.centroid, e.dwell_time_sec, *e.bbox_xyxy))
+    assert len(rows) > 100
+    np.testing.assert_array_equal(np.array(rows, np.float64).reshape(-1, 11), g["events"])

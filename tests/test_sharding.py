@@ -78,3 +78,50 @@ def test_workload_is_identical_wherever_a_stream_is_generated(pkg):
     assert whole.zones[2] == part.zones[0]
     for k in ("boxes", "cls", "logit", "present"):
         np.testing.assert_array_equal(whole.objects[2][k], part.objects[0][k])
+
+
+def _record_worker(rank, world, port, total_streams, out):
+    sys.path.insert(0, ROOT)
+    import numpy as np
+    import torch.distributed as dist
+    import importlib
+    pkg = importlib.import_module("rtmodt_b200")
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine = pkg.sharding.shard_streams(total_streams, world, rank)
+    # stream s (global) emits s % 3 events; a rank numbers its streams from 0
+    rec = np.zeros(sum(s % 3 for s in mine), np.dtype(pkg._lib.EVENT_DTYPE))
+    k = 0
+    for local, s in enumerate(mine):
+        for e in range(s % 3):
+            rec[k]["stream"], rec[k]["track_id"], rec[k]["zone"], rec[k]["dwell"] = local, 100 * s + e, e, 0.25 * s
+            rec[k]["xyxy"] = (s, e, s + 1, e + 1)
+            k += 1
+    totals, gathered = pkg.sharding.reduce_summary([len(mine), len(rec)], rec, first_stream=mine.start)
+    out.put((rank, totals, gathered.tobytes()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_event_records_are_gathered_over_gloo_world_size_2(pkg):
+    """the padded 64-byte event records of every rank, in global stream order on every rank."""
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    total = 9                                                         # 5 + 4 streams, different record counts per rank
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_record_worker, args=(r, 2, port, total, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    for rank, totals, raw in res:
+        rec = np.frombuffer(raw, np.dtype(pkg._lib.EVENT_DTYPE))
+        assert totals == [total, sum(s % 3 for s in range(total))]
+        assert rec["stream"].tolist() == [s for s in range(total) for _ in range(s % 3)]      # global ids, stream order
+        assert rec["track_id"].tolist() == [100 * s + e for s in range(total) for e in range(s % 3)]
+        assert rec["xyxy"][:, 2].tolist() == [s + 1 for s in range(total) for _ in range(s % 3)]
