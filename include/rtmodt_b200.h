@@ -384,6 +384,23 @@ int rtm_post_backbone_step_host(const rtm_step_io* io, const rtm_step_host_io* h
                                 const rtm_nms_params* params, rtm_cuda_stream stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Checkpoint / resume of a batch's state (the reference keeps the same state in the Python
+ * lists and dicts of _ByteTrackCore and ZoneEventEngine and has no way to save it): the track table with its
+ * counters, the zone dwell / cooldown state and the Kalman state of all B streams, packed into ONE host blob
+ * (a 64-byte header that records the shapes, then the arrays).  zone_state / kalman may be NULL (not stored;
+ * num_columns is then ignored).  Both calls enqueue their copies on `stream` and synchronise it before they
+ * return - they are not on the per-frame path.  rtm_state_import refuses a blob whose header does not match
+ * the tables it is given.
+ * ---------------------------------------------------------------------------------------- */
+size_t rtm_state_bytes(int32_t num_streams, int32_t capacity, int32_t num_columns, int32_t with_zone_state,
+                       int32_t with_kalman);
+int rtm_state_export(const rtm_track_table* table, const rtm_zone_state* zone_state, int32_t num_columns,
+                     const rtm_kalman_state* kalman, void* host_blob, size_t blob_bytes, rtm_cuda_stream stream);
+int rtm_state_import(const rtm_track_table* table, const rtm_zone_state* zone_state, int32_t num_columns,
+                     const rtm_kalman_state* kalman, const void* host_blob, size_t blob_bytes,
+                     rtm_cuda_stream stream);
+
+/* ------------------------------------------------------------------------------------------
  * Measurement aid (off by default; nothing below runs on the per-frame path unless enabled).
  * While enabled, every kernel launch of the library is bracketed by a pair of CUDA events on
  * the launching stream; rtm_profile_read synchronises them, adds the elapsed milliseconds and

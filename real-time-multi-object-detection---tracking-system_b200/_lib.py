@@ -159,6 +159,11 @@ SIGNATURES = {
     "rtm_zone_step": (C.c_int, [C.POINTER(ZoneSet), C.POINTER(TrackTable), C.c_void_p,
                                 C.POINTER(ZoneState), C.POINTER(ZoneState), C.c_double, C.c_void_p,
                                 C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rtm_state_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "rtm_state_export": (C.c_int, [C.POINTER(TrackTable), C.POINTER(ZoneState), C.c_int32, C.POINTER(KalmanState),
+                                   C.c_void_p, C.c_size_t, C.c_void_p]),
+    "rtm_state_import": (C.c_int, [C.POINTER(TrackTable), C.POINTER(ZoneState), C.c_int32, C.POINTER(KalmanState),
+                                   C.c_void_p, C.c_size_t, C.c_void_p]),
     "rtm_profile_enable": (C.c_int, [C.c_int32]),
     "rtm_profile_read": (C.c_int, [f64p, i32p]),
     "rtm_post_backbone_step": (C.c_int, [C.POINTER(StepIO), C.POINTER(NmsParams), C.c_void_p]),

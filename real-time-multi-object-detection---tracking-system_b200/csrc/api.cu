@@ -191,3 +191,121 @@ extern "C" int rtm_post_backbone_step_host(const rtm_step_io* io, const rtm_step
   if (h->done_event) RTM_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(h->done_event), s));
   return RTM_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------
+// checkpoint / resume
+// ---------------------------------------------------------------------------------------
+namespace {
+
+struct StateHeader {  // 64 bytes
+  char magic[8];      // "RTMSTATE"
+  int32_t version, num_streams, capacity, num_columns, with_zone_state, with_kalman;
+  int32_t reserved[8];
+};
+static_assert(sizeof(StateHeader) == 64, "state blob header");
+
+struct StatePiece {
+  void* dev;
+  size_t bytes;
+};
+
+// the arrays of a state blob in the order they are stored
+int state_pieces(const rtm_track_table* t, const rtm_zone_state* z, int num_columns, const rtm_kalman_state* k, StatePiece* out) {
+  const size_t B = t->num_streams, rows = B * static_cast<size_t>(t->capacity);
+  int n = 0;
+  out[n++] = {t->count, B * 4};
+  out[n++] = {t->next_id, B * 4};
+  out[n++] = {t->track_id, rows * 4};
+  out[n++] = {t->xyxy, rows * 16};
+  out[n++] = {t->confidence, rows * 4};
+  out[n++] = {t->class_id, rows * 4};
+  out[n++] = {t->age, rows * 4};
+  out[n++] = {t->time_since_update, rows * 4};
+  if (z) {
+    out[n++] = {z->first_seen, rows * num_columns * 8};
+    out[n++] = {z->last_alert, rows * num_columns * 8};
+  }
+  if (k) {
+    out[n++] = {k->mean, rows * 8 * 4};
+    out[n++] = {k->cov, rows * 12 * 4};
+  }
+  return n;
+}
+
+int check_state_args(const rtm_track_table* t, const rtm_zone_state* z, int num_columns, const rtm_kalman_state* k) {
+  RTM_REQUIRE(t && t->num_streams > 0 && t->capacity > 0, "rtm_state: bad track table");
+  RTM_REQUIRE(t->count && t->next_id && t->track_id && t->xyxy && t->confidence && t->class_id && t->age && t->time_since_update,
+              "rtm_state: null track table array");
+  if (z) RTM_REQUIRE(z->first_seen && z->last_alert && num_columns > 0, "rtm_state: bad zone state");
+  if (k) RTM_REQUIRE(k->mean && k->cov, "rtm_state: bad Kalman state");
+  return RTM_OK;
+}
+
+}  // namespace
+
+extern "C" size_t rtm_state_bytes(int32_t num_streams, int32_t capacity, int32_t num_columns, int32_t with_zone_state,
+                                  int32_t with_kalman) {
+  if (num_streams <= 0 || capacity <= 0) return 0;
+  const size_t B = num_streams, rows = B * static_cast<size_t>(capacity);
+  size_t n = sizeof(StateHeader) + B * 8 + rows * (4 + 16 + 4 + 4 + 4 + 4);
+  if (with_zone_state) n += rows * static_cast<size_t>(num_columns > 0 ? num_columns : 0) * 16;
+  if (with_kalman) n += rows * 20 * 4;
+  return n;
+}
+
+extern "C" int rtm_state_export(const rtm_track_table* table, const rtm_zone_state* zone_state, int32_t num_columns,
+                                const rtm_kalman_state* kalman, void* host_blob, size_t blob_bytes, rtm_cuda_stream stream) {
+  int rc = check_state_args(table, zone_state, num_columns, kalman);
+  if (rc) return rc;
+  const size_t need = rtm_state_bytes(table->num_streams, table->capacity, num_columns, zone_state != nullptr, kalman != nullptr);
+  RTM_REQUIRE(host_blob && blob_bytes >= need, "rtm_state_export: blob has %zu bytes, %zu needed", blob_bytes, need);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  StateHeader h = {};
+  memcpy(h.magic, "RTMSTATE", 8);
+  h.version = 1;
+  h.num_streams = table->num_streams;
+  h.capacity = table->capacity;
+  h.num_columns = zone_state ? num_columns : 0;
+  h.with_zone_state = zone_state != nullptr;
+  h.with_kalman = kalman != nullptr;
+  memcpy(host_blob, &h, sizeof(h));
+  StatePiece pieces[12];
+  const int n = state_pieces(table, zone_state, num_columns, kalman, pieces);
+  char* p = static_cast<char*>(host_blob) + sizeof(h);
+  for (int i = 0; i < n; ++i) {
+    RTM_CUDA(cudaMemcpyAsync(p, pieces[i].dev, pieces[i].bytes, cudaMemcpyDeviceToHost, s));
+    p += pieces[i].bytes;
+  }
+  RTM_CUDA(cudaStreamSynchronize(s));
+  return RTM_OK;
+}
+
+extern "C" int rtm_state_import(const rtm_track_table* table, const rtm_zone_state* zone_state, int32_t num_columns,
+                                const rtm_kalman_state* kalman, const void* host_blob, size_t blob_bytes, rtm_cuda_stream stream) {
+  int rc = check_state_args(table, zone_state, num_columns, kalman);
+  if (rc) return rc;
+  RTM_REQUIRE(host_blob && blob_bytes >= sizeof(StateHeader), "rtm_state_import: blob too small");
+  StateHeader h;
+  memcpy(&h, host_blob, sizeof(h));
+  RTM_REQUIRE(memcmp(h.magic, "RTMSTATE", 8) == 0 && h.version == 1, "rtm_state_import: not a state blob (or another version)");
+  RTM_REQUIRE(h.num_streams == table->num_streams && h.capacity == table->capacity,
+              "rtm_state_import: blob holds %d streams x %d rows, the tables %d x %d", h.num_streams, h.capacity, table->num_streams,
+              table->capacity);
+  RTM_REQUIRE((h.with_zone_state != 0) == (zone_state != nullptr) && (!zone_state || h.num_columns == num_columns),
+              "rtm_state_import: zone state of the blob (%d columns) and of the call (%d) differ", h.with_zone_state ? h.num_columns : 0,
+              zone_state ? num_columns : 0);
+  RTM_REQUIRE((h.with_kalman != 0) == (kalman != nullptr), "rtm_state_import: Kalman state present on one side only");
+  const size_t need = rtm_state_bytes(h.num_streams, h.capacity, h.num_columns, h.with_zone_state, h.with_kalman);
+  RTM_REQUIRE(blob_bytes >= need, "rtm_state_import: blob has %zu bytes, %zu needed", blob_bytes, need);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  StatePiece pieces[12];
+  const int n = state_pieces(table, zone_state, num_columns, kalman, pieces);
+  const char* p = static_cast<const char*>(host_blob) + sizeof(h);
+  for (int i = 0; i < n; ++i) {
+    RTM_CUDA(cudaMemcpyAsync(pieces[i].dev, p, pieces[i].bytes, cudaMemcpyHostToDevice, s));
+    p += pieces[i].bytes;
+  }
+  RTM_CUDA(cudaStreamSynchronize(s));
+  return RTM_OK;
+}

@@ -193,6 +193,93 @@ __device__ __forceinline__ void track_prefetch(const TrackArgs& a, const int b, 
   }
 }
 
+// Columns of a stage binned by the x coordinate of their box centre, for stages with many columns (a crowd):
+// a row then only looks at the columns whose box can intersect its own - every other pair has IoU exactly +0 and
+// cannot be the row's first arg-max unless the whole row is zero, in which case the row matches nothing anyway
+// (match_thresh > 0).  Exact by construction: a column d intersects row t only if
+//   t.x1 - w_d / 2 < cx_d < t.x2 + w_d / 2,  w_d <= w_max,
+// so the bins covering [t.x1 - w_max / 2, t.x2 + w_max / 2], widened by one bin on each side against rounding, hold
+// every such column.  The order inside a bin is arbitrary (atomics); ties are resolved by the column's index in the
+// stage's list, as np.argmax does.
+constexpr int kColBins = 64;
+constexpr int kBinMinCols = 128;  // stages with fewer columns scan them all
+struct ColBins {
+  int start[kColBins + 1];  // first position of a bin in `order`
+  int cursor[kColBins];
+  unsigned lo_bits, hi_bits, w_bits;  // min / max centre, max width as orderable floats
+  float xmin, inv_w, half_wmax;
+};
+
+__device__ __forceinline__ int col_bin(const ColBins* cb, const float cx) {
+  const float f = (cx - cb->xmin) * cb->inv_w;
+  return !(f >= 0.f) ? 0 : (f >= static_cast<float>(kColBins - 1) ? kColBins - 1 : static_cast<int>(f));
+}
+
+// All threads call it (block barriers inside).  s_order: m ints.
+template <int THREADS>
+__device__ __forceinline__ void bin_columns(const float4* s_box, const int* s_list, const int m, ColBins* cb, int* s_order) {
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    cb->lo_bits = 0xffffffffu;
+    cb->hi_bits = 0u;
+    cb->w_bits = 0u;
+  }
+  for (int b = tid; b < kColBins; b += THREADS) cb->cursor[b] = 0;
+  __syncthreads();
+  for (int j = tid; j < m; j += THREADS) {
+    const float4 d = s_box[s_list[j]];
+    const float cx = (d.x + d.z) * 0.5f, w = d.z - d.x;
+    if (cx == cx && fabsf(cx) < 1e30f) {  // (NaN / infinite boxes have IoU 0 with everything: where they land does not matter)
+      atomicMin(&cb->lo_bits, float_orderable(cx));
+      atomicMax(&cb->hi_bits, float_orderable(cx));
+    }
+    if (w == w && w < 1e30f) atomicMax(&cb->w_bits, float_orderable(fmaxf(w, 0.f)));
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const float lo = cb->lo_bits == 0xffffffffu ? 0.f : float_from_orderable(cb->lo_bits);
+    const float hi = cb->hi_bits == 0u ? 0.f : float_from_orderable(cb->hi_bits);
+    cb->xmin = lo;
+    cb->inv_w = static_cast<float>(kColBins) / fmaxf(hi - lo, 1e-3f);
+    cb->half_wmax = cb->w_bits == 0u ? 0.f : 0.5f * float_from_orderable(cb->w_bits);
+  }
+  __syncthreads();
+  for (int j = tid; j < m; j += THREADS) {
+    const float4 d = s_box[s_list[j]];
+    atomicAdd(&cb->cursor[col_bin(cb, (d.x + d.z) * 0.5f)], 1);
+  }
+  __syncthreads();
+  if (tid < 32) {  // exclusive prefix over the 64 bins by one warp
+    const int c0 = cb->cursor[2 * tid], c1 = cb->cursor[2 * tid + 1];
+    int incl = c0 + c1;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(kFull, incl, d);
+      if (tid >= d) incl += o;
+    }
+    const int base = incl - (c0 + c1);
+    cb->start[2 * tid] = base;
+    cb->start[2 * tid + 1] = base + c0;
+    cb->cursor[2 * tid] = base;
+    cb->cursor[2 * tid + 1] = base + c0;
+    if (tid == 31) cb->start[kColBins] = incl;
+  }
+  __syncthreads();
+  for (int j = tid; j < m; j += THREADS) {
+    const float4 d = s_box[s_list[j]];
+    s_order[atomicAdd(&cb->cursor[col_bin(cb, (d.x + d.z) * 0.5f)], 1)] = j;
+  }
+  __syncthreads();
+}
+
+// positions [*p0, *p1) of `order` that can hold a column intersecting box a
+__device__ __forceinline__ void col_range(const ColBins* cb, const float4 a, int* p0, int* p1) {
+  const int b0 = max(col_bin(cb, a.x - cb->half_wmax) - 1, 0);
+  const int b1 = min(col_bin(cb, a.z + cb->half_wmax) + 1, kColBins - 1);
+  *p0 = cb->start[b0];
+  *p1 = cb->start[b1 + 1];
+}
+
 // One association stage: rows = tracks with s_match[t] < 0, columns = s_list[0..m).
 // On return s_match[t] holds (det index | flag) for the rows that won their column.
 // A group of G lanes (G = 4 .. 32, a power of two chosen from the number of columns) takes a row at
@@ -204,10 +291,12 @@ __device__ __forceinline__ void associate(const TrackPrefetch* pf, const float4*
                                           const float* kf_mean, const int32_t* g_tsu, size_t row0, int T,
                                           const float4* s_box, const float* s_area,
                                           const int* s_list, int m, int* s_win, int* s_match,
-                                          float thresh, int flag) {
+                                          float thresh, int flag, ColBins* cb, int* s_order) {
   const int tid = threadIdx.x;
   for (int j = tid; j < m; j += THREADS) s_win[j] = INT_MAX;
-  __syncthreads();
+  const bool binned = m >= kBinMinCols && thresh > 0.f;  // block-uniform
+  if (binned) bin_columns<THREADS>(s_box, s_list, m, cb, s_order);
+  else __syncthreads();
   // lanes per row: few enough that the rows of a typical table (a few hundred) keep all groups busy,
   // enough that a lane's share of the columns stays short
   const int G = m <= 8 ? 4 : (m <= 64 ? 8 : (m <= 256 ? 16 : 32));
@@ -222,12 +311,25 @@ __device__ __forceinline__ void associate(const TrackPrefetch* pf, const float4*
       const float4 a = t < kTrackPrefRows ? pf->abox[t]
                                           : (kf_mean ? kalman_predicted_box(kf_mean, row0 + t, g_tsu[row0 + t]) : g_box[t]);
       const float area_a = box_area(a);
-      for (int j = sub; j < m; j += G) {
-        const int d = s_list[j];
-        const float v = pair_iou(a, area_a, s_box[d], s_area[d]);
-        if (v > best) {  // strict: first arg-max of the lane's columns
-          best = v;
-          bj = j;
+      if (binned) {
+        int p0, p1;
+        col_range(cb, a, &p0, &p1);
+        for (int p = p0 + sub; p < p1; p += G) {
+          const int j = s_order[p], d = s_list[j];
+          const float v = pair_iou(a, area_a, s_box[d], s_area[d]);
+          if (v > best || (v == best && j < bj)) {  // the bin order is arbitrary: the lower column wins a tie
+            best = v;
+            bj = j;
+          }
+        }
+      } else {
+        for (int j = sub; j < m; j += G) {
+          const int d = s_list[j];
+          const float v = pair_iou(a, area_a, s_box[d], s_area[d]);
+          if (v > best) {  // strict: first arg-max of the lane's columns
+            best = v;
+            bj = j;
+          }
         }
       }
     }
@@ -358,8 +460,11 @@ __device__ __forceinline__ int associate_optimal(const TrackPrefetch* pf, const 
                                                  const float* kf_mean, const int32_t* g_tsu, size_t row0, int T,
                                                  const float4* s_box, const float* s_area, const int* s_list, int m,
                                                  int* s_win, int* s_match, const double cost_limit, int flag,
-                                                 AssignScratch* sc, int* deg_row, int* deg_col) {
+                                                 AssignScratch* sc, int* deg_row, int* deg_col, ColBins* cb, int* s_order) {
   const int tid = threadIdx.x;
+  // admissible pairs have IoU > match_thresh: with a positive threshold (cost_limit < 1) they intersect
+  const bool binned = m >= kBinMinCols && cost_limit < 1.0;  // block-uniform
+  if (binned) bin_columns<THREADS>(s_box, s_list, m, cb, s_order);
   for (int j = tid; j < m; j += THREADS) {
     s_win[j] = INT_MAX;
     deg_col[j] = 0;
@@ -379,8 +484,10 @@ __device__ __forceinline__ int associate_optimal(const TrackPrefetch* pf, const 
       const float4 a = t < kTrackPrefRows ? pf->abox[t]
                                           : (kf_mean ? kalman_predicted_box(kf_mean, row0 + t, g_tsu[row0 + t]) : g_box[t]);
       const float area_a = box_area(a);
-      for (int j = sub; j < m; j += G) {
-        const int d = s_list[j];
+      int p0 = 0, p1 = m;
+      if (binned) col_range(cb, a, &p0, &p1);
+      for (int p = p0 + sub; p < p1; p += G) {
+        const int j = binned ? s_order[p] : p, d = s_list[j];
         const float cst = __fsub_rn(1.f, pair_iou(a, area_a, s_box[d], s_area[d]));  // tracker.py:167, float32
         if (static_cast<double>(cst) < cost_limit) {
           const int e = atomicAdd(&sc->n_edges, 1);
@@ -486,10 +593,12 @@ __device__ __forceinline__ void track_stream(const TrackArgs& a, const int b, un
   int* s_cls = reinterpret_cast<int*>(s_conf + S);       // S
   int* s_match = s_cls + S;                             // cap
   int* s_scan = s_match + cap;                          // 33 (+ 7 spare)
+  int* s_order = s_scan + 40;                           // S  columns of a stage in bin order
+  ColBins* s_bins = reinterpret_cast<ColBins*>(s_order + S);
   // optimal-assignment scratch (only laid out by track_smem_bytes when that mode is on)
-  int* s_deg_row = s_scan + 40;                         // cap
+  int* s_deg_row = reinterpret_cast<int*>(s_bins + 1);  // cap
   int* s_deg_col = s_deg_row + cap;                     // S
-  AssignScratch* s_assign = reinterpret_cast<AssignScratch*>(s_deg_col + S);
+  AssignScratch* s_assign = reinterpret_cast<AssignScratch*>((reinterpret_cast<uintptr_t>(s_deg_col + S) + 15) & ~static_cast<uintptr_t>(15));
   const bool optimal = WITH_OPTIMAL && a.assignment == RTM_ASSIGN_OPTIMAL;
 
   const size_t row0 = static_cast<size_t>(b) * cap;
@@ -569,11 +678,11 @@ __device__ __forceinline__ void track_stream(const TrackArgs& a, const int b, un
   if (T > 0 && H > 0) {
     if (WITH_OPTIMAL && optimal) {
       if (associate_optimal<THREADS>(pf, in_box, a.kf_mean_in, a.tin.time_since_update, row0, T, s_box, s_area, s_hi, H, s_win,
-                                     s_match, a.cost_limit, 0, s_assign, s_deg_row, s_deg_col))
+                                     s_match, a.cost_limit, 0, s_assign, s_deg_row, s_deg_col, s_bins, s_order))
         st |= RTM_STATUS_ASSIGN_LIMIT;
     } else {
       associate<THREADS>(pf, in_box, a.kf_mean_in, a.tin.time_since_update, row0, T, s_box, s_area, s_hi, H, s_win, s_match,
-                         a.match_thresh, 0);
+                         a.match_thresh, 0, s_bins, s_order);
     }
     for (int j = tid; j < H; j += THREADS) s_born[j] = (s_win[j] == INT_MAX);
     __syncthreads();
@@ -583,11 +692,11 @@ __device__ __forceinline__ void track_stream(const TrackArgs& a, const int b, un
   if (T > 0 && L > 0) {
     if (WITH_OPTIMAL && optimal) {
       if (associate_optimal<THREADS>(pf, in_box, a.kf_mean_in, a.tin.time_since_update, row0, T, s_box, s_area, s_lo, L, s_win,
-                                     s_match, a.cost_limit, kStage2Flag, s_assign, s_deg_row, s_deg_col))
+                                     s_match, a.cost_limit, kStage2Flag, s_assign, s_deg_row, s_deg_col, s_bins, s_order))
         st |= RTM_STATUS_ASSIGN_LIMIT;
     } else {
       associate<THREADS>(pf, in_box, a.kf_mean_in, a.tin.time_since_update, row0, T, s_box, s_area, s_lo, L, s_win, s_match,
-                         a.match_thresh, kStage2Flag);
+                         a.match_thresh, kStage2Flag, s_bins, s_order);
     }
   }
 
@@ -685,9 +794,9 @@ __device__ __forceinline__ void track_stream(const TrackArgs& a, const int b, un
 
 inline size_t track_smem_bytes(int det_stride, int capacity, bool optimal = false) {
   if (optimal)
-    return static_cast<size_t>(det_stride) * (16 + 4 + 4 * 4 + 4 + 4 + 4 + 4) + static_cast<size_t>(capacity) * 8 + 40 * 4 +
-           sizeof(AssignScratch) + 16;
-  return static_cast<size_t>(det_stride) * (16 + 4 + 4 * 4 + 4 + 4 + 4) + static_cast<size_t>(capacity) * 4 + 40 * 4;
+    return static_cast<size_t>(det_stride) * (16 + 4 + 4 * 4 + 4 + 4 + 4 + 4 + 4) + static_cast<size_t>(capacity) * 8 + 40 * 4 +
+           sizeof(ColBins) + sizeof(AssignScratch) + 16;
+  return static_cast<size_t>(det_stride) * (16 + 4 + 4 * 4 + 4 + 4 + 4 + 4) + static_cast<size_t>(capacity) * 4 + 40 * 4 + sizeof(ColBins);
 }
 
 }  // namespace rtm

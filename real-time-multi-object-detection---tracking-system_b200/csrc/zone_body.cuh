@@ -2,6 +2,7 @@
 // post-backbone kernel).  See zone.cu for the semantics and the reference citations.
 #pragma once
 
+#include <limits.h>
 #include <math.h>
 
 #include "rtm_common.cuh"
@@ -58,6 +59,7 @@ struct ZonePrefetch {
   int2 poly[kZonePrefVertices];
   double dwell[kMaxZonesPerStream], cool[kMaxZonesPerStream];
   int off[kMaxZonesPerStream + 1], col[kMaxZonesPerStream];
+  int4 bbox[kMaxZonesPerStream];  // x_min, y_min, x_max, y_max of the zone's vertices: a point outside is outside the polygon
   int nz, v0, staged;
 };
 
@@ -81,6 +83,17 @@ __device__ __forceinline__ void zone_prefetch(const ZoneArgs& a, const int b, Zo
   const int2* g_poly = reinterpret_cast<const int2*>(a.zs.poly_xy);
   if (staged)
     for (int i = tid; i < nv; i += THREADS) zp->poly[i] = g_poly[v0 + i];
+  for (int z = tid; z < nz; z += THREADS) {  // (from global memory: the staged copy is not visible to this thread yet)
+    int4 bb = make_int4(INT_MAX, INT_MAX, INT_MIN, INT_MIN);
+    for (int i = zp->off[z]; i < zp->off[z + 1]; ++i) {
+      const int2 v = g_poly[v0 + i];
+      bb.x = min(bb.x, v.x);
+      bb.y = min(bb.y, v.y);
+      bb.z = max(bb.z, v.x);
+      bb.w = max(bb.w, v.y);
+    }
+    zp->bbox[z] = bb;
+  }
   if (tid == 0) {
     zp->nz = nz;
     zp->v0 = v0;
@@ -147,7 +160,9 @@ __device__ __forceinline__ void zone_stream(const ZoneArgs& a, const int b, unsi
       for (int z = 0; z < nz; ++z) {
         if (zp->col[z] != c) continue;
         const int p0 = zp->off[z], k = zp->off[z + 1] - p0;
-        if (point_in_polygon(poly + p0, k, cx, cy) >= 0) {
+        const int4 bb = zp->bbox[z];
+        // cv2.pointPolygonTest >= 0 (inside or on the boundary) is impossible outside the vertices' bounding box
+        if (cx >= bb.x && cx <= bb.z && cy >= bb.y && cy <= bb.w && point_in_polygon(poly + p0, k, cx, cy) >= 0) {
           if (fs != fs) fs = now;  // not in the zone before: start the dwell timer
           const double dwell = now - fs;
           if (dwell >= zp->dwell[z] && now - la >= zp->cool[z]) {

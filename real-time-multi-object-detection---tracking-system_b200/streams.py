@@ -431,6 +431,36 @@ class StreamBatch:
                     self.status.data_ptr(), st))
         self._advance()
 
+    # -- checkpoint / resume -------------------------------------------------
+    def _state_args(self):
+        t = self.tables[self.cur]
+        z = self.zones
+        return (C.byref(t.struct), C.byref(z.state_in()[2]) if z is not None else None, z.num_columns if z is not None else 0,
+                C.byref(t.kalman) if self.use_kalman else None)
+
+    def export_state(self) -> bytes:
+        """The batch's whole state - track tables, next ids, zone dwell / cooldown state, Kalman state - as one blob
+        (rtm_state_export; synchronises).  The reference has no counterpart: its state lives in Python lists and dicts."""
+        import torch
+        z = self.zones
+        n = self.lib.rtm_state_bytes(self.B, self.tables[0].capacity, z.num_columns if z is not None else 0, int(z is not None),
+                                     int(self.use_kalman))
+        blob = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)              # steps in flight on the library's stream included
+            _lib.check(self.lib.rtm_state_export(*self._state_args(), blob.data_ptr(), n, _lib.cuda_stream()))
+        return blob.numpy().tobytes() + int(self.frame_id).to_bytes(8, "little", signed=True)
+
+    def import_state(self, blob: bytes) -> None:
+        """Resume from :meth:`export_state` of a batch of the same shape (streams, max_tracks, zone columns, motion model)."""
+        import torch
+        n = len(blob) - 8
+        buf = torch.from_numpy(np.frombuffer(blob, np.uint8, n).copy())
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)
+            _lib.check(self.lib.rtm_state_import(*self._state_args(), buf.data_ptr(), n, _lib.cuda_stream()))
+        self.frame_id = int.from_bytes(blob[n:], "little", signed=True)
+
     # -- results -----------------------------------------------------------
     def check_status(self) -> None:
         st = self.status.cpu().numpy()

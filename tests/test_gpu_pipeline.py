@@ -322,3 +322,38 @@ def test_host_feeder_copies_event_heads_only_and_says_so(pkg):
     feeder = pkg.HostFeeder(sb, torch.bfloat16, event_prefix=64)
     res = feeder.step([torch.from_numpy(h).to(torch.bfloat16) for h in frames[-1]], now=9.0, frame_id=9)
     assert [len(e) for e in res.events()] == [len(e) for e in sb.read_events()]
+
+
+@pytest.mark.parametrize("kalman", [False, True])
+def test_state_export_import_resumes_bit_exactly(pkg, kalman):
+    """rtm_state_export / rtm_state_import (checkpoint / resume): a batch resumed from a blob in
+    another object continues exactly like the one that was never interrupted; a blob of another shape is refused."""
+    import torch
+    B, F = 3, 24
+    frames = moving_heads(pkg, B, F, seed=13)
+    dev = torch.device("cuda", 0)
+    heads = [[torch.from_numpy(h).to(torch.bfloat16).to(dev).contiguous() for h in fr] for fr in frames]
+    zones = [pkg.synth.make_zones(seed=b, num_zones=4, width=1920, height=1080, dwell_time_sec=0.2, cooldown_sec=0.4) for b in range(B)]
+    make = lambda n=B, z=zones: pkg.StreamBatch(n, z, src_hw=(1080, 1920), classes=WANTED, max_tracks=128, use_kalman=kalman)
+    a = make()
+    for f in range(11):                                            # an odd number of steps: the tables' parity differs
+        a.step(heads[f], now=3.0 + f / 30.0, frame_id=f)
+    blob = a.export_state()
+    b = make()
+    b.import_state(blob)
+    assert b.frame_id == a.frame_id == 11
+    for f in range(11, F):
+        for sb in (a, b):
+            sb.step(heads[f], now=3.0 + f / 30.0, frame_id=f)
+        ta, na = a.read_tracks()
+        tb, nb = b.read_tracks()
+        assert na.tolist() == nb.tolist()
+        for x, y in zip(ta, tb):
+            assert [(t["track_id"], t["age"], t["time_since_update"], t["xyxy"].tolist()) for t in x] == \
+                   [(t["track_id"], t["age"], t["time_since_update"], t["xyxy"].tolist()) for t in y]
+        ea, eb = a.read_events(), b.read_events()
+        assert [[(e.track_id, e.zone_name, e.dwell_time_sec) for e in s] for s in ea] == \
+               [[(e.track_id, e.zone_name, e.dwell_time_sec) for e in s] for s in eb]
+    assert sum(len(t) for t in ta) > 10
+    with pytest.raises(pkg.RtmError):
+        make(2, zones[:2]).import_state(blob)

@@ -193,7 +193,7 @@ def test_facade_does_work_proportional_to_the_call_and_handles_repeated_ids(pkg,
             ids = np.concatenate([ids, ids[:2]])                    # the same ids again, later in the same call
         tracks = []
         for k, i in enumerate(ids):
-            c = np.array([(37 * int(i) + 3 * f + 11 * k) % 640, (53 * int(i) + 2 * f) % 480], np.float32)
+            c = np.array([(37 * int(i)) % 640 + 0.4 * f, (53 * int(i)) % 480 + 0.2 * f], np.float32)   # slow drift: they dwell
             tracks.append(types.SimpleNamespace(track_id=int(i), xyxy=np.array([c[0] - 6, c[1] - 8, c[0] + 6, c[1] + 8], np.float32),
                                                 class_id=int(i) % 3))
         got = eng.process(tracks, f)
@@ -201,5 +201,5 @@ def test_facade_does_work_proportional_to_the_call_and_handles_repeated_ids(pkg,
         assert [(e.track_id, e.zone_name, e.centroid, e.dwell_time_sec, e.frame_id) for e in got] == \
                [(e.track_id, e.zone_name, e.centroid, e.dwell_time_sec, e.frame_id) for e in exp]
         total += len(got)
-    assert total > 30
-    assert eng._tables.capacity <= 32 and len(eng._cooldown) > 40     # state on the host, a small table on the device
+    assert total > 20
+    assert eng._tables.capacity <= 32 and len(eng._cooldown) > 10     # state on the host, a small table on the device

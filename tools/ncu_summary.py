@@ -19,7 +19,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-OURS = ("decode_tma_kernel", "decode_ldg_kernel", "post_kernel", "nms_kernel", "track_step_kernel", "zone_step_kernel",
+OURS = ("step_kernel", "letterbox_decimate3_kernel", "decode_tma_kernel", "decode_ldg_kernel", "post_kernel", "nms_kernel", "track_step_kernel", "zone_step_kernel",
         "letterbox_kernel", "pred_candidates_kernel", "decode_head_kernel", "kalman", "lapjv")
 
 METRICS = [
@@ -55,6 +55,8 @@ def full(tag):
     rep = os.path.join(ROOT, "gpurun_out", f"prof_{tag}.ncu-rep")
     if not os.path.exists(rep):
         return
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    old = json.load(open(tpath)) if os.path.exists(tpath) else {}
     txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(txt.splitlines()))
     hdr, units, data = rows[0], rows[1], rows[2:]
@@ -74,9 +76,12 @@ def full(tag):
     summary = {k: {"dram_bytes_read_per_launch": sum(a for a, _ in v) / len(v),
                    "dram_bytes_write_per_launch": sum(b for _, b in v) / len(v),
                    "launches_captured": len(v)} for k, v in traffic.items()}
-    summary["source"] = f"ncu --set full --clock-control none, gpurun_out/prof_{tag}.ncu-rep -> profiles/{tag}_full.csv"
-    with open(os.path.join(ROOT, "profiles", "traffic.json"), "w") as f:
-        json.dump(summary, f, indent=1)
+    for v in summary.values():
+        v["source"] = f"ncu --set full --clock-control none, gpurun_out/prof_{tag}.ncu-rep -> profiles/{tag}_full.csv"
+    old.pop("source", None)
+    old.update(summary)                                  # kernels captured in other sessions keep their entries
+    with open(tpath, "w") as f:
+        json.dump(old, f, indent=1)
     print("wrote", out)
 
 

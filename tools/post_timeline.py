@@ -24,7 +24,9 @@ if "--build" in sys.argv:
     sys.exit(0)
 
 os.environ["RTM_LIB_PATH"] = TL_LIB
-os.environ["RTM_STEP_FUSED"] = "0"      # the stage stamps are indexed by blockIdx = stream: the two-launch post kernel
+if "--fused" not in sys.argv:
+    os.environ["RTM_STEP_FUSED"] = "0"  # the two-launch post kernel (stamps indexed by blockIdx = stream); --fused: the step kernel's workers
+sys.argv = [a for a in sys.argv if a != "--fused"]
 import ctypes as C
 import numpy as np
 import torch
@@ -39,7 +41,7 @@ wl = PostBackboneWorkload(S, F, first_stream=0, device=dev, dtype=torch.bfloat16
 sb = pkg.StreamBatch(S, wl.zones, src_hw=(1080, 1920), classes=[0, 1, 2, 3, 5, 7], max_tracks=512, device=dev)
 lib = sb.lib
 lib.rtm_debug_timeline.restype, lib.rtm_debug_timeline.argtypes = C.c_int, [C.c_void_p]
-buf = torch.zeros((S, 32), dtype=torch.int64, device=dev)
+buf = torch.zeros((16384 + 16 * 512 * 8,), dtype=torch.int64, device=dev)   # stage rows first, the step kernel's CTA rows behind
 for f in range(16):
     sb.step(wl.heads[f % F], now=1.7e9 + f / 30, frame_id=f)
 torch.cuda.synchronize()
@@ -49,7 +51,7 @@ for f in range(16, 16 + steps):
     buf.zero_()
     sb.step(wl.heads[f % F], now=1.7e9 + f / 30, frame_id=f)
     torch.cuda.synchronize()
-    acc.append(buf.cpu().numpy().copy())
+    acc.append(buf[:S * 32].view(S, 32).cpu().numpy().copy())
 pkg._lib.check(lib.rtm_debug_timeline(None))
 t = np.stack(acc).astype(np.float64)          # (steps, S, 32)
 ids = [0, 1, 2, 3, 4, 5, 7, 8, 6, 10, 11, 12, 13, 14, 20, 21, 30]
