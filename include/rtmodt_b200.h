@@ -50,9 +50,10 @@ enum {
   RTM_STATUS_CAND_OVERFLOW = 4,  /* NMS candidates exceed the workspace capacity       */
   RTM_STATUS_EVENT_OVERFLOW = 8, /* events of one step exceed event_stride             */
   RTM_STATUS_ZONE_LIMIT = 16,    /* a stream has more than 64 zones                    */
-  RTM_STATUS_ASSIGN_LIMIT = 32   /* RTM_ASSIGN_OPTIMAL: more than 4096 admissible pairs in a
-                                    stage, or a conflict component with more than 32 rows or
-                                    columns                                              */
+  RTM_STATUS_ASSIGN_LIMIT = 32   /* RTM_ASSIGN_OPTIMAL without (enough) assign_scratch: more than
+                                    4096 admissible pairs in a stage, or a conflict component with
+                                    more than 32 rows or columns; with scratch: more admissible
+                                    pairs in a stage than the scratch was sized for        */
 };
 
 /* per-detection outcome of one tracker step (rtm_track_step: det_kind) */
@@ -213,7 +214,15 @@ typedef struct rtm_track_options {
   double cost_limit;                 /* RTM_ASSIGN_OPTIMAL: lap's cost_limit, `1 - match_thresh` evaluated in
                                         double as tracker.py:170 does; a pair is admissible iff
                                         (double)float32(1 - IoU) < cost_limit                         */
+  /* RTM_ASSIGN_OPTIMAL: device scratch for association stages that outgrow the shared-memory solver (crowds, low
+   * thresholds) - rtm_assign_scratch_bytes() bytes for the whole batch, or NULL / 0: such stages then set
+   * RTM_STATUS_ASSIGN_LIMIT.  lap.lapjv itself has no such limits (tracker.py:168-181). */
+  void* assign_scratch;
+  size_t assign_scratch_bytes;
 } rtm_track_options;
+
+/* scratch for num_streams streams whose stages hold up to max_pairs admissible (track, detection) pairs each */
+size_t rtm_assign_scratch_bytes(int32_t num_streams, int32_t capacity, int32_t det_stride, int32_t max_pairs);
 
 int rtm_track_step_ex(const rtm_track_table* table_in, const rtm_track_table* table_out,
                       const float* det_xyxy, const float* det_conf, const int32_t* det_cls,
@@ -320,6 +329,8 @@ typedef struct rtm_step_io {
    * lap's cost_limit for RTM_ASSIGN_OPTIMAL (see rtm_track_options) */
   int32_t assignment;
   double cost_limit;
+  void* assign_scratch;        /* as in rtm_track_options */
+  size_t assign_scratch_bytes;
   /* Pipelining of consecutive steps.  scan_async = 0 (default): everything goes to `stream` as ordinary
    * launches; the head tensors are ordered on `stream` like any other input and a step starts when the
    * step before it has finished.  scan_async = 1: the caller states that the head tensors are complete

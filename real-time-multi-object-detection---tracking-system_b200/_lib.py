@@ -26,8 +26,8 @@ _STATUS_TEXT = {
     STATUS_CAND_OVERFLOW: "NMS candidates exceed the workspace capacity",
     STATUS_EVENT_OVERFLOW: "zone events of one step exceed the event buffer (raise max_events)",
     STATUS_ZONE_LIMIT: f"a stream has more than {MAX_ZONES_PER_STREAM} zones",
-    STATUS_ASSIGN_LIMIT: "optimal assignment: more than 4096 admissible pairs in a stage or a conflict component "
-                         "with more than 32 rows / columns",
+    STATUS_ASSIGN_LIMIT: "optimal assignment: more admissible pairs in a stage than the solver's scratch holds "
+                         "(raise max_pairs)",
 }
 
 i32p = C.POINTER(C.c_int32)
@@ -62,10 +62,12 @@ ASSIGN_GREEDY, ASSIGN_OPTIMAL = 0, 1
 class TrackOptions(C.Structure):
     _fields_ = [("track_thresh", C.c_float), ("match_thresh", C.c_float), ("track_buffer", C.c_int32),
                 ("assignment", C.c_int32), ("kalman_in", C.POINTER(KalmanState)),
-                ("kalman_out", C.POINTER(KalmanState)), ("cost_limit", C.c_double)]
+                ("kalman_out", C.POINTER(KalmanState)), ("cost_limit", C.c_double),
+                ("assign_scratch", C.c_void_p), ("assign_scratch_bytes", C.c_size_t)]
 
 
-def track_options(track_thresh, match_thresh, track_buffer, assignment="greedy", kalman_in=None, kalman_out=None):
+def track_options(track_thresh, match_thresh, track_buffer, assignment="greedy", kalman_in=None, kalman_out=None,
+                  assign_scratch=None):
     """rtm_track_options; ``assignment`` = "greedy" (what the reference runs without lap, tracker.py:182-194)
     or "lapjv" (its lap.lapjv branch, tracker.py:168-181: cost_limit = 1 - match_thresh in double)."""
     if assignment not in ("greedy", "lapjv"):
@@ -74,7 +76,9 @@ def track_options(track_thresh, match_thresh, track_buffer, assignment="greedy",
                         ASSIGN_OPTIMAL if assignment == "lapjv" else ASSIGN_GREEDY,
                         C.pointer(kalman_in) if kalman_in is not None else None,
                         C.pointer(kalman_out) if kalman_out is not None else None,
-                        1 - float(match_thresh))
+                        1 - float(match_thresh),
+                        assign_scratch.data_ptr() if assign_scratch is not None else None,
+                        assign_scratch.numel() if assign_scratch is not None else 0)
 
 
 class ZoneSet(C.Structure):
@@ -116,6 +120,7 @@ class StepIO(C.Structure):
         ("event_count", C.c_void_p), ("status", C.c_void_p),
         ("kalman_in", C.POINTER(KalmanState)), ("kalman_out", C.POINTER(KalmanState)),
         ("assignment", C.c_int32), ("cost_limit", C.c_double),
+        ("assign_scratch", C.c_void_p), ("assign_scratch_bytes", C.c_size_t),
         ("scan_async", C.c_int32), ("heads_ready_event", C.c_void_p), ("results_alternate", C.c_int32),
     ]
 
@@ -156,6 +161,7 @@ SIGNATURES = {
     "rtm_track_step_ex": (C.c_int, [C.POINTER(TrackTable), C.POINTER(TrackTable), C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(TrackOptions),
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rtm_assign_scratch_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "rtm_zone_step": (C.c_int, [C.POINTER(ZoneSet), C.POINTER(TrackTable), C.c_void_p,
                                 C.POINTER(ZoneState), C.POINTER(ZoneState), C.c_double, C.c_void_p,
                                 C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),

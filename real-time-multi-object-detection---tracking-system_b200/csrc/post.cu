@@ -307,7 +307,11 @@ void fill_post_args(PostArgs* a, const rtm_step_io* io, const rtm_nms_params* pa
   a->trk = rtm::TrackArgs{*io->table_in, *io->table_out, io->det_xyxy, io->det_conf, io->det_cls, io->det_count,
                           io->det_stride, io->track_thresh, io->match_thresh, io->track_buffer, io->det_track_id,
                           io->det_kind, io->src_row, io->status,
-                          nullptr, nullptr, nullptr, nullptr, io->assignment, io->cost_limit};
+                          nullptr, nullptr, nullptr, nullptr, io->assignment, io->cost_limit, nullptr, 0};
+  if (io->assign_scratch && io->assign_scratch_bytes) {
+    a->trk.assign_scratch = static_cast<unsigned char*>(io->assign_scratch);
+    a->trk.assign_scratch_per_stream = io->assign_scratch_bytes / io->table_in->num_streams / 16 * 16;
+  }
   if (io->kalman_in) {
     a->trk.kf_mean_in = io->kalman_in->mean;
     a->trk.kf_cov_in = io->kalman_in->cov;
@@ -484,7 +488,7 @@ extern "C" int rtm_post_backbone_step(const rtm_step_io* io, const rtm_nms_param
                             io->det_count, io->det_stride, io->status, io->workspace, io->workspace_bytes, stream);
     if (rc) return rc;
     const rtm_track_options opt{io->track_thresh, io->match_thresh, io->track_buffer, io->assignment, io->kalman_in,
-                                io->kalman_out, io->cost_limit};
+                                io->kalman_out, io->cost_limit, io->assign_scratch, io->assign_scratch_bytes};
     rc = rtm_track_step_ex(io->table_in, io->table_out, io->det_xyxy, io->det_conf, io->det_cls, io->det_count,
                            io->det_stride, &opt, io->det_track_id, io->det_kind, io->src_row, io->status, stream);
     if (rc) return rc;

@@ -65,7 +65,12 @@ extern "C" int rtm_track_step_ex(const rtm_track_table* table_in, const rtm_trac
               opt->assignment);
   TrackArgs a{*table_in, *table_out, det_xyxy, det_conf, det_cls, det_count, det_stride,
               opt->track_thresh, opt->match_thresh, opt->track_buffer, det_track_id, det_kind, src_row, status,
-              nullptr, nullptr, nullptr, nullptr, opt->assignment, opt->cost_limit};
+              nullptr, nullptr, nullptr, nullptr, opt->assignment, opt->cost_limit, nullptr, 0};
+  if (opt->assign_scratch && opt->assign_scratch_bytes) {
+    RTM_REQUIRE((reinterpret_cast<uintptr_t>(opt->assign_scratch) & 15) == 0, "rtm_track_step: assign_scratch must be 16-byte aligned");
+    a.assign_scratch = static_cast<unsigned char*>(opt->assign_scratch);
+    a.assign_scratch_per_stream = opt->assign_scratch_bytes / table_in->num_streams / 16 * 16;
+  }
   if (opt->kalman_in) {
     RTM_REQUIRE(opt->kalman_in->mean && opt->kalman_in->cov && opt->kalman_out->mean && opt->kalman_out->cov,
                 "rtm_track_step: null Kalman state arrays");
@@ -86,7 +91,13 @@ extern "C" int rtm_track_step(const rtm_track_table* table_in, const rtm_track_t
                               float match_thresh, int32_t track_buffer, int32_t* det_track_id,
                               int32_t* det_kind, int32_t* src_row, int32_t* status,
                               rtm_cuda_stream stream) {
-  const rtm_track_options opt{track_thresh, match_thresh, track_buffer, RTM_ASSIGN_GREEDY, nullptr, nullptr, 0.0};
+  const rtm_track_options opt{track_thresh, match_thresh, track_buffer, RTM_ASSIGN_GREEDY, nullptr, nullptr, 0.0, nullptr, 0};
   return rtm_track_step_ex(table_in, table_out, det_xyxy, det_conf, det_cls, det_count, det_stride, &opt, det_track_id,
                            det_kind, src_row, status, stream);
+}
+
+extern "C" size_t rtm_assign_scratch_bytes(int32_t num_streams, int32_t capacity, int32_t det_stride, int32_t max_pairs) {
+  if (num_streams <= 0 || capacity <= 0 || det_stride <= 0 || max_pairs < 0) return 0;
+  const size_t per = (rtm::assign_global_fixed_bytes(capacity, det_stride) + static_cast<size_t>(max_pairs) * 6 + 31) / 16 * 16;
+  return per * num_streams;
 }

@@ -30,6 +30,9 @@ struct TrackArgs {
   float* kf_cov_out;
   int32_t assignment;  // RTM_ASSIGN_*
   double cost_limit;   // RTM_ASSIGN_OPTIMAL: lap's cost_limit = 1 - match_thresh (tracker.py:170), in double
+  // RTM_ASSIGN_OPTIMAL: global scratch for stages beyond the shared-memory solver (null: they set RTM_STATUS_ASSIGN_LIMIT)
+  unsigned char* assign_scratch;
+  size_t assign_scratch_per_stream;
 };
 
 // ---- constant-velocity filter of ByteTrack (xyah), stored as four (position, velocity) filters.
@@ -455,12 +458,277 @@ static __device__ __noinline__ void hungarian_component(AssignScratch* sc, const
     if (p[j] >= 1 && p[j] <= r) match[p[j] - 1] = j - 1;
 }
 
+// ---------------------------------------------------------------------------------------
+// The general solver: any number of admissible pairs, components of any size, in global scratch.
+//
+// lap's extended problem [[C, L/2], [L/2, 0]] has the same optima as this one: every row takes an admissible
+// column at cost c - L (< 0) or stays unmatched at cost 0; columns are used at most once.  It is solved exactly by
+// shortest augmenting paths (Jonker-Volgenant form: row potentials u <= 0, column potentials v, reduced costs
+// c - L - u - v >= 0, float64), one row insertion after the other, each a Dijkstra search over the sparse
+// adjacency in which the whole block relaxes and selects: "leave this tree row unmatched" is a terminal of its own
+// beside "reach a free column".  Ties are resolved towards the lower column / the row reached first, so the result does
+// not depend on the order in which the pairs were collected.  Rows are the stage's still-open rows, columns its
+// still-free columns: what the shared-memory solver has settled before (pairs alone in their row and column, small
+// components) stays settled - components are independent.
+// ---------------------------------------------------------------------------------------
+struct AssignGlobal {
+  int e_cap;
+  int* row_start;           // (T + 1)
+  int* row_col;             // (T)   column matched to the row, -1 = none
+  double* u;                // (T)
+  double* v;                // (S)
+  double* dist;             // (S)
+  int* pred;                // (S)   tree row a column was reached from
+  int* col_row;             // (S)   row matched to the column, -1 = free
+  int* scanned;             // (S)
+  float* e_cost;            // (e_cap) 1 - IoU, float32 as the reference hands it to lap
+  unsigned short* e_col;    // (e_cap)
+};
+
+inline __host__ __device__ size_t assign_global_fixed_bytes(int capacity, int det_stride) {
+  return (static_cast<size_t>(capacity) + 1) * 4 + static_cast<size_t>(capacity) * (4 + 8) + static_cast<size_t>(det_stride) * (8 + 8 + 4 + 4 + 4) + 64;
+}
+
+__device__ __forceinline__ AssignGlobal assign_global_layout(unsigned char* base, size_t bytes, int capacity, int S) {
+  AssignGlobal g;
+  unsigned char* p = base;
+  g.u = reinterpret_cast<double*>(p); p += static_cast<size_t>(capacity) * 8;
+  g.v = reinterpret_cast<double*>(p); p += static_cast<size_t>(S) * 8;
+  g.dist = reinterpret_cast<double*>(p); p += static_cast<size_t>(S) * 8;
+  g.row_start = reinterpret_cast<int*>(p); p += (static_cast<size_t>(capacity) + 1) * 4;
+  g.row_col = reinterpret_cast<int*>(p); p += static_cast<size_t>(capacity) * 4;
+  g.pred = reinterpret_cast<int*>(p); p += static_cast<size_t>(S) * 4;
+  g.col_row = reinterpret_cast<int*>(p); p += static_cast<size_t>(S) * 4;
+  g.scanned = reinterpret_cast<int*>(p); p += static_cast<size_t>(S) * 4;
+  p = base + ((p - base + 15) & ~static_cast<size_t>(15));
+  const size_t left = bytes > static_cast<size_t>(p - base) ? bytes - (p - base) : 0;
+  g.e_cap = static_cast<int>(left / 6 > 0x3fffffff ? 0x3fffffff : left / 6);
+  g.e_cost = reinterpret_cast<float*>(p);
+  g.e_col = reinterpret_cast<unsigned short*>(p + static_cast<size_t>(g.e_cap) * 4);
+  return g;
+}
+
+// Returns 1 when the scratch cannot hold the stage's admissible pairs (nothing is changed then), else 0.
+template <int THREADS, typename RowBox>
+__device__ __forceinline__ int assign_general(RowBox row_box, const int T, const float4* s_box, const float* s_area,
+                                              const int* s_list, const int m, int* s_win, int* s_match, const double cost_limit,
+                                              const int flag, const ColBins* cb, const int* s_order, const bool binned, int* deg_row,
+                                              int* s_scan, const AssignGlobal g) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int kWarps = THREADS / 32;
+  const double kInf = 1e300;
+  __shared__ double r_val[32];
+  __shared__ int r_idx[32];
+  __shared__ double sh_d;      // distance of the row being scanned
+  __shared__ double sh_dummy;  // cheapest "leave a tree row unmatched" so far
+  __shared__ int sh_i, sh_dummy_row, sh_state, sh_total;
+  const int G = 8, sub = tid & (G - 1), groups = THREADS / G;  // lanes per row while collecting pairs
+
+  auto for_pairs = [&](const int t, auto&& fn) {  // admissible pairs (j, cost) of open row t over the stage's free columns
+    const float4 a = row_box(t);
+    const float area_a = box_area(a);
+    int p0 = 0, p1 = m;
+    if (binned) col_range(cb, a, &p0, &p1);
+    for (int p = p0 + sub; p < p1; p += G) {
+      const int j = binned ? s_order[p] : p, d = s_list[j];
+      if (s_win[j] != INT_MAX) continue;
+      const float cst = __fsub_rn(1.f, pair_iou(a, area_a, s_box[d], s_area[d]));
+      if (static_cast<double>(cst) < cost_limit) fn(j, cst);
+    }
+  };
+  // ---- pairs per open row, CSR offsets ----
+  for (int t = tid; t < T; t += THREADS) deg_row[t] = 0;
+  __syncthreads();
+  for (int t0 = 0; t0 < T; t0 += groups) {
+    const int t = t0 + tid / G;
+    if (t < T && s_match[t] < 0) {
+      int n = 0;
+      for_pairs(t, [&](int, float) { ++n; });
+      if (n) atomicAdd(&deg_row[t], n);
+    }
+  }
+  __syncthreads();
+  int run = 0;
+  for (int t0 = 0; t0 < T; t0 += THREADS) {
+    const int t = t0 + tid;
+    int tot;
+    const int off = run + block_exclusive_sum<THREADS>(t < T ? deg_row[t] : 0, s_scan, &tot);
+    if (t < T) g.row_start[t] = off;
+    run += tot;
+  }
+  if (tid == 0) {
+    g.row_start[T] = run;
+    sh_total = run;
+  }
+  __syncthreads();
+  const int E = sh_total;
+  if (E > g.e_cap) return 1;
+  for (int t = tid; t < T; t += THREADS) deg_row[t] = 0;  // now the fill cursor of the row
+  for (int j = tid; j < m; j += THREADS) {
+    g.v[j] = 0.0;
+    g.col_row[j] = -1;
+  }
+  __syncthreads();
+  for (int t0 = 0; t0 < T; t0 += groups) {
+    const int t = t0 + tid / G;
+    if (t < T && s_match[t] < 0) {
+      const int base = g.row_start[t];
+      for_pairs(t, [&](int j, float cst) {
+        const int k = base + atomicAdd(&deg_row[t], 1);
+        g.e_col[k] = static_cast<unsigned short>(j);
+        g.e_cost[k] = cst;
+      });
+    }
+  }
+  __syncthreads();
+  // u = the row's cheapest shifted cost (<= 0): every reduced cost starts non-negative
+  for (int t = tid; t < T; t += THREADS) {
+    double lo = 0.0;
+    for (int k = g.row_start[t]; k < g.row_start[t + 1]; ++k) lo = fmin(lo, static_cast<double>(g.e_cost[k]) - cost_limit);
+    g.u[t] = lo;
+    g.row_col[t] = -1;
+  }
+  __syncthreads();
+  // ---- one augmentation per open row that has a pair ----
+  for (int i0 = 0; i0 < T; ++i0) {
+    if (g.row_start[i0] == g.row_start[i0 + 1]) continue;  // block-uniform (global memory written before the barrier above)
+    for (int j = tid; j < m; j += THREADS) {
+      g.dist[j] = kInf;
+      g.scanned[j] = 0;
+    }
+    if (tid == 0) {
+      sh_i = i0;
+      sh_d = 0.0;
+      sh_dummy = kInf;
+      sh_dummy_row = -1;
+      sh_state = 0;
+    }
+    __syncthreads();
+    while (true) {
+      const int i = sh_i;
+      const double di = sh_d, ui = g.u[i];
+      // relax the row's pairs (few: one warp is plenty); note the cheaper way out through the row itself
+      if (warp == 0) {
+        for (int k = g.row_start[i] + lane; k < g.row_start[i + 1]; k += 32) {
+          const int j = g.e_col[k];
+          if (g.scanned[j]) continue;
+          const double nd = di + ((static_cast<double>(g.e_cost[k]) - cost_limit) - ui - g.v[j]);
+          if (nd < g.dist[j]) {
+            g.dist[j] = nd;
+            g.pred[j] = i;
+          }
+        }
+        if (lane == 0) {
+          const double dd = di - ui;  // the row's own way out: reduced cost 0 - u_i
+          if (dd < sh_dummy) {
+            sh_dummy = dd;
+            sh_dummy_row = i;
+          }
+        }
+      }
+      __syncthreads();
+      // nearest unscanned column (ties: the lower column)
+      double best = kInf;
+      int bj = INT_MAX;
+      for (int j = tid; j < m; j += THREADS) {
+        const double dj = g.dist[j];
+        if (!g.scanned[j] && (dj < best || (dj == best && j < bj))) {
+          best = dj;
+          bj = j;
+        }
+      }
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        const double ob = __shfl_xor_sync(kFull, best, d);
+        const int oj = __shfl_xor_sync(kFull, bj, d);
+        if (ob < best || (ob == best && oj < bj)) {
+          best = ob;
+          bj = oj;
+        }
+      }
+      if (lane == 0) {
+        r_val[warp] = best;
+        r_idx[warp] = bj;
+      }
+      __syncthreads();
+      if (warp == 0) {
+        best = lane < kWarps ? r_val[lane] : kInf;
+        bj = lane < kWarps ? r_idx[lane] : INT_MAX;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+          const double ob = __shfl_xor_sync(kFull, best, d);
+          const int oj = __shfl_xor_sync(kFull, bj, d);
+          if (ob < best || (ob == best && oj < bj)) {
+            best = ob;
+            bj = oj;
+          }
+        }
+        if (lane == 0) {
+          if (!(best < sh_dummy)) {
+            sh_state = 1;  // the path ends in a tree row that stays unmatched
+          } else if (g.col_row[bj] < 0) {
+            sh_state = 2;  // ... or in a free column
+            r_idx[0] = bj;
+            sh_d = best;
+          } else {
+            g.scanned[bj] = 1;
+            sh_i = g.col_row[bj];
+            sh_d = best;
+          }
+        }
+      }
+      __syncthreads();
+      if (sh_state) break;
+    }
+    // potentials: every tree node moves by (final distance - its own distance)
+    const double D = sh_state == 1 ? sh_dummy : sh_d;
+    for (int j = tid; j < m; j += THREADS) {
+      if (g.scanned[j]) {
+        const double delta = D - g.dist[j];
+        g.v[j] -= delta;
+        g.u[g.col_row[j]] += delta;
+      }
+    }
+    if (tid == 0) g.u[i0] += D;
+    __syncthreads();
+    if (tid == 0) {  // flip the path
+      int j;
+      if (sh_state == 1) {
+        const int ik = sh_dummy_row;
+        j = g.row_col[ik];
+        g.row_col[ik] = -1;
+        if (ik == i0) j = -1;
+      } else {
+        j = r_idx[0];
+      }
+      while (j >= 0) {
+        const int i = g.pred[j];
+        const int jn = g.row_col[i];
+        g.row_col[i] = j;
+        g.col_row[j] = i;
+        j = i == i0 ? -1 : jn;
+      }
+    }
+    __syncthreads();
+  }
+  for (int t = tid; t < T; t += THREADS) {
+    const int j = g.row_col[t];
+    if (s_match[t] < 0 && g.row_start[t] != g.row_start[t + 1] && j >= 0) {
+      s_match[t] = s_list[j] | flag;
+      s_win[j] = t;
+    }
+  }
+  __syncthreads();
+  return 0;
+}
+
 template <int THREADS>
 __device__ __forceinline__ int associate_optimal(const TrackPrefetch* pf, const float4* __restrict__ g_box,
                                                  const float* kf_mean, const int32_t* g_tsu, size_t row0, int T,
                                                  const float4* s_box, const float* s_area, const int* s_list, int m,
                                                  int* s_win, int* s_match, const double cost_limit, int flag,
-                                                 AssignScratch* sc, int* deg_row, int* deg_col, ColBins* cb, int* s_order) {
+                                                 AssignScratch* sc, int* deg_row, int* deg_col, ColBins* cb, int* s_order,
+                                                 int* s_scan, unsigned char* scratch, size_t scratch_bytes, int capacity, int det_stride) {
   const int tid = threadIdx.x;
   // admissible pairs have IoU > match_thresh: with a positive threshold (cost_limit < 1) they intersect
   const bool binned = m >= kBinMinCols && cost_limit < 1.0;  // block-uniform
@@ -516,8 +784,8 @@ __device__ __forceinline__ int associate_optimal(const TrackPrefetch* pf, const 
   __syncthreads();
   // ---- 3. the rest, component by component (thread 0) ----
   if (tid == 0) {
-    if (sc->n_edges > kAssignMaxEdges) sc->limit_hit = 1;
-    for (int e0 = 0; e0 < E; ++e0) {
+    if (sc->n_edges > kAssignMaxEdges) sc->limit_hit = 1;  // the list is incomplete: components cannot be told from it
+    for (int e0 = 0; e0 < E && !sc->limit_hit; ++e0) {
       if (sc->edge_cost[e0] < 0.f) continue;
       int *rows = sc->rows, *cols = sc->cols, r = 0, c = 0;
       float* cost = sc->cost;
@@ -572,7 +840,14 @@ __device__ __forceinline__ int associate_optimal(const TrackPrefetch* pf, const 
     }
   }
   __syncthreads();
-  return sc->limit_hit;
+  if (!sc->limit_hit) return 0;
+  // beyond the shared-memory solver: everything still open goes to the general one, if the caller gave it scratch
+  if (!scratch || scratch_bytes < assign_global_fixed_bytes(capacity, det_stride)) return 1;
+  auto row_box = [&](const int t) {
+    return t < kTrackPrefRows ? pf->abox[t] : (kf_mean ? kalman_predicted_box(kf_mean, row0 + t, g_tsu[row0 + t]) : g_box[t]);
+  };
+  return assign_general<THREADS>(row_box, T, s_box, s_area, s_list, m, s_win, s_match, cost_limit, flag, cb, s_order, binned, deg_row,
+                                 s_scan, assign_global_layout(scratch, scratch_bytes, capacity, det_stride));
 }
 
 // One stream.  `smem_raw`: track_smem_bytes(det_stride, capacity) bytes of shared memory,
@@ -600,6 +875,7 @@ __device__ __forceinline__ void track_stream(const TrackArgs& a, const int b, un
   int* s_deg_col = s_deg_row + cap;                     // S
   AssignScratch* s_assign = reinterpret_cast<AssignScratch*>((reinterpret_cast<uintptr_t>(s_deg_col + S) + 15) & ~static_cast<uintptr_t>(15));
   const bool optimal = WITH_OPTIMAL && a.assignment == RTM_ASSIGN_OPTIMAL;
+  unsigned char* scratch = a.assign_scratch ? a.assign_scratch + static_cast<size_t>(b) * a.assign_scratch_per_stream : nullptr;
 
   const size_t row0 = static_cast<size_t>(b) * cap;
   const size_t det0 = static_cast<size_t>(b) * S;
@@ -678,7 +954,7 @@ __device__ __forceinline__ void track_stream(const TrackArgs& a, const int b, un
   if (T > 0 && H > 0) {
     if (WITH_OPTIMAL && optimal) {
       if (associate_optimal<THREADS>(pf, in_box, a.kf_mean_in, a.tin.time_since_update, row0, T, s_box, s_area, s_hi, H, s_win,
-                                     s_match, a.cost_limit, 0, s_assign, s_deg_row, s_deg_col, s_bins, s_order))
+                                     s_match, a.cost_limit, 0, s_assign, s_deg_row, s_deg_col, s_bins, s_order, s_scan, scratch, a.assign_scratch_per_stream, cap, S))
         st |= RTM_STATUS_ASSIGN_LIMIT;
     } else {
       associate<THREADS>(pf, in_box, a.kf_mean_in, a.tin.time_since_update, row0, T, s_box, s_area, s_hi, H, s_win, s_match,
@@ -692,7 +968,7 @@ __device__ __forceinline__ void track_stream(const TrackArgs& a, const int b, un
   if (T > 0 && L > 0) {
     if (WITH_OPTIMAL && optimal) {
       if (associate_optimal<THREADS>(pf, in_box, a.kf_mean_in, a.tin.time_since_update, row0, T, s_box, s_area, s_lo, L, s_win,
-                                     s_match, a.cost_limit, kStage2Flag, s_assign, s_deg_row, s_deg_col, s_bins, s_order))
+                                     s_match, a.cost_limit, kStage2Flag, s_assign, s_deg_row, s_deg_col, s_bins, s_order, s_scan, scratch, a.assign_scratch_per_stream, cap, S))
         st |= RTM_STATUS_ASSIGN_LIMIT;
     } else {
       associate<THREADS>(pf, in_box, a.kf_mean_in, a.tin.time_since_update, row0, T, s_box, s_area, s_lo, L, s_win, s_match,

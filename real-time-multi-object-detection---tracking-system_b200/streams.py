@@ -245,7 +245,7 @@ class StreamBatch:
                  agnostic_nms: bool = False, track_thresh: float = 0.5, track_buffer: int = 30,
                  match_thresh: float = 0.8, max_tracks: int = 1024, max_events: Optional[int] = None,
                  det_slots: Optional[int] = None, device="cuda:0", use_kalman: bool = False,
-                 assignment: str = "greedy") -> None:
+                 assignment: str = "greedy", max_pairs: Optional[int] = None) -> None:
         import torch
         self.lib = _lib.lib()
         self.device = torch.device(device)
@@ -277,6 +277,13 @@ class StreamBatch:
             # assignment: "greedy" = what the reference runs without `lap` (and here); "lapjv" = its lap branch
             self.assignment = assignment
             _lib.track_options(0.5, 0.8, 30, assignment)          # validates the name
+            # "lapjv": scratch of the general solver (stages with many admissible pairs or large conflict components);
+            # max_pairs = admissible (track, detection) pairs a stage of one stream may hold
+            self.assign_scratch = None
+            if assignment == "lapjv":
+                pairs = int(max_pairs if max_pairs is not None else 16 * max(self.det_stride, 64))
+                n = self.lib.rtm_assign_scratch_bytes(B, int(max_tracks), self.det_stride, pairs)
+                self.assign_scratch = torch.zeros(n, dtype=torch.uint8, device=self.device)
             self.tables = [DeviceTrackTable(B, max_tracks, self.device, kalman=self.use_kalman) for _ in range(2)]
             self.src_row = torch.zeros(B, max_tracks, **i32)
             self.zones = None
@@ -365,6 +372,7 @@ class StreamBatch:
             io.kalman_out = C.pointer(self.tables[self.cur ^ 1].kalman)
         if self.assignment == "lapjv":
             io.assignment, io.cost_limit = _lib.ASSIGN_OPTIMAL, 1 - self.match_thresh      # tracker.py:170
+            io.assign_scratch, io.assign_scratch_bytes = self.assign_scratch.data_ptr(), self.assign_scratch.numel()
         return io
 
     def _advance(self) -> None:
@@ -415,7 +423,8 @@ class StreamBatch:
             res = self._res[self.cur ^ 1]
             want_assign = S == self.det_stride
             opt = _lib.track_options(self.track_thresh, self.match_thresh, self.track_buffer, self.assignment,
-                                     tin.kalman if self.use_kalman else None, tout.kalman if self.use_kalman else None)
+                                     tin.kalman if self.use_kalman else None, tout.kalman if self.use_kalman else None,
+                                     self.assign_scratch)
             _lib.check(self.lib.rtm_track_step_ex(
                 C.byref(tin.struct), C.byref(tout.struct), det_xyxy.data_ptr(), det_conf.data_ptr(),
                 det_cls.data_ptr(), det_count.data_ptr(), S, C.byref(opt),

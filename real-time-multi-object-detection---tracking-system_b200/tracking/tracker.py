@@ -71,6 +71,10 @@ class _ByteTrackCore:
             self._det_kind = torch.zeros(1, self.max_dets, dtype=torch.int32, device=self.device)
             self._src_row = torch.zeros(1, max_tracks, dtype=torch.int32, device=self.device)
             self._status = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self._assign_scratch = None                      # "lapjv": scratch of the general solver (crowds, low thresholds)
+            if assignment == "lapjv":
+                n = self._lib.rtm_assign_scratch_bytes(1, int(max_tracks), self.max_dets, 64 * self.max_dets)
+                self._assign_scratch = torch.zeros(n, dtype=torch.uint8, device=self.device)
 
     # -- the reference's attribute names ------------------------------------
     @property
@@ -95,7 +99,8 @@ class _ByteTrackCore:
             self._det_count.fill_(n)
             tin, tout = self._tables[self._cur], self._tables[self._cur ^ 1]
             opt = _lib.track_options(self.track_thresh, self.match_thresh, self.track_buffer, self.assignment,
-                                     tin.kalman if self.use_kalman else None, tout.kalman if self.use_kalman else None)
+                                     tin.kalman if self.use_kalman else None, tout.kalman if self.use_kalman else None,
+                                     self._assign_scratch)
             _lib.check(self._lib.rtm_track_step_ex(
                 C.byref(tin.struct), C.byref(tout.struct), self._det_xyxy.data_ptr(),
                 self._det_conf.data_ptr(), self._det_cls.data_ptr(), self._det_count.data_ptr(),

@@ -224,3 +224,30 @@ def test_active_tracks_is_a_view_not_a_step(pkg):
         a = trk.active_tracks()
         b = trk.active_tracks()
         assert len(a) == len(b) == 1 and a[0].trail == b[0].trail and len(a[0].trail) == f + 1
+
+
+@pytest.mark.parametrize("case", ["thresh_0.3", "thresh_0.05", "no_scratch"])
+def test_optimal_assignment_has_no_size_limits(pkg, case):
+    """lap.lapjv solves a problem of any size (tracker.py:168-181).  In a 1000-object crowd at match_thresh = 0.05 a
+    stage holds ~3,500 admissible pairs (more in later frames) in conflict components of up to ~750 rows (at 0.3: 1,200
+    pairs, components of 23): beyond the shared-memory solver (4096 pairs, 32 x 32 components) the general solver in
+    global scratch takes over - same state and assignments as the scipy emulation, no status bit.  Without scratch the same
+    clip reports RTM_STATUS_ASSIGN_LIMIT instead of guessing."""
+    import torch
+    kw = pkg.synth.dense_crowd_kwargs(1000)
+    if case != "no_scratch":
+        thr = float(case.split("_")[1])
+        sb = run_batch_against_oracle(pkg, B=2, F=5, slots=1024, clip_kw=kw, max_tracks=4096, seed=77,
+                                      track_kw=dict(assignment="lapjv", match_thresh=thr, max_pairs=200_000),
+                                      oracle_kw=dict(assign=tracker_ref.assign_lapjv_emulated, match_thresh=thr))
+        assert not sb.status.cpu().numpy().any()
+        return
+    xyxy, conf, cls, count = pkg.synth.scripted_batch(1, 3, 1024, seed=77, **kw)
+    sb = pkg.StreamBatch(1, None, max_det=1024, max_tracks=4096, max_pairs=0, assignment="lapjv", match_thresh=0.05)
+    sb.assign_scratch = None                                        # a caller of the C ABI that passes no scratch
+    sb._io_cache.clear()
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(sb.device)
+    with pytest.raises(pkg.RtmError):
+        for f in range(3):
+            sb.track_only(t(xyxy[f]), t(conf[f]), t(cls[f]), t(count[f]), now=0.0)
+            sb.check_status()
