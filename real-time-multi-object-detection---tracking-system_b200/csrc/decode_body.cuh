@@ -107,6 +107,7 @@ struct TmaGeom {
   int evict_first;    // L2 evict-first hint on the tile loads
   int static_rounds;  // ring rounds with the static schedule (tile = blockIdx + k * grid) before tickets take over
   int trigger;        // release programmatic dependents (the next scan on the same stream) at once
+  int l2_ahead;       // > 0: whoever draws ticket t also prefetches tile t + l2_ahead into L2 (a ring cycle of all teams)
 };
 
 struct TmaMaps {
@@ -341,6 +342,21 @@ __device__ __forceinline__ void tma_scan_cta(const TmaMaps& maps, const TmaGeom&
                       &full_bar[s0 + s], x, 0, b, policy);
       };
       auto wait_empty = [&](int s, int parity) { mbar_wait(&empty_bar[s0 + s], parity); };
+      // L2 prefetch of the tile that will be drawn `l2_ahead` tickets from now, by whichever team that will be: every
+      // tile beyond the first ones is prefetched exactly once, about one ring cycle before its TMA load, which then
+      // finds it in L2 - the ring's two stages per team cover an L2 hit, not a DRAM access under load
+      auto prefetch_l2 = [&](int t) {
+        if (tg.l2_ahead <= 0) return;
+        t += tg.l2_ahead;
+        if (t >= tg.total_tiles) return;
+        const int b = t / tps, r = t - b * tps;
+        const int li = r >= tb2 ? 2 : (r >= tb1 ? 1 : 0);
+        const int x = (r - (li == 2 ? tb2 : (li == 1 ? tb1 : 0))) * kTileW;
+        asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(
+                         reinterpret_cast<uint64_t>(li == 0 ? &map0 : (li == 1 ? &map1 : &map2))),
+                     "r"(x), "r"(0), "r"(b)
+                     : "memory");
+      };
       // first round of the ring: tiles vcta + k * vgrid, no ticket needed; the tickets of the
       // second round are drawn meanwhile (all in flight together), later ones one ring cycle ahead
       const int nstatic = spt * tg.static_rounds;
@@ -367,12 +383,18 @@ __device__ __forceinline__ void tma_scan_cta(const TmaMaps& maps, const TmaGeom&
           tk[k] = (k < spt && spt + k >= nstatic) ? atomicAdd(ws.tile_counter, 1) : 0;
 #pragma unroll
         for (int k = 0; k < kMaxStages; ++k)
-          if (k < spt) ctl->next[s0 + k] = spt + k < nstatic ? vcta + (spt + k) * vgrid : dyn0 + tk[k];
+          if (k < spt) {
+            ctl->next[s0 + k] = spt + k < nstatic ? vcta + (spt + k) * vgrid : dyn0 + tk[k];
+            if (spt + k >= nstatic) prefetch_l2(dyn0 + tk[k]);
+          }
         int issued = 2 * spt;  // tiles of this team that have a source by now
         int s = 0, fill = 1, drawn = 0, drawn_for = -1;  // ticket in flight and the stage it is for
         while (true) {
           wait_empty(s, (fill - 1) & 1);
-          if (drawn_for >= 0) ctl->next[s0 + drawn_for] = dyn0 + drawn;  // arrived while the ring drained
+          if (drawn_for >= 0) {
+            ctl->next[s0 + drawn_for] = dyn0 + drawn;  // arrived while the ring drained
+            prefetch_l2(dyn0 + drawn);
+          }
           const int t = ctl->next[s0 + s];
           if (t >= tg.total_tiles) {
             ctl->tile[s0 + s] = make_int4(-1, 0, 0, 0);

@@ -743,6 +743,7 @@ int plan_tma_scan(const void* p3, const void* p4, const void* p5, const HeadGeom
   static const int evict_env = env_int("RTM_TMA_EVICT_FIRST", 1);
   tg.evict_first = evict_env;
   tg.trigger = 0;
+  tg.l2_ahead = 0;
   tg.stages = 0;
   if (tg.tile_bytes % 128 != 0) return 0;
   return 1;
