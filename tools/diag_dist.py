@@ -25,6 +25,7 @@ ap.add_argument("--side-stream", action="store_true")
 ap.add_argument("--steps", type=int, default=20)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--streams", type=int, default=64)
+ap.add_argument("--frames", type=int, default=4)
 ap.add_argument("--tag", default="")
 a = ap.parse_args()
 
@@ -47,7 +48,7 @@ if a.dist:
 pkg = importlib.import_module("rtmodt_b200")
 from rtmodt_b200.workload import PostBackboneWorkload
 
-S, F, K = a.streams, 4, a.steps
+S, F, K = a.streams, a.frames, a.steps
 wl = PostBackboneWorkload(S, F, first_stream=rank * S, device=dev, dtype=torch.bfloat16)
 sb = pkg.StreamBatch(S, wl.zones, src_hw=(1080, 1920), classes=[0, 1, 2, 3, 5, 7], max_tracks=512, device=dev)
 f = 0
