@@ -412,7 +412,11 @@ def run_b200(args):
             batch.check_status()
             return float(ms.item())
 
+        # warm-up: the W steps asked for, then one untimed rehearsal of the K-step region itself (the first region after
+        # other kernels have run is 1 - 1.5 us per step slower than every later one: instruction cache, TLB)
         run_steps(sb, wl.heads, W, True)
+        barrier()
+        run_steps(sb, wl.heads, K, True)
         ms_total = timed(sb, wl.heads, True)
         value = total_streams * K / (ms_total / 1e3)
         run_steps(sb, wl.heads, W)
@@ -508,7 +512,7 @@ def run_b200(args):
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "rehearsal_steps": K,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": scaling_label(world), "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args, total_streams),
             "single_stream": {"value": total_streams * K / (ms_single / 1e3), "ms_per_step": ms_single / K,
@@ -650,18 +654,18 @@ def e2e_bench(pkg, wl, sb, f0, K, W, total_streams, world, dev, pinned_frames=4)
 
 def modes_bench(pkg, wl, dev, S, F, steps=100):
     """The same workload with the tracker's opt-in modes (neither is the reference's default behaviour
-    here): use_kalman=True (fused path) and assignment="lapjv" (three launches per step)."""
+    here): use_kalman=True and assignment="lapjv", both inside the step kernel, steps back to back (heads_ready)."""
     import torch
     out = {}
     for name, kw in (("kalman", dict(use_kalman=True)), ("lapjv", dict(assignment="lapjv"))):
         sb = pkg.StreamBatch(S, wl.zones, src_hw=(1080, 1920), classes=WANTED, max_tracks=512, device=dev, **kw)
         for f in range(20):
-            sb.step(wl.heads[f % F], now=T0 + f / FPS, frame_id=f)
+            sb.step(wl.heads[f % F], now=T0 + f / FPS, frame_id=f, heads_ready=True)
         torch.cuda.synchronize(dev)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for f in range(20, 20 + steps):
-            sb.step(wl.heads[f % F], now=T0 + f / FPS, frame_id=f)
+            sb.step(wl.heads[f % F], now=T0 + f / FPS, frame_id=f, heads_ready=True)
         b.record()
         b.synchronize()
         sb.check_status()
