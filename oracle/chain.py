@@ -26,7 +26,7 @@ def event_key(e):
 
 
 def run_chain_parity(sb, get_heads, get_host_heads, zones, num_frames, src_hw=(1080, 1920), classes=None,
-                     t0=1_700_000_000.0, fps=30.0, heads_ready=None, digests=True):
+                     t0=1_700_000_000.0, fps=30.0, heads_ready=None, digests=True, imgsz=(640, 640)):
     """Steps ``sb`` (a fresh StreamBatch over n streams) through ``num_frames`` frames and compares every stream
     with the oracle chain after every frame.
 
@@ -46,7 +46,7 @@ def run_chain_parity(sb, get_heads, get_host_heads, zones, num_frames, src_hw=(1
         got = sb.read_detections()
         tracks, next_id = sb.read_tracks()
         evs = sb.read_events()
-        ref = detect_ref.detect_post(get_host_heads(f), src_hw, classes=classes)
+        ref = detect_ref.detect_post(get_host_heads(f), src_hw, imgsz=imgsz, classes=classes)
         for s in range(n):
             r, g = ref[s], got[s]
             if digests:

@@ -357,3 +357,43 @@ def test_state_export_import_resumes_bit_exactly(pkg, kalman):
     assert sum(len(t) for t in ta) > 10
     with pytest.raises(pkg.RtmError):
         make(2, zones[:2]).import_state(blob)
+
+
+@pytest.mark.parametrize("case", ["f16", "rectangle_384x640", "crowded_over_1024_candidates"])
+@pytest.mark.parametrize("heads_ready", [None, True])
+def test_step_kernel_variants_match_the_oracle_chain(pkg, case, heads_ready):
+    """The one-launch step beyond the bench shape: f16 head tensors, the stride-32 rectangle ultralytics uses for .pt
+    models (1080p -> 384 x 640, 5040 anchors), and frames whose candidates outgrow the shared-memory NMS (> 1024 per
+    stream: the workspace's spill arrays) - each held to the oracle chain frame by frame, in both step modes."""
+    import torch
+    from oracle import chain
+    B, F = 3, 6
+    dev = torch.device("cuda", 0)
+    imgsz = (384, 640) if case.startswith("rectangle") else (640, 640)
+    tdt = torch.float16 if case == "f16" else torch.bfloat16
+    n_obj = 130 if case.startswith("crowded") else 14
+    rng = np.random.default_rng(77)
+    wh = np.stack([rng.uniform(30, 110, (B, n_obj)), rng.uniform(30, 120, (B, n_obj))], -1)
+    c = np.stack([rng.uniform(60, imgsz[1] - 60, (B, n_obj)), rng.uniform(60, imgsz[0] - 60, (B, n_obj))], -1)
+    v = rng.uniform(-1.5, 1.5, (B, n_obj, 2))
+    cls = rng.choice(np.asarray(WANTED), (B, n_obj))
+    frames = []
+    for f in range(F):
+        c = c + v
+        levels = [[], [], []]
+        for b in range(B):
+            boxes = np.concatenate([c[b] - wh[b] / 2, c[b] + wh[b] / 2], 1)
+            for l, t in enumerate(pkg.synth.plant_head(rng, boxes, cls[b], imgsz=imgsz, distractor_frac=0.0, logit_range=(0.0, 3.0))):
+                levels[l].append(t)
+        frames.append([torch.from_numpy(np.stack(l)).to(tdt) for l in levels])
+    dev_frames = [[t.to(dev).contiguous() for t in fr] for fr in frames]
+    zones = [pkg.synth.make_zones(seed=b, num_zones=4, width=1920, height=1080, dwell_time_sec=0.1, cooldown_sec=0.2) for b in range(B)]
+    sb = pkg.StreamBatch(B, zones, src_hw=(1080, 1920), imgsz=imgsz, classes=WANTED, max_tracks=512, device=dev)
+    res = chain.run_chain_parity(sb, lambda f: dev_frames[f], lambda f: [t.float() for t in frames[f]], zones, F,
+                                 src_hw=(1080, 1920), classes=WANTED, heads_ready=heads_ready, imgsz=imgsz, digests=False)
+    sb.close()
+    assert res["ok"], res
+    assert res["detections_checked"] > B * F * 8
+    if case.startswith("crowded"):
+        ws_cand = sum(int((torch.sigmoid(t[:, 64:].float()).amax(1) > 0.35).sum()) for t in frames[0]) / B
+        assert ws_cand > 1024, ws_cand                              # the spill path was the one that ran
