@@ -71,3 +71,32 @@ def test_nms_params_class_mask(pkg):
     assert p.class_mask[0] == 0b10101111 and p.class_mask[1] == 0
     p = pkg._lib.make_nms_params(classes=None, num_classes=80)
     assert p.class_mask[0] == 0xFFFFFFFF and p.class_mask[2] == 0xFFFF and p.class_mask[3] == 0
+
+
+def test_ctypes_structs_match_the_header_as_a_c_compiler_lays_it_out(pkg, tmp_path):
+    """include/rtmodt_b200.h is plain C: gcc compiles it, prints sizeof / offsetof of every struct the Python binding
+    mirrors, and the numbers have to agree with the ctypes Structures field by field."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    L = pkg._lib
+    pairs = [("rtm_nms_params", L.NmsParams), ("rtm_track_table", L.TrackTable), ("rtm_kalman_state", L.KalmanState),
+             ("rtm_track_options", L.TrackOptions), ("rtm_zone_set", L.ZoneSet), ("rtm_zone_state", L.ZoneState),
+             ("rtm_zone_event", L.ZoneEventRec), ("rtm_step_io", L.StepIO), ("rtm_step_host_io", L.StepHostIO)]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "rtmodt_b200.h"', 'int main(void) {']
+    for cname, cls in pairs:
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, cls in pairs:
+        assert int(got[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
