@@ -77,6 +77,18 @@ def timed(ready):
     return e0.elapsed_time(e1) * 1e3 / K
 
 
+def host_cost(ready, n=300):
+    """wall time of the issuing loop alone (the GPU is still busy when it returns unless the host is the slower side)"""
+    import time
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    run(n, ready)
+    t1 = time.perf_counter()
+    torch.cuda.synchronize(dev)
+    t2 = time.perf_counter()
+    return (t1 - t0) / n * 1e6, (t2 - t0) / n * 1e6
+
+
 def body():
     out = {}
     for name, ready in (("async", True), ("single", None)):
@@ -100,7 +112,8 @@ if sampler:
 sb.check_status()
 print(f"diag rank={rank}/{world} dist={int(a.dist)} sampler={int(a.sampler)} side={int(a.side_stream)} K={K} "
       f"maxconn={os.environ.get('CUDA_DEVICE_MAX_CONNECTIONS', '-')} {a.tag} "
-      + " ".join(f"{k}: min {v[0]:.2f} med {v[len(v) // 2]:.2f} max {v[-1]:.2f} us/step" for k, v in res.items()), flush=True)
+      + " ".join(f"{k}: min {v[0]:.2f} med {v[len(v) // 2]:.2f} max {v[-1]:.2f} us/step" for k, v in res.items())
+      + " | issue loop %.1f us/step (loop + drain %.1f)" % host_cost(True), flush=True)
 if a.dist:
     dist.barrier()
     dist.destroy_process_group()
