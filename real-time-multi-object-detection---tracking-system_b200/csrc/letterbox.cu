@@ -210,6 +210,100 @@ __global__ void __launch_bounds__(256) letterbox_decimate3_kernel(const Letterbo
   }
 }
 
+// The same gather for 16-bit outputs, twice as wide: a thread produces 32 consecutive output pixels from nine aligned
+// 32-byte loads (LDG.E.256: every lane owns whole sectors - the 16-byte version asked L1 for 32 half-sectors per
+// instruction, ncu: l1tex at 75 % of its peak) and writes each plane as two 32-byte stores (whole sectors again; the
+// 16-byte stores sent every sector to L2 twice, half filled).  u8 -> T(v / 255) without the table: v * 0x3b808081
+// (the float next to 1 / 255) rounds to the same bf16 / f16 as the IEEE quotient for all 256 values
+// (tests/test_gpu_detect.py checks the kernel against cv2 + torch bit for bit), so a byte costs one PRMT that plants it
+// in the mantissa of 2^23, one FFMA and half a pack instruction, and no shared-memory lookup with random bank conflicts.
+constexpr int kWidePix = 32;
+
+__device__ __forceinline__ void ldg256_stream(const void* p, uint32_t* w) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint32_t* w) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+               "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
+template <typename T>
+__device__ __forceinline__ uint32_t pack_unit_pair(float lo, float hi);
+template <>
+__device__ __forceinline__ uint32_t pack_unit_pair<__nv_bfloat16>(float lo, float hi) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+template <>
+__device__ __forceinline__ uint32_t pack_unit_pair<__half>(float lo, float hi) {
+  const __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+// byte k (compile-time) of word x as a float in [0, 1]: rn(v * c), c = 0x3b808081
+template <int K>
+__device__ __forceinline__ float unit_from_byte(uint32_t x) {
+  const float c = __uint_as_float(0x3b808081u);
+  const float t = __uint_as_float(__byte_perm(x, 0x4B000000u, 0x7650 | K));  // 2^23 + v, exact
+  return __fmaf_rn(t, c, -8388608.f * c);                                       // 2^23 * c is exact: = rn(v * c)
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) letterbox_decimate3_wide_kernel(const LetterboxArgs a) {
+  static_assert(sizeof(T) == 2, "16-bit outputs only");
+  const int groups_per_row = a.out_w / kWidePix;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= groups_per_row * a.out_h) return;
+  const int b = blockIdx.y;
+  const int oy = g / groups_per_row;
+  const int ox0 = (g - oy * groups_per_row) * kWidePix;
+  const int ry = oy - a.top, rx0 = ox0 - a.left;
+  T* out = static_cast<T*>(a.out) + (static_cast<long long>(b) * 3 * a.out_h + oy) * a.out_w + ox0;
+  const long long plane = static_cast<long long>(a.out_h) * a.out_w;
+  if (ry < 0 || ry >= a.new_h || rx0 < 0 || rx0 >= a.new_w) {  // whole groups are inside or outside (host-checked)
+    const float pad = unit_from_byte<0>(114u);
+    uint32_t p[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) p[e] = pack_unit_pair<T>(pad, pad);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      stg256(out + c * plane, p);
+      stg256(out + c * plane + 16, p);
+    }
+    return;
+  }
+  const uint8_t* row = a.frames + static_cast<long long>(b) * a.frame_stride + static_cast<long long>(3 * ry + 1) * a.row_stride;
+  const uint8_t* src = row + 9 * rx0;  // 9 * 32 g: 32-byte aligned; first tap at byte 3
+  uint32_t w[72];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) ldg256_stream(src + 32 * k, w + 8 * k);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {  // c: B, G, R in the source -> plane 2 - c
+    uint32_t o[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      const int o0 = 3 + 9 * (2 * e) + c, o1 = 3 + 9 * (2 * e + 1) + c;  // byte offsets inside the span: compile-time
+      float lo, hi;
+      switch (o0 & 3) {
+        case 0: lo = unit_from_byte<0>(w[o0 >> 2]); break;
+        case 1: lo = unit_from_byte<1>(w[o0 >> 2]); break;
+        case 2: lo = unit_from_byte<2>(w[o0 >> 2]); break;
+        default: lo = unit_from_byte<3>(w[o0 >> 2]); break;
+      }
+      switch (o1 & 3) {
+        case 0: hi = unit_from_byte<0>(w[o1 >> 2]); break;
+        case 1: hi = unit_from_byte<1>(w[o1 >> 2]); break;
+        case 2: hi = unit_from_byte<2>(w[o1 >> 2]); break;
+        default: hi = unit_from_byte<3>(w[o1 >> 2]); break;
+      }
+      o[e] = pack_unit_pair<T>(lo, hi);
+    }
+    stg256(out + (2 - c) * plane, o);
+    stg256(out + (2 - c) * plane + 16, o + 8);
+  }
+}
+
 // host copy of linear_tap (same IEEE operations) to recognise the pure 3 : 1 decimation
 bool taps_are_decimate3(int dst, double scale, int ssize, bool horizontal) {
   for (int d = 0; d < dst; ++d) {
@@ -265,6 +359,17 @@ int launch_letterbox(const uint8_t* frames, int num_streams, int src_h, int src_
       new_w % kDecPix == 0 && (reinterpret_cast<uintptr_t>(frames) & 15) == 0 && row_stride % 16 == 0 && frame_stride % 16 == 0 &&
       row_stride >= 9ll * new_w && taps_are_decimate3(new_w, a.scale_x, src_w, true) &&
       taps_are_decimate3(new_h, a.scale_y, src_h, false)) {
+    static const bool allow_wide = !(getenv("RTM_LETTERBOX_IMPL") && strcmp(getenv("RTM_LETTERBOX_IMPL"), "narrow") == 0);
+    if (allow_wide && out_dtype != RTM_F32 && out_w % kWidePix == 0 && left % kWidePix == 0 && new_w % kWidePix == 0 &&
+        (reinterpret_cast<uintptr_t>(frames) & 31) == 0 && row_stride % 32 == 0 && frame_stride % 32 == 0) {
+      const int wgroups = (out_w / kWidePix) * out_h;
+      dim3 wgrid((wgroups + 127) / 128, num_streams);
+      if (out_dtype == RTM_F16) letterbox_decimate3_wide_kernel<__half><<<wgrid, 128, 0, s>>>(a);
+      else if (out_dtype == RTM_BF16) letterbox_decimate3_wide_kernel<__nv_bfloat16><<<wgrid, 128, 0, s>>>(a);
+      else RTM_REQUIRE(false, "rtm_letterbox: unknown out_dtype %d", out_dtype);
+      RTM_LAUNCH_CHECK("letterbox_decimate3_wide_kernel");
+      return RTM_OK;
+    }
     const int dgroups = (out_w / kDecPix) * out_h;
     dim3 dgrid((dgroups + 255) / 256, num_streams);
     switch (out_dtype) {

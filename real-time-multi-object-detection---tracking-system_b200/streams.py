@@ -101,6 +101,15 @@ class DeviceTrackTable:
             self.kf_cov = torch.zeros(B, cap, 12, **f32)
             self.kalman = _lib.KalmanState(self.kf_mean.data_ptr(), self.kf_cov.data_ptr())
 
+    def grown(self, capacity: int) -> "DeviceTrackTable":
+        """A table of ``capacity`` >= this one's rows per stream holding the same rows and counters."""
+        big = DeviceTrackTable(self.num_streams, max(int(capacity), self.capacity), self.device, kalman=self.kalman is not None)
+        big.count.copy_(self.count)
+        big.next_id.copy_(self.next_id)
+        for k in self.FIELDS + (("kf_mean", "kf_cov") if self.kalman is not None else ()):
+            getattr(big, k)[:, :self.capacity] = getattr(self, k)
+        return big
+
     def to_host(self):
         """dict of host numpy arrays (synchronises)."""
         out = {k: getattr(self, k).cpu().numpy() for k in self.FIELDS}

@@ -56,25 +56,41 @@ class _ByteTrackCore:
         # "greedy": the branch of tracker.py:163-194 the reference takes when `lap` is missing (as here);
         # "lapjv": its lap.lapjv branch, solved exactly on the GPU
         self.assignment = assignment
+        self.auto_grow = True              # False: a full table raises RtmError instead (fixed memory)
         _lib.track_options(track_thresh, match_thresh, track_buffer, assignment)
         self._lib = _lib.lib()
         self.device = torch.device(device)
-        self.max_dets = int(max_dets)
         with torch.cuda.device(self.device):
             self._tables = [DeviceTrackTable(1, max_tracks, self.device, kalman=self.use_kalman) for _ in range(2)]
             self._cur = 0
-            self._det_xyxy = torch.zeros(1, self.max_dets, 4, dtype=torch.float32, device=self.device)
-            self._det_conf = torch.zeros(1, self.max_dets, dtype=torch.float32, device=self.device)
-            self._det_cls = torch.zeros(1, self.max_dets, dtype=torch.int32, device=self.device)
-            self._det_count = torch.zeros(1, dtype=torch.int32, device=self.device)
-            self._det_tid = torch.zeros(1, self.max_dets, dtype=torch.int32, device=self.device)
-            self._det_kind = torch.zeros(1, self.max_dets, dtype=torch.int32, device=self.device)
-            self._src_row = torch.zeros(1, max_tracks, dtype=torch.int32, device=self.device)
             self._status = torch.zeros(1, dtype=torch.int32, device=self.device)
-            self._assign_scratch = None                      # "lapjv": scratch of the general solver (crowds, low thresholds)
-            if assignment == "lapjv":
-                n = self._lib.rtm_assign_scratch_bytes(1, int(max_tracks), self.max_dets, 64 * self.max_dets)
-                self._assign_scratch = torch.zeros(n, dtype=torch.uint8, device=self.device)
+            self._alloc_slots(int(max_dets))
+
+    def _alloc_slots(self, max_dets: int) -> None:
+        """Detection slots and everything sized by them or by the table capacity."""
+        import torch
+        cap, dev = self._tables[0].capacity, self.device
+        self.max_dets = max_dets
+        self._det_xyxy = torch.zeros(1, max_dets, 4, dtype=torch.float32, device=dev)
+        self._det_conf = torch.zeros(1, max_dets, dtype=torch.float32, device=dev)
+        self._det_cls = torch.zeros(1, max_dets, dtype=torch.int32, device=dev)
+        self._det_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._det_tid = torch.zeros(1, max_dets, dtype=torch.int32, device=dev)
+        self._det_kind = torch.zeros(1, max_dets, dtype=torch.int32, device=dev)
+        self._src_row = torch.zeros(1, cap, dtype=torch.int32, device=dev)
+        self._assign_scratch = None                          # "lapjv": scratch of the general solver (crowds, low thresholds)
+        if self.assignment == "lapjv":
+            n = self._lib.rtm_assign_scratch_bytes(1, cap, max_dets, 64 * max_dets)
+            self._assign_scratch = torch.zeros(n, dtype=torch.uint8, device=dev)
+
+    def _grow(self, max_tracks: int, max_dets: int) -> None:
+        """The reference's lists have no capacity (tracker.py:55, 127-134): the tables double when a frame does not
+        fit.  The step that reported the overflow wrote the OTHER table only, so it is simply run again."""
+        import torch
+        with torch.cuda.device(self.device):
+            if max_tracks > self._tables[0].capacity:
+                self._tables = [t.grown(max_tracks) for t in self._tables]
+            self._alloc_slots(max(max_dets, self.max_dets))
 
     # -- the reference's attribute names ------------------------------------
     @property
@@ -90,27 +106,32 @@ class _ByteTrackCore:
         import torch
         n = len(confidence)
         if n > self.max_dets:
-            raise _lib.RtmError(f"{n} detections > max_dets={self.max_dets}")
-        with torch.cuda.device(self.device):
-            if n:
-                self._det_xyxy[0, :n] = torch.as_tensor(np.ascontiguousarray(xyxy, np.float32).reshape(n, 4)).to(self.device)
-                self._det_conf[0, :n] = torch.as_tensor(np.ascontiguousarray(confidence, np.float32)).to(self.device)
-                self._det_cls[0, :n] = torch.as_tensor(np.ascontiguousarray(class_id, np.int32)).to(self.device)
-            self._det_count.fill_(n)
-            tin, tout = self._tables[self._cur], self._tables[self._cur ^ 1]
-            opt = _lib.track_options(self.track_thresh, self.match_thresh, self.track_buffer, self.assignment,
-                                     tin.kalman if self.use_kalman else None, tout.kalman if self.use_kalman else None,
-                                     self._assign_scratch)
-            _lib.check(self._lib.rtm_track_step_ex(
-                C.byref(tin.struct), C.byref(tout.struct), self._det_xyxy.data_ptr(),
-                self._det_conf.data_ptr(), self._det_cls.data_ptr(), self._det_count.data_ptr(),
-                self.max_dets, C.byref(opt), self._det_tid.data_ptr(), self._det_kind.data_ptr(),
-                self._src_row.data_ptr(), self._status.data_ptr(), _lib.cuda_stream()))
-            self._cur ^= 1
-            self._last_n = n
-        st = self._status.cpu().numpy()
-        if st.any():
-            self._status.zero_()
+            self._grow(self._tables[0].capacity, 1 << (n - 1).bit_length())
+        while True:
+            with torch.cuda.device(self.device):
+                if n:
+                    self._det_xyxy[0, :n] = torch.as_tensor(np.ascontiguousarray(xyxy, np.float32).reshape(n, 4)).to(self.device)
+                    self._det_conf[0, :n] = torch.as_tensor(np.ascontiguousarray(confidence, np.float32)).to(self.device)
+                    self._det_cls[0, :n] = torch.as_tensor(np.ascontiguousarray(class_id, np.int32)).to(self.device)
+                self._det_count.fill_(n)
+                tin, tout = self._tables[self._cur], self._tables[self._cur ^ 1]
+                opt = _lib.track_options(self.track_thresh, self.match_thresh, self.track_buffer, self.assignment,
+                                         tin.kalman if self.use_kalman else None, tout.kalman if self.use_kalman else None,
+                                         self._assign_scratch)
+                _lib.check(self._lib.rtm_track_step_ex(
+                    C.byref(tin.struct), C.byref(tout.struct), self._det_xyxy.data_ptr(),
+                    self._det_conf.data_ptr(), self._det_cls.data_ptr(), self._det_count.data_ptr(),
+                    self.max_dets, C.byref(opt), self._det_tid.data_ptr(), self._det_kind.data_ptr(),
+                    self._src_row.data_ptr(), self._status.data_ptr(), _lib.cuda_stream()))
+                st = self._status.cpu().numpy()
+                if st.any():
+                    self._status.zero_()
+            if (int(st[0]) & _lib.STATUS_TRACK_OVERFLOW) and self.auto_grow:
+                self._grow(2 * self._tables[0].capacity, self.max_dets)      # tin is untouched: run the frame again
+                continue
+            break
+        self._cur ^= 1
+        self._last_n = n
         _lib.raise_on_status(st, "MultiObjectTracker")
         # the reference filters on time_since_update == 0 AFTER ageing every track, so nothing
         # ever qualifies (tracker.py:141, 144-147)

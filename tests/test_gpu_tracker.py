@@ -118,9 +118,43 @@ def test_thresholds_ties_and_degenerate_frames(pkg):
 def test_track_table_overflow_is_reported_not_truncated(pkg):
     import types
     trk = pkg.MultiObjectTracker(max_tracks=8, max_dets=16)
+    trk._core.auto_grow = False
     xy = np.arange(12, dtype=np.float32)[:, None] * 100 + np.array([0, 0, 10, 10], np.float32)
     with pytest.raises(pkg.RtmError, match="capacity"):
         trk.update(types.SimpleNamespace(xyxy=xy, confidence=np.full(12, 0.9, np.float32), class_id=np.zeros(12, np.int32)))
+
+
+@pytest.mark.parametrize("mode", ["greedy", "lapjv", "kalman"])
+def test_facade_tables_grow_like_the_reference_lists(pkg, mode):
+    """tracker.py:55, 127-134: the reference's track list and detection arrays have no capacity.  A facade that
+    starts with 8 rows / 4 detection slots ends up, frame by frame, where the oracle does (the overflowing step is
+    repeated on doubled tables: ids, order and state are those of a table that was large enough all along)."""
+    import types
+    rng = np.random.default_rng(5)
+    kw = dict(use_kalman=True) if mode == "kalman" else dict(assignment=mode)
+    trk = pkg.MultiObjectTracker(max_tracks=8, max_dets=4, **kw)
+    big = pkg.MultiObjectTracker(max_tracks=1024, max_dets=256, **kw)
+    pos = rng.uniform(0, 1500, (150, 2)).astype(np.float32)
+    for f in range(12):
+        n = min(150, 3 + 14 * f)                           # 3, 17, 31, ... detections: slots and rows overflow repeatedly
+        p = pos[:n] + np.float32(2.0 * f)
+        xy = np.concatenate([p, p + np.float32(60)], axis=1)
+        conf = np.where(np.arange(n) % 5 == 4, 0.3, 0.9).astype(np.float32)
+        det = types.SimpleNamespace(xyxy=xy, confidence=conf, class_id=(np.arange(n) % 3).astype(np.int32))
+        trk.update(det)
+        big.update(det)
+        a, b = trk._core._tracks, big._core._tracks
+        assert len(a) == len(b) and trk._core._next_id == big._core._next_id
+        for x, y in zip(a, b):
+            assert {k: v for k, v in x.items() if k != "xyxy"} == {k: v for k, v in y.items() if k != "xyxy"}
+            np.testing.assert_array_equal(x["xyxy"], y["xyxy"])
+        np.testing.assert_array_equal(trk._core.assignments()[0], big._core.assignments()[0])
+        if mode == "greedy":
+            if f == 0:
+                orc = tracker_ref.TrackerOracle()
+            orc.step(xy, conf, det.class_id)
+            assert [t["track_id"] for t in a] == orc.track_id.tolist() and trk._core._next_id == orc.next_id
+    assert trk._core._tables[0].capacity >= 128 and trk._core.max_dets >= 150
 
 
 @pytest.mark.parametrize("clip", ["slow", "gaps", "crowd"])

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Letterbox timing: 64 x 1080p -> 640 x 640 bf16 (the 3 : 1 decimation path) and 720p (general path).
-RTM_LETTERBOX_IMPL=unstaged | direct select the other kernels."""
+RTM_LETTERBOX_IMPL=narrow (16 pixels per thread, table lookup) | direct (general kernel) select the other kernels."""
 import importlib, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
