@@ -18,6 +18,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <math.h>
+#include <type_traits>
 #include <stdlib.h>
 #include <string.h>
 
@@ -304,6 +305,138 @@ __global__ void __launch_bounds__(128) letterbox_decimate3_wide_kernel(const Let
   }
 }
 
+// General ratios, 4-byte aligned rows: a block owns a tile of 16 output rows x 128 output columns.
+//   * the horizontal taps of the 128 columns are computed once per block (shared memory) instead of once per pixel:
+//     byte offset of the left tap in its row, and the weight pair packed for DP2A;
+//   * lane l owns columns l, l + 32, l + 64, l + 96 of two rows, so the lanes of a warp read NEIGHBOURING source
+//     pixels (the 8-pixels-per-thread kernel sent every byte load to 12 different cache lines);
+//   * the 6 bytes of a tap pair (B G R B G R at 3 x0) come from three aligned 32-bit loads and two funnel shifts; one
+//     PRMT puts the two bytes of a channel side by side and one DP2A forms a0 p0 + a1 p1 (cv::resize's horizontal pass);
+//   * 16-bit outputs are converted like the 3 : 1 kernel (exact for all 256 values), float goes through the table.
+// The arithmetic is the arithmetic of letterbox_kernel; unit weights (no resize, borders) reproduce the source byte.
+constexpr int kTileCols = 128, kTileRows = 16;  // 4 columns per lane, 2 rows per warp
+
+// The three aligned words that hold bytes 3 x0 .. 3 x0 + 5 of a row, for the four columns of a lane at once (all loads
+// are issued before any is used: the kernel lives on the loads it keeps in flight).  Words past the end of a row only
+// ever meet zero weights, so reading on into the next row is harmless; CLAMP (the last source row of the last frame,
+// where "on" would leave the buffer) replaces them by the row's last word.
+template <bool CLAMP>
+__device__ __forceinline__ void tap_words(const uint8_t* row, const uint32_t (&wo)[4], uint32_t last_word, uint32_t (&w)[4][3]) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (CLAMP) {
+      w[k][0] = __ldg(reinterpret_cast<const uint32_t*>(row + wo[k]));
+      w[k][1] = __ldg(reinterpret_cast<const uint32_t*>(row + min(wo[k] + 4u, last_word)));
+      w[k][2] = __ldg(reinterpret_cast<const uint32_t*>(row + min(wo[k] + 8u, last_word)));
+    } else {
+      const uint32_t* p = reinterpret_cast<const uint32_t*>(row + wo[k]);
+      w[k][0] = __ldg(p);
+      w[k][1] = __ldg(p + 1);
+      w[k][2] = __ldg(p + 2);
+    }
+  }
+}
+// cv::resize's horizontal pass on the words of one column: a0 p0 + a1 p1 per channel (B, G, R)
+__device__ __forceinline__ void tap_dot(const uint32_t (&w)[3], uint32_t sh, uint32_t wt, uint32_t (&h)[3]) {
+  const uint32_t lo = __funnelshift_r(w[0], w[1], sh), hi = __funnelshift_r(w[1], w[2], sh);  // bytes 0..3, 4..7 from 3 x0
+  h[0] = __dp2a_lo(wt, __byte_perm(lo, hi, 0x3030), 0u);                                      // B: bytes 0, 3
+  h[1] = __dp2a_lo(wt, __byte_perm(lo, hi, 0x4141), 0u);                                      // G: bytes 1, 4
+  h[2] = __dp2a_lo(wt, __byte_perm(lo, hi, 0x5252), 0u);                                      // R: bytes 2, 5
+}
+template <typename T>
+__device__ __forceinline__ T tile_unit(uint32_t v, const T* lut) {  // T(v / 255), v <= 255
+  if constexpr (sizeof(T) == 4) {
+    return lut[v];
+  } else {
+    const float f = unit_from_byte<0>(v);
+    if constexpr (std::is_same<T, __half>::value) return __float2half_rn(f);
+    else return __float2bfloat16_rn(f);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256, 4) letterbox_tile_kernel(const LetterboxArgs a) {
+  __shared__ int s_off[kTileCols];       // 3 * x0, or -1 for a padding column
+  __shared__ uint32_t s_wt[kTileCols];   // a0 | a1 << 16 (0 for a padding column)
+  __shared__ T s_lut[sizeof(T) == 4 ? 256 : 1];
+  const int tid = threadIdx.x;
+  const int col0 = blockIdx.x * kTileCols, row0 = blockIdx.y * kTileRows, b = blockIdx.z;
+  if (sizeof(T) == 4) s_lut[tid] = from_u8<T>(tid);
+  if (tid < kTileCols) {
+    const int rx = col0 + tid - a.left;
+    int off = -1;
+    uint32_t wt = 0;
+    if (rx >= 0 && rx < a.new_w && col0 + tid < a.out_w) {
+      int x0 = rx, x1 = rx, a0 = 1 << kCoefBits, a1 = 0;
+      if (a.resize) linear_tap<true>(rx, a.scale_x, a.src_w, &x0, &x1, &a0, &a1);
+      off = 3 * x0;  // a1 != 0 implies x1 == x0 + 1 (the fraction is reset where the taps are clamped)
+      wt = static_cast<uint32_t>(a0) | (static_cast<uint32_t>(a1) << 16);
+    }
+    s_off[tid] = off;
+    s_wt[tid] = wt;
+  }
+  __syncthreads();
+  const int lane = tid & 31, warp = tid >> 5;
+  const uint32_t last_word = static_cast<uint32_t>(a.row_stride) - 4u;  // byte offset of the row's last whole word
+  const uint8_t* frame = a.frames + static_cast<long long>(b) * a.frame_stride;
+  const long long plane = static_cast<long long>(a.out_h) * a.out_w;
+  const T pad = tile_unit<T>(114u, s_lut);
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr) {
+    const int oy = row0 + 2 * warp + rr;
+    if (oy >= a.out_h) break;
+    const int ry = oy - a.top;
+    T* out = static_cast<T*>(a.out) + (static_cast<long long>(b) * 3 * a.out_h + oy) * a.out_w + col0 + lane;
+    if (ry < 0 || ry >= a.new_h) {  // padding row
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (col0 + lane + 32 * k < a.out_w) out[32 * k] = out[plane + 32 * k] = out[2 * plane + 32 * k] = pad;
+      continue;
+    }
+    int y0 = ry, y1 = ry, b0 = 1 << kCoefBits, b1 = 0;
+    if (a.resize) linear_tap<false>(ry, a.scale_y, a.src_h, &y0, &y1, &b0, &b1);
+    const uint8_t* r0 = frame + static_cast<long long>(y0) * a.row_stride;
+    const uint8_t* r1 = frame + static_cast<long long>(y1) * a.row_stride;
+    const uint32_t m0 = static_cast<uint32_t>(b0) << 16, m1 = static_cast<uint32_t>(b1) << 16;  // (b x) >> 16 = umulhi(b << 16, x)
+    uint32_t wo[4], sh[4], wt[4];
+    bool live[4];  // a pixel of the resized image (not a padding column, not past the output row)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int col = lane + 32 * k;
+      const int off = s_off[col];
+      live[k] = off >= 0;
+      wt[k] = s_wt[col];
+      wo[k] = live[k] ? static_cast<uint32_t>(off) & ~3u : 0u;
+      sh[k] = (static_cast<uint32_t>(off) & 3u) * 8u;
+    }
+    uint32_t w0[4][3], w1[4][3];
+    const bool last_rows = b == static_cast<int>(gridDim.z) - 1 && max(y0, y1) == a.src_h - 1;
+    if (!last_rows) {
+      tap_words<false>(r0, wo, last_word, w0);
+      if (b1) tap_words<false>(r1, wo, last_word, w1);
+    } else {
+      tap_words<true>(r0, wo, last_word, w0);
+      if (b1) tap_words<true>(r1, wo, last_word, w1);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint32_t h0[3], h1[3] = {0u, 0u, 0u};
+      tap_dot(w0[k], sh[k], wt[k], h0);
+      if (b1) tap_dot(w1[k], sh[k], wt[k], h1);
+      if (col0 + lane + 32 * k < a.out_w) {
+        // cv::resize's vertical pass.  No clamp: with a0 + a1 <= 2049 and b0 + b1 <= 2049 (each weight is a rounding of
+        // f * 2048 or (1 - f) * 2048) the sum is at most (2049 * 32655) >> 16 = 1020, i.e. 255 after the final shift
+        const T v0 = tile_unit<T>((__umulhi(m0, h0[0] >> 4) + __umulhi(m1, h1[0] >> 4) + 2u) >> 2, s_lut);
+        const T v1 = tile_unit<T>((__umulhi(m0, h0[1] >> 4) + __umulhi(m1, h1[1] >> 4) + 2u) >> 2, s_lut);
+        const T v2 = tile_unit<T>((__umulhi(m0, h0[2] >> 4) + __umulhi(m1, h1[2] >> 4) + 2u) >> 2, s_lut);
+        out[2 * plane + 32 * k] = live[k] ? v0 : pad;  // BGR -> RGB planes
+        out[plane + 32 * k] = live[k] ? v1 : pad;
+        out[32 * k] = live[k] ? v2 : pad;
+      }
+    }
+  }
+}
+
 // host copy of linear_tap (same IEEE operations) to recognise the pure 3 : 1 decimation
 bool taps_are_decimate3(int dst, double scale, int ssize, bool horizontal) {
   for (int d = 0; d < dst; ++d) {
@@ -386,6 +519,27 @@ int launch_letterbox(const uint8_t* frames, int num_streams, int src_h, int src_
         RTM_REQUIRE(false, "rtm_letterbox: unknown out_dtype %d", out_dtype);
     }
     RTM_LAUNCH_CHECK("letterbox_decimate3_kernel");
+    return RTM_OK;
+  }
+  // tile kernel (RTM_LETTERBOX_IMPL=pixels turns it off): needs rows that start on 4-byte boundaries
+  static const bool allow_tile = !(getenv("RTM_LETTERBOX_IMPL") && strcmp(getenv("RTM_LETTERBOX_IMPL"), "pixels") == 0);
+  if (allow_tile && (reinterpret_cast<uintptr_t>(frames) & 3) == 0 && row_stride % 4 == 0 && frame_stride % 4 == 0 &&
+      row_stride < (1ll << 31) && row_stride >= 12) {
+    dim3 tgrid((out_w + kTileCols - 1) / kTileCols, (out_h + kTileRows - 1) / kTileRows, num_streams);
+    switch (out_dtype) {
+      case RTM_F32:
+        letterbox_tile_kernel<float><<<tgrid, 256, 0, s>>>(a);
+        break;
+      case RTM_F16:
+        letterbox_tile_kernel<__half><<<tgrid, 256, 0, s>>>(a);
+        break;
+      case RTM_BF16:
+        letterbox_tile_kernel<__nv_bfloat16><<<tgrid, 256, 0, s>>>(a);
+        break;
+      default:
+        RTM_REQUIRE(false, "rtm_letterbox: unknown out_dtype %d", out_dtype);
+    }
+    RTM_LAUNCH_CHECK("letterbox_tile_kernel");
     return RTM_OK;
   }
   switch (out_dtype) {

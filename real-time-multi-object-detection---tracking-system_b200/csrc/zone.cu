@@ -14,20 +14,37 @@
 // share a state column, so their order matters and is kept; different columns never interact).
 // Fired (row, zone) pairs are ranked with a block scan so the event list comes out in the
 // reference's (track order, zone order).
+#include <stdlib.h>
+
 #include "zone_body.cuh"
 
 namespace {
 
-constexpr int kZoneThreads = 256;
 using rtm::ZoneArgs;
 
-__global__ void __launch_bounds__(kZoneThreads) zone_step_kernel(const ZoneArgs a) {
+// 256 threads per stream, or 1024 when the tables are large (crowds: the step is a chain of dependent loads per
+// (row, column) pair, so the pairs a thread walks one after the other set the time - ncu: 12 % of the warp slots
+// active at 256 threads and 128 streams)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) zone_step_kernel(const ZoneArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_scan[33];
   __shared__ rtm::ZonePrefetch zp;
-  rtm::zone_prefetch<kZoneThreads>(a, blockIdx.x, &zp);
+  rtm::zone_prefetch<THREADS>(a, blockIdx.x, &zp);
   __syncthreads();
-  rtm::zone_stream<kZoneThreads>(a, blockIdx.x, smem_raw, s_scan, &zp);
+  rtm::zone_stream<THREADS>(a, blockIdx.x, smem_raw, s_scan, &zp);
+}
+
+template <int THREADS>
+int launch_zone(const ZoneArgs& a, size_t smem, cudaStream_t stream) {
+  if (smem > 24 * 1024)
+    if (int rc = rtm::ensure_dynamic_smem(reinterpret_cast<const void*>(zone_step_kernel<THREADS>), smem)) return rc;
+  {
+    rtm::ProfileScope prof(RTM_K_ZONE, stream);
+    zone_step_kernel<THREADS><<<a.trk.num_streams, THREADS, smem, stream>>>(a);
+  }
+  RTM_LAUNCH_CHECK("zone_step_kernel");
+  return RTM_OK;
 }
 
 }  // namespace
@@ -49,12 +66,7 @@ extern "C" int rtm_zone_step(const rtm_zone_set* zones, const rtm_track_table* t
              events, event_stride, event_count, status};
   const size_t smem = rtm::zone_smem_bytes(event_stride);
   RTM_REQUIRE(smem + sizeof(rtm::ZonePrefetch) <= 226 * 1024, "rtm_zone_step: %zu B of shared memory needed", smem);
-  if (smem > 24 * 1024)
-    if (int rc = rtm::ensure_dynamic_smem(reinterpret_cast<const void*>(zone_step_kernel), smem)) return rc;
-  {
-    rtm::ProfileScope prof(RTM_K_ZONE, static_cast<cudaStream_t>(stream));
-    zone_step_kernel<<<tracks->num_streams, kZoneThreads, smem, static_cast<cudaStream_t>(stream)>>>(a);
-  }
-  RTM_LAUNCH_CHECK("zone_step_kernel");
-  return RTM_OK;
+  static const int forced = getenv("RTM_ZONE_THREADS") ? atoi(getenv("RTM_ZONE_THREADS")) : 0;
+  const bool wide = forced ? forced == 1024 : static_cast<long long>(tracks->capacity) * zones->num_columns >= 8192;
+  return wide ? launch_zone<1024>(a, smem, static_cast<cudaStream_t>(stream)) : launch_zone<256>(a, smem, static_cast<cudaStream_t>(stream));
 }
