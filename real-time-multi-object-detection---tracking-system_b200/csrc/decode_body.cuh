@@ -108,10 +108,26 @@ struct TmaGeom {
   int static_rounds;  // ring rounds with the static schedule (tile = blockIdx + k * grid) before tickets take over
   int trigger;        // release programmatic dependents (the next scan on the same stream) at once
   int l2_ahead;       // > 0: whoever draws ticket t also prefetches tile t + l2_ahead into L2 (a ring cycle of all teams)
+  // lazy box rows (tma_scan_cta<..., LAZY = true>): the ring holds the class rows of a tile only; the 64 DFL values of
+  // an anchor are read from global memory, by the block's decoder warps, for candidates only
+  int cls_tile_bytes;  // class rows of a tile
 };
 
 struct TmaMaps {
-  CUtensorMap tile[3];  // per level: the ring's tiles
+  CUtensorMap tile[3];  // per level: the ring's tiles (all channels)
+  CUtensorMap cls[3];   // per level: class rows only (box: tile width x num_classes x 1)
+};
+
+// LAZY: candidates on their way from the consumer warps (N1 done: stream, level, anchor, score, class) to the decoder
+// warps (D1: the anchor's 64 DFL values from global memory, expectation, box, store).  A bounded ring in shared memory,
+// many producers, many consumers, sequence numbers per slot: state == pos: free for the producer that drew position pos;
+// pos + 1: filled; the decoder that drew pos reads it and sets pos + slots.
+constexpr int kCandQueueSlots = 128;
+struct CandQueue {
+  int head, tail;
+  int final_tail;  // < 0 while the scan runs; then the number of candidates pushed in all
+  int state[kCandQueueSlots];
+  int4 rec[kCandQueueSlots];  // stream | level << 24, anchor within the level, score bits, class
 };
 
 // What the one-launch step kernel adds around a scan (all null / zero for the stand-alone kernel):
@@ -287,19 +303,120 @@ struct ScanCtl {
   int4 tile[kMaxStages];  // per stage: (stream, level, first anchor of the tile within the level, -); x < 0 = no more tiles
   int next[kMaxStages];   // ticket drawn for the stage's next fill (producer lane only)
   int issued[4];          // tiles each team's producer has handed to its consumers
+  unsigned long long tl[4];  // RTM_TIMELINE builds: team 0's consumer wait ns, loop ns, tiles; its producer's wait ns
 };
+
+__device__ __forceinline__ int ld_volatile_shared(const int* p) {
+  int v;
+  asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile_shared(int* p, int v) {
+  asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+// all threads of the block, before a block barrier and before anyone pushes
+__device__ __forceinline__ void cand_queue_init(CandQueue* cq) {
+  for (int i = threadIdx.x; i < kCandQueueSlots; i += blockDim.x) cq->state[i] = i;
+  if (threadIdx.x == 0) {
+    cq->head = 0;
+    cq->tail = 0;
+    cq->final_tail = -1;
+  }
+}
+__device__ __forceinline__ void cand_push(CandQueue* cq, int pos, int b, int li, int pix, float score, int cls) {
+  const int slot = pos & (kCandQueueSlots - 1);
+  for (uint32_t spin = 0; ld_volatile_shared(&cq->state[slot]) != pos; ++spin)  // a full ring: the decoders are behind
+    if (spin > (1u << 26)) __trap();
+  cq->rec[slot] = make_int4(b | (li << 24), pix, __float_as_int(score), cls);
+  __threadfence_block();
+  st_volatile_shared(&cq->state[slot], pos + 1);
+}
+
+// A decoder warp (LAZY): four lanes per candidate, one per box side; eight candidates per round.  Each lane reads its
+// side's 16 DFL values of the anchor from global memory (one value per channel row: a 32-byte sector each; neighbouring
+// candidates share sectors), forms the expectation with the function every decode path uses, and the side-0 lane
+// assembles and stores the box.  Returns when the scan is over and the queue is empty.
+template <typename T>
+__device__ __forceinline__ void cand_decoder_warp(CandQueue* cq, const void* const (&head)[3], const TmaGeom& tg, const Workspace& ws) {
+  const int lane = threadIdx.x & 31, grp = lane >> 2, side = lane & 3;
+  const int ch = kBoxCh + tg.g.num_classes;
+  while (true) {
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&cq->head, 8);
+    base = __shfl_sync(kFull, base, 0);
+    const int pos = base + grp, slot = pos & (kCandQueueSlots - 1);
+    bool have = false;
+    int4 rec = make_int4(0, 0, 0, 0);
+    if (side == 0) {
+      for (uint32_t spin = 0;; ++spin) {
+        if (ld_volatile_shared(&cq->state[slot]) == pos + 1) {
+          have = true;
+          break;
+        }
+        const int ft = ld_volatile_shared(&cq->final_tail);
+        if (ft >= 0 && pos >= ft) break;
+        __nanosleep(64);
+        if (spin > (1u << 24)) __trap();
+      }
+      if (have) {
+        __threadfence_block();
+        rec = cq->rec[slot];
+        st_volatile_shared(&cq->state[slot], pos + kCandQueueSlots);  // free for the producer one lap on
+      }
+    }
+    have = __shfl_sync(kFull, have ? 1 : 0, grp * 4) != 0;
+    rec.x = __shfl_sync(kFull, rec.x, grp * 4);
+    rec.y = __shfl_sync(kFull, rec.y, grp * 4);
+    rec.z = __shfl_sync(kFull, rec.z, grp * 4);
+    rec.w = __shfl_sync(kFull, rec.w, grp * 4);
+    if (!__any_sync(kFull, have)) break;  // every position of this round lies past the end: so will all later ones
+    const int b = rec.x & 0xffffff, li = rec.x >> 24, pix = rec.y;
+    float d = 0.f;
+    if (have) {
+      const int hw = tg.g.lv[li].hw;
+      const T* src = static_cast<const T*>(head[li]) + (static_cast<size_t>(b) * ch + side * kRegMax) * hw + pix;
+      float x[kRegMax];
+#pragma unroll
+      for (int k = 0; k < kRegMax; ++k) x[k] = to_float(__ldg(src + static_cast<size_t>(k) * hw));
+      d = dfl_expectation(x);
+    }
+    const float t = __shfl_sync(kFull, d, grp * 4 + 1), r = __shfl_sync(kFull, d, grp * 4 + 2), bt = __shfl_sync(kFull, d, grp * 4 + 3);
+    if (have && side == 0) {
+      const int w = tg.g.lv[li].w;
+      const int y = pix / w, xx = pix - y * w;
+      store_candidate(ws, b, tg.g.lv[li].anchor0 + pix,
+                      dist_to_xyxy(d, t, r, bt, static_cast<float>(xx) + 0.5f, static_cast<float>(y) + 0.5f,
+                                   static_cast<float>(tg.g.lv[li].stride), nullptr),
+                      __int_as_float(rec.z), rec.w);
+    }
+  }
+}
+
+// after the scan (and, LAZY, after the decoder warps have returned and a block barrier): one thread reports the CTA's tiles
+__device__ __forceinline__ void scan_publish(const ScanSync& sync, const ScanCtl* ctl, int groups) {
+  if (!sync.tiles_done) return;
+  int done = 0;
+  for (int g = 0; g < groups; ++g) done += ctl->issued[g];
+  if (done) {
+    __threadfence();
+    atomicAdd(sync.tiles_done, done);
+  }
+}
 
 // The scan of one CTA.  `cta` / `num_ctas`: this CTA's index among the scan CTAs of the launch and their
 // number; the block has tma_threads(kTileW, GROUPS) threads, all of which must call it.  Ends with a block
 // barrier after the last candidate store of the CTA; thread 0 then publishes how many tiles were done (sync.tiles_done).
-template <typename T, bool NC80, int kTileW, int GROUPS>
+template <typename T, bool NC80, int kTileW, int GROUPS, bool LAZY = false>
 __device__ __forceinline__ void tma_scan_cta(const TmaMaps& maps, const TmaGeom& tg, const rtm_nms_params& prm,
                                              const float logit_gate, const Workspace& ws, const ScanSync& sync,
-                                             const int cta, const int num_ctas, unsigned char* tile_smem, ScanCtl* ctl) {
-  const CUtensorMap &map0 = maps.tile[0], &map1 = maps.tile[1], &map2 = maps.tile[2];
+                                             const int cta, const int num_ctas, unsigned char* tile_smem, ScanCtl* ctl,
+                                             CandQueue* cq = nullptr) {
+  const CUtensorMap &map0 = LAZY ? maps.cls[0] : maps.tile[0], &map1 = LAZY ? maps.cls[1] : maps.tile[1],
+                    &map2 = LAZY ? maps.cls[2] : maps.tile[2];
   using P = Pair<T>;
   constexpr int kTeamWarps = kTileW / kAnchorsPerWarp;
   constexpr int kConsumerWarps = GROUPS * kTeamWarps;
+  const int stage_bytes = LAZY ? tg.cls_tile_bytes : tg.tile_bytes;  // what a ring stage holds
   uint64_t* full_bar = ctl->full_bar;
   uint64_t* empty_bar = ctl->empty_bar;
 
@@ -315,6 +432,7 @@ __device__ __forceinline__ void tma_scan_cta(const TmaMaps& maps, const TmaGeom&
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("bar.sync 1, %0;" ::"n"(kScanThreadsCta) : "memory");
+  // (LAZY: the candidate queue was initialised by the caller, before a barrier of the whole block)
 
   // every team has a ring of its own: stages [team * spt, (team + 1) * spt), filled by its own producer warp
   // (GROUPS virtual CTAs side by side: the ticket round trip of a producer is hidden behind its team's tiles)
@@ -337,11 +455,20 @@ __device__ __forceinline__ void tma_scan_cta(const TmaMaps& maps, const TmaGeom&
         const int li = r >= tb2 ? 2 : (r >= tb1 ? 1 : 0);
         const int x = (r - (li == 2 ? tb2 : (li == 1 ? tb1 : 0))) * kTileW;
         ctl->tile[s0 + s] = make_int4(b, li, x, 0);
-        mbar_expect_tx(&full_bar[s0 + s], tg.tile_bytes);
-        tma_load_tile(tile_smem + static_cast<size_t>(s0 + s) * tg.tile_bytes, li == 0 ? &map0 : (li == 1 ? &map1 : &map2),
-                      &full_bar[s0 + s], x, 0, b, policy);
+        mbar_expect_tx(&full_bar[s0 + s], stage_bytes);
+        tma_load_tile(tile_smem + static_cast<size_t>(s0 + s) * stage_bytes, li == 0 ? &map0 : (li == 1 ? &map1 : &map2),
+                      &full_bar[s0 + s], x, LAZY ? kBoxCh : 0, b, policy);
       };
+#ifdef RTM_TIMELINE
+      unsigned long long tl_empty = 0;
+      auto wait_empty = [&](int s, int parity) {
+        const unsigned long long t0 = global_timer_ns();
+        mbar_wait(&empty_bar[s0 + s], parity);
+        tl_empty += global_timer_ns() - t0;
+      };
+#else
       auto wait_empty = [&](int s, int parity) { mbar_wait(&empty_bar[s0 + s], parity); };
+#endif
       // L2 prefetch of the tile that will be drawn `l2_ahead` tickets from now, by whichever team that will be: every
       // tile beyond the first ones is prefetched exactly once, about one ring cycle before its TMA load, which then
       // finds it in L2 - the ring's two stages per team cover an L2 hit, not a DRAM access under load
@@ -417,6 +544,9 @@ __device__ __forceinline__ void tma_scan_cta(const TmaMaps& maps, const TmaGeom&
         }
       }
       ctl->issued[team] = handed;
+#ifdef RTM_TIMELINE
+      if (team == 0) ctl->tl[3] = tl_empty;
+#endif
     }
   } else {
     // ===== consumer warps =====
@@ -464,8 +594,19 @@ __device__ __forceinline__ void tma_scan_cta(const TmaMaps& maps, const TmaGeom&
       if (lane == 0) spin_until_ge(sync.slot_free, sync.slot_free_target);
       __syncwarp();
     }
+#ifdef RTM_TIMELINE
+    unsigned long long tl_wait = 0, tl_tiles = 0;
+    const unsigned long long tl_begin = global_timer_ns();
+#endif
     while (true) {
+#ifdef RTM_TIMELINE
+      const unsigned long long tl_t0 = global_timer_ns();
       mbar_wait(&full_bar[s], phase);
+      tl_wait += global_timer_ns() - tl_t0;
+      ++tl_tiles;
+#else
+      mbar_wait(&full_bar[s], phase);
+#endif
       int b, li, x0;
       asm volatile("ld.volatile.shared.v4.s32 {%0, %1, %2, _}, [%3];" : "=r"(b), "=r"(li), "=r"(x0) : "r"(smem_u32(&ctl->tile[s])));
       if (b < 0) break;
@@ -473,8 +614,8 @@ __device__ __forceinline__ void tma_scan_cta(const TmaMaps& maps, const TmaGeom&
       level_of(li, &lv_w, &lv_stride, &lv_anchor0);
       const int lv_hw = li == 2 ? hw2 : (li == 1 ? hw1 : hw0);
       const int pix = x0 + col;
-      const T* tile = reinterpret_cast<const T*>(tile_smem + static_cast<size_t>(s) * tg.tile_bytes);
-      const T* cls_rows = tile + kBoxCh * kTileW;      // first class row of the tile
+      const T* tile = reinterpret_cast<const T*>(tile_smem + static_cast<size_t>(s) * stage_bytes);
+      const T* cls_rows = LAZY ? tile : tile + kBoxCh * kTileW;  // first class row of the tile
       const T* cls_col = cls_rows + q * kTileW + col;  // row of class q
 
       // ---- N1 gate: packed running maximum over this quarter's classes for both anchors ----
@@ -547,7 +688,20 @@ __device__ __forceinline__ void tma_scan_cta(const TmaMaps& maps, const TmaGeom&
         }
         cand0 = best0 > prm.conf_thres && class_wanted(prm, bc0 & 255);
         cand1 = best1 > prm.conf_thres && class_wanted(prm, bc1 & 255);
-        if (__any_sync(kFull, cand0 || cand1)) {
+        if (LAZY) {
+          // hand the candidates to the decoder warps: the warp goes on with its next tile
+          const unsigned m0b = __ballot_sync(kFull, cand0 && q == 0), m1b = __ballot_sync(kFull, cand1 && q == 0);
+          if (m0b | m1b) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&cq->tail, __popc(m0b) + __popc(m1b));
+            base = __shfl_sync(kFull, base, 0);
+            if (q == 0) {
+              const unsigned below = (1u << lane) - 1u;
+              if (cand0) cand_push(cq, base + __popc(m0b & below), b, li, pix, best0, bc0 & 255);
+              if (cand1) cand_push(cq, base + __popc(m0b) + __popc(m1b & below), b, li, pix + 1, best1, bc1 & 255);
+            }
+          }
+        } else if (__any_sync(kFull, cand0 || cand1)) {
           // side q of the lane's two anchors: both sets of 16 bins come out of shared memory first (a packed
           // load yields both anchors), then the stage is handed back to the producer and the arithmetic follows
           float x0v[kRegMax], x1v[kRegMax];
@@ -586,6 +740,13 @@ __device__ __forceinline__ void tma_scan_cta(const TmaMaps& maps, const TmaGeom&
         phase ^= 1;
       }
     }
+#ifdef RTM_TIMELINE
+    if (warp == 0 && lane == 0) {
+      ctl->tl[0] = tl_wait;
+      ctl->tl[1] = global_timer_ns() - tl_begin;
+      ctl->tl[2] = tl_tiles - 1;
+    }
+#endif
   }
   // every candidate of this CTA's tiles is stored; publish that (the post stage of the launch waits for all tiles)
   asm volatile("bar.sync 1, %0;" ::"n"(kScanThreadsCta) : "memory");
@@ -594,7 +755,10 @@ __device__ __forceinline__ void tma_scan_cta(const TmaMaps& maps, const TmaGeom&
       mbar_inval(&full_bar[s]);
       mbar_inval(&empty_bar[s]);
     }
-    if (sync.tiles_done) {
+    if (LAZY) {  // every candidate of the CTA is in the queue (or decoded already): the decoder warps may run dry
+      asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(&cq->final_tail)), "r"(*reinterpret_cast<volatile int*>(&cq->tail)) : "memory");
+    }
+    if (!LAZY && sync.tiles_done) {
       int done = 0;
       for (int g = 0; g < GROUPS; ++g) done += ctl->issued[g];
       if (done) {

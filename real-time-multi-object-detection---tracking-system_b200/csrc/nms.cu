@@ -722,6 +722,11 @@ int plan_tma_scan(const void* p3, const void* p4, const void* p5, const HeadGeom
       CUresult r = encode(&fresh.tile[l], tensor_map_dtype<T>(), 3, const_cast<void*>(ptrs[l]), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return 0;
+      // the same tensor seen through a smaller box (lazy box rows): the class rows of a tile
+      const cuuint32_t cls_box[3] = {kTileW, static_cast<cuuint32_t>(g.num_classes), 1};
+      r = encode(&fresh.cls[l], tensor_map_dtype<T>(), 3, const_cast<void*>(ptrs[l]), dims, strides, cls_box, estr,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return 0;
     }
     if (cache.size() < 64) {
       cache.push_back(MapEntry{key, fresh});
@@ -738,6 +743,7 @@ int plan_tma_scan(const void* p3, const void* p4, const void* p5, const HeadGeom
   for (int l = 0; l < 3; ++l) tg.tiles_before[l + 1] = tg.tiles_before[l] + (g.lv[l].hw + kTileW - 1) / kTileW;
   tg.total_tiles = tg.tiles_before[3] * B;
   tg.tile_bytes = ch * kTileW * static_cast<int>(sizeof(T));
+  tg.cls_tile_bytes = g.num_classes * kTileW * static_cast<int>(sizeof(T));
   static const int static_env = env_int("RTM_TMA_STATIC_ROUNDS", 1);
   tg.static_rounds = static_env < 0 ? 0 : static_env;
   static const int evict_env = env_int("RTM_TMA_EVICT_FIRST", 1);

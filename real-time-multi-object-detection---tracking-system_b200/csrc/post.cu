@@ -124,6 +124,7 @@ struct StepArgs {
   int caller_target;
   int* stream_seq;         // (B) steps completed per stream
   int chain;               // a stream's post stage waits for stream_seq[b] == seq (the previous step may still run)
+  const void* head[3];     // the head tensors (LAZY: the decoder warps read the DFL values of candidates from them)
 };
 
 // Diagnosis builds (-DRTM_TIMELINE, tools/step_timeline.py): CTA-level stamps of the step kernel, a row of 8 words per
@@ -152,7 +153,7 @@ struct StreamChain {
   }
 };
 
-template <typename T, bool WITH_OPTIMAL>
+template <typename T, bool WITH_OPTIMAL, bool LAZY>
 __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) step_kernel(const __grid_constant__ rtm::TmaMaps maps,
                                                                             const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -160,6 +161,8 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) step_kernel(cons
   __shared__ int s_keep[rtm::kMaxDetCap];
   __shared__ int s_scan[33];
   __shared__ int s_job;
+  __shared__ __align__(16) unsigned char cq_raw[LAZY ? sizeof(rtm::CandQueue) : 16];
+  rtm::CandQueue* const cq = reinterpret_cast<rtm::CandQueue*>(cq_raw);
   const int tid = threadIdx.x;
   // the next step's kernel (a programmatic dependent on the library's stream) may start as soon as every CTA of
   // this grid has got here: what it must not overtake is ordered through the counters above
@@ -175,15 +178,25 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) step_kernel(cons
   if (blockIdx.x == 0 && tid == 0) *a.rearm = 0;
 
   // ---- scan ----
+  if (LAZY) {
+    rtm::cand_queue_init(cq);
+    __syncthreads();
+  }
+  const rtm::ScanSync scan_sync{a.slot_free, a.slot_free_target, a.tiles_done};
   if (tid < kScanRoleThreads) {
     rtm::Workspace ws = a.post.ws;
     ws.tile_counter = a.tile_tickets;
-    rtm::tma_scan_cta<T, true, 80, kScanTeams>(maps, a.tg, a.post.prm, a.logit_gate, ws,
-                                                rtm::ScanSync{a.slot_free, a.slot_free_target, a.tiles_done},
-                                                static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x), smem_raw, &ctl);
+    rtm::tma_scan_cta<T, true, 80, kScanTeams, LAZY>(maps, a.tg, a.post.prm, a.logit_gate, ws, scan_sync,
+                                                     static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x), smem_raw, &ctl, cq);
+  } else if (LAZY) {
+    // the block's other warps decode the candidates the scan finds (D1), until the scan is over and the queue empty
+    rtm::cand_decoder_warp<T>(cq, a.head, a.tg, a.post.ws);
   }
   __syncthreads();  // the ring is shared memory for the post stage from here on
+  if (LAZY && tid == 0) rtm::scan_publish(scan_sync, &ctl, kScanTeams);  // (after the decoders' stores)
   RTM_STEP_MARK(a.seq, 1);
+  RTM_STEP_MARK(a.seq, 6, (ctl.tl[0] & 0xffffffffull) | (ctl.tl[1] << 32));  // team 0: consumer wait ns | consumer loop ns
+  RTM_STEP_MARK(a.seq, 7, (ctl.tl[3] & 0xffffffffull) | (ctl.tl[2] << 32));  // team 0: producer wait ns | tiles
 
   // ---- post: streams by ticket, on the launch's first CTAs ----
   // (as many as there are streams, 64 at most: with more, the post stages of a large batch would take every CTA slot
@@ -291,12 +304,38 @@ StreamWriteValue32Fn stream_write_value32() {
   return fn;
 }
 
-template <typename T>
-int launch_step_kernel(const cudaLaunchConfig_t& cfg, bool optimal, const rtm::TmaMaps& maps, const StepArgs& a, size_t smem) {
-  if (int rc = rtm::ensure_dynamic_smem(reinterpret_cast<const void*>(optimal ? step_kernel<T, true> : step_kernel<T, false>), smem)) return rc;
-  if (optimal) RTM_CUDA(cudaLaunchKernelEx(&cfg, step_kernel<T, true>, maps, a));
-  else RTM_CUDA(cudaLaunchKernelEx(&cfg, step_kernel<T, false>, maps, a));
+template <typename T, bool LAZY>
+int launch_step_kernel_as(const cudaLaunchConfig_t& cfg, bool optimal, const rtm::TmaMaps& maps, const StepArgs& a, size_t smem) {
+  if (int rc = rtm::ensure_dynamic_smem(reinterpret_cast<const void*>(optimal ? step_kernel<T, true, LAZY> : step_kernel<T, false, LAZY>), smem))
+    return rc;
+  if (optimal) RTM_CUDA(cudaLaunchKernelEx(&cfg, step_kernel<T, true, LAZY>, maps, a));
+  else RTM_CUDA(cudaLaunchKernelEx(&cfg, step_kernel<T, false, LAZY>, maps, a));
   return RTM_OK;
+}
+template <typename T>
+int launch_step_kernel(const cudaLaunchConfig_t& cfg, bool optimal, bool lazy, const rtm::TmaMaps& maps, const StepArgs& a, size_t smem) {
+  return lazy ? launch_step_kernel_as<T, true>(cfg, optimal, maps, a, smem) : launch_step_kernel_as<T, false>(cfg, optimal, maps, a, smem);
+}
+template <typename T>
+const void* step_kernel_ptr(bool optimal, bool lazy) {
+  if (lazy) return optimal ? reinterpret_cast<const void*>(step_kernel<T, true, true>) : reinterpret_cast<const void*>(step_kernel<T, false, true>);
+  return optimal ? reinterpret_cast<const void*>(step_kernel<T, true, false>) : reinterpret_cast<const void*>(step_kernel<T, false, false>);
+}
+// static shared memory of a step kernel variant (the ring depth is chosen so that two CTAs share an SM)
+size_t step_kernel_static_smem(int head_dtype, bool optimal, bool lazy) {
+  static size_t cache[3][2][2] = {};
+  const int d = head_dtype == RTM_F32 ? 0 : (head_dtype == RTM_F16 ? 1 : 2);
+  size_t& v = cache[d][optimal][lazy];
+  if (!v) {
+    const void* f = d == 0 ? step_kernel_ptr<float>(optimal, lazy) : (d == 1 ? step_kernel_ptr<__half>(optimal, lazy) : step_kernel_ptr<__nv_bfloat16>(optimal, lazy));
+    cudaFuncAttributes attr;
+    if (cudaFuncGetAttributes(&attr, f) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return 16 * 1024;
+    }
+    v = attr.sharedSizeBytes;
+  }
+  return v;
 }
 
 void fill_post_args(PostArgs* a, const rtm_step_io* io, const rtm_nms_params* params, size_t work) {
@@ -336,13 +375,24 @@ int step_fused(const rtm_step_io* io, const rtm_nms_params* params, cudaStream_t
   if (!plan.nc80) return 0;
   // ring depth: as many stages as fit into a CTA's share of the SM (two CTAs per SM), the same number for every team
   static const int stages_env = env_int_or("RTM_STEP_STAGES", 0);
-  const size_t budget = 100 * 1024;
+  static const bool lazy_env = env_flag("RTM_STEP_LAZY", true);
+  const bool lazy = lazy_env && plan.tg.cls_tile_bytes % 128 == 0 && kStepThreads > kScanRoleThreads;
+  // dynamic shared memory a CTA may use with a second CTA beside it: half the SM's 228 KB less 1 KB the system keeps per CTA
+  // and the kernel's static part
+  const size_t budget = (228 * 1024 / kStepCtasPerSm - 1024 - step_kernel_static_smem(io->head_dtype, optimal, lazy)) / 128 * 128;
   if (post_smem > budget) return 0;  // (large tables: the two-launch pipeline has the shared memory for them)
-  int stages = stages_env > 0 ? stages_env : static_cast<int>(budget / plan.tg.tile_bytes);
+  // lazy box rows (RTM_STEP_LAZY=0 turns it off): the ring holds class rows only; candidates go through a queue to the
+  // block's other warps, which read the 64 DFL values of each from global memory and decode them beside the scan
+  const size_t stage_bytes = lazy ? plan.tg.cls_tile_bytes : plan.tg.tile_bytes;
+  int stages = stages_env > 0 ? stages_env : static_cast<int>(budget / stage_bytes);
   if (stages > rtm::kMaxStages) stages = rtm::kMaxStages;
+  // (lazy: eight stages fit, but with them the SM's whole shared memory is taken and the L1 that is left slows the post
+  // stages: 28.1 us per step against 23.8 with six; four: 25.6)
+  if (lazy && stages_env <= 0 && stages > 6) stages = 6;
   stages -= stages % kScanTeams;
   if (stages < kScanTeams) return 0;
   plan.tg.stages = stages;
+
   // first ring round static (no ticket round trip before the first load; every CTA of the grid starts at once, see the
   // grid size below), tickets after that (RTM_STEP_STATIC=0: tickets from the first tile on)
   static const int static_env = env_int_or("RTM_STEP_STATIC", 1);
@@ -351,7 +401,7 @@ int step_fused(const rtm_step_io* io, const rtm_nms_params* params, cudaStream_t
   // 34.9 - 38.1 vs 29.6 us per step - the prefetches double the TMA unit's row requests)
   static const int ahead_env = env_int_or("RTM_STEP_L2_AHEAD", 0);
   plan.tg.l2_ahead = ahead_env > 0 ? ahead_env : 0;
-  const size_t ring = static_cast<size_t>(stages) * plan.tg.tile_bytes;
+  const size_t ring = static_cast<size_t>(stages) * stage_bytes;
   const size_t smem = ring > post_smem ? ring : post_smem;
 
   rtm::WorkspaceCtx* ctx = nullptr;
@@ -393,6 +443,9 @@ int step_fused(const rtm_step_io* io, const rtm_nms_params* params, cudaStream_t
   a.caller_mark = a.post.ws.sync;
   a.caller_target = 0;
   a.stream_seq = a.post.ws.sync + rtm::kSyncStreamSeq;
+  a.head[0] = io->head_p3;
+  a.head[1] = io->head_p4;
+  a.head[2] = io->head_p5;
 
   const bool async = io->scan_async != 0;
   cudaStream_t ls = s;
@@ -449,13 +502,13 @@ int step_fused(const rtm_step_io* io, const rtm_nms_params* params, cudaStream_t
     rtm::ProfileScope prof(RTM_K_STEP, ls);
     switch (io->head_dtype) {
       case RTM_F32:
-        rc = launch_step_kernel<float>(cfg, optimal, plan.maps, a, smem);
+        rc = launch_step_kernel<float>(cfg, optimal, lazy, plan.maps, a, smem);
         break;
       case RTM_F16:
-        rc = launch_step_kernel<__half>(cfg, optimal, plan.maps, a, smem);
+        rc = launch_step_kernel<__half>(cfg, optimal, lazy, plan.maps, a, smem);
         break;
       default:
-        rc = launch_step_kernel<__nv_bfloat16>(cfg, optimal, plan.maps, a, smem);
+        rc = launch_step_kernel<__nv_bfloat16>(cfg, optimal, lazy, plan.maps, a, smem);
     }
   }
   if (rc) return rc;

@@ -60,6 +60,18 @@ for seq, r in rows:
     w = r[r[:, 3] > 0]
     print(f"  {seq:4d} | {len(r):3d} {us(r[:,0].min()):8.2f} {us(r[:,0].max()):8.2f} | {us(r[:,1].min()):8.2f} {us(np.median(r[:,1])):8.2f} {us(r[:,1].max()):8.2f} | "
           f"{len(w):3d} {int(w[:,3].sum()):3d} {us(w[:,5].min()):8.2f} {us(w[:,5].max()):8.2f} {us(w[:,2].min()):8.2f} {us(w[:,2].max()):8.2f} | {len(set(r[:,4].astype(int)))}")
+raw = buf[16384:].cpu().numpy().reshape(16, 512, 8)
+cw, cl, pw, nt = [], [], [], []
+for seq, _ in rows:
+    r = raw[seq & 15]
+    live = r[:, 0] > 0
+    cw.append((r[live, 6] & 0xffffffff).astype(np.float64)); cl.append((r[live, 6] >> 32).astype(np.float64))
+    pw.append((r[live, 7] & 0xffffffff).astype(np.float64)); nt.append((r[live, 7] >> 32).astype(np.float64))
+cw, cl, pw, nt = (np.concatenate(x) for x in (cw, cl, pw, nt))
+print("  team 0 of every CTA: tiles %.1f, consumer loop %.2f us of which waiting for a full stage %.2f us (%.0f %%); per tile: %.2f us, "
+      "of which work %.2f us; producer waiting for an empty stage %.2f us" %
+      (nt.mean(), cl.mean() / 1e3, cw.mean() / 1e3, 100 * cw.sum() / max(cl.sum(), 1), cl.sum() / max(nt.sum(), 1) / 1e3,
+       (cl.sum() - cw.sum()) / max(nt.sum(), 1) / 1e3, pw.mean() / 1e3))
 ends = [r[:, 2].max() for _, r in rows]
 print("  step period (last end to last end): mean %.2f us" % (np.diff(ends).mean() / 1e3))
 scan_len = [np.median(r[:, 1]) - r[:, 0].min() for _, r in rows]
