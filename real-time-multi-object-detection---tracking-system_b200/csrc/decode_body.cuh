@@ -220,6 +220,9 @@ struct Pair<__nv_bfloat16> {
   static __device__ __forceinline__ V vmax(V a, V b) { return __hmax2(a, b); }
   static __device__ __forceinline__ float lo(V v) { return __low2float(v); }
   static __device__ __forceinline__ float hi(V v) { return __high2float(v); }
+  // both halves = the largest value of the type that is <= x; 0xffff per half that is greater than the bound
+  static __device__ __forceinline__ V floor_splat(float x) { return __bfloat162bfloat162(__float2bfloat16_rd(x)); }
+  static __device__ __forceinline__ uint32_t gt_mask(V a, V b) { return __hgt2_mask(a, b); }
 };
 template <>
 struct Pair<__half> {
@@ -229,6 +232,8 @@ struct Pair<__half> {
   static __device__ __forceinline__ V vmax(V a, V b) { return __hmax2(a, b); }
   static __device__ __forceinline__ float lo(V v) { return __low2float(v); }
   static __device__ __forceinline__ float hi(V v) { return __high2float(v); }
+  static __device__ __forceinline__ V floor_splat(float x) { return __half2half2(__float2half_rd(x)); }
+  static __device__ __forceinline__ uint32_t gt_mask(V a, V b) { return __hgt2_mask(a, b); }
 };
 template <>
 struct Pair<float> {
@@ -238,6 +243,8 @@ struct Pair<float> {
   static __device__ __forceinline__ V vmax(V a, V b) { return make_float2(fmaxf(a.x, b.x), fmaxf(a.y, b.y)); }
   static __device__ __forceinline__ float lo(V v) { return v.x; }
   static __device__ __forceinline__ float hi(V v) { return v.y; }
+  static __device__ __forceinline__ V floor_splat(float x) { return make_float2(x, x); }
+  static __device__ __forceinline__ uint32_t gt_mask(V a, V b) { return (a.x > b.x ? 0xffffu : 0u) | (a.y > b.y ? 0xffff0000u : 0u); }
 };
 
 // exact N1 of one anchor column for the lanes of its four class quarters: probability and index
@@ -300,7 +307,8 @@ __device__ __forceinline__ void anchor_best(const T* cls_col, const int q, const
 struct ScanCtl {
   uint64_t full_bar[kMaxStages];
   uint64_t empty_bar[kMaxStages];
-  int4 tile[kMaxStages];  // per stage: (stream, level, first anchor of the tile within the level, -); x < 0 = no more tiles
+  int4 tile[kMaxStages];  // per stage: (stream, level, first anchor of the tile within the level, anchors of the level from there on); x < 0 = no more tiles
+  int mask_off[kMaxStages];  // per stage: byte offset of the tile's first anchor in the candidate mask
   int next[kMaxStages];   // ticket drawn for the stage's next fill (producer lane only)
   int issued[4];          // tiles each team's producer has handed to its consumers
   unsigned long long tl[4];  // RTM_TIMELINE builds: team 0's consumer wait ns, loop ns, tiles; its producer's wait ns
@@ -449,12 +457,14 @@ __device__ __forceinline__ void tma_scan_cta(const TmaMaps& maps, const TmaGeom&
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map1)) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map2)) : "memory");
       int handed = 0;  // tiles this producer has handed to its team
+      const int mask_row_bytes = ws.words * 4;
       auto issue = [&](int s, int t) {
         ++handed;
         const int b = t / tps, r = t - b * tps;
         const int li = r >= tb2 ? 2 : (r >= tb1 ? 1 : 0);
         const int x = (r - (li == 2 ? tb2 : (li == 1 ? tb1 : 0))) * kTileW;
-        ctl->tile[s0 + s] = make_int4(b, li, x, 0);
+        ctl->mask_off[s0 + s] = b * mask_row_bytes + ((tg.g.lv[li].anchor0 + x) >> 3);
+        ctl->tile[s0 + s] = make_int4(b, li, x, tg.g.lv[li].hw - x);
         mbar_expect_tx(&full_bar[s0 + s], stage_bytes);
         tma_load_tile(tile_smem + static_cast<size_t>(s0 + s) * stage_bytes, li == 0 ? &map0 : (li == 1 ? &map1 : &map2),
                       &full_bar[s0 + s], x, LAZY ? kBoxCh : 0, b, policy);
@@ -558,8 +568,8 @@ __device__ __forceinline__ void tma_scan_cta(const TmaMaps& maps, const TmaGeom&
     const int w0 = tg.g.lv[0].w, w1 = tg.g.lv[1].w, w2 = tg.g.lv[2].w;
     const int a1 = tg.g.lv[1].anchor0, a2 = tg.g.lv[2].anchor0;
     const int st0 = tg.g.lv[0].stride, st1 = tg.g.lv[1].stride, st2 = tg.g.lv[2].stride;
-    const int hw0 = tg.g.lv[0].hw, hw1 = tg.g.lv[1].hw, hw2 = tg.g.lv[2].hw;
     uint8_t* mask_bytes = reinterpret_cast<uint8_t*>(ws.mask);
+    const typename P::V gate_pair = P::floor_splat(logit_gate);
 
     auto level_of = [&](int li, int* lv_w, int* lv_stride, int* lv_anchor0) {
       *lv_w = li == 2 ? w2 : (li == 1 ? w1 : w0);
@@ -607,12 +617,10 @@ __device__ __forceinline__ void tma_scan_cta(const TmaMaps& maps, const TmaGeom&
 #else
       mbar_wait(&full_bar[s], phase);
 #endif
-      int b, li, x0;
-      asm volatile("ld.volatile.shared.v4.s32 {%0, %1, %2, _}, [%3];" : "=r"(b), "=r"(li), "=r"(x0) : "r"(smem_u32(&ctl->tile[s])));
+      int b, li, x0, left;
+      asm volatile("ld.volatile.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(b), "=r"(li), "=r"(x0), "=r"(left) : "r"(smem_u32(&ctl->tile[s])));
       if (b < 0) break;
-      int lv_w, lv_stride, lv_anchor0;
-      level_of(li, &lv_w, &lv_stride, &lv_anchor0);
-      const int lv_hw = li == 2 ? hw2 : (li == 1 ? hw1 : hw0);
+      const int mask_off = ld_volatile_shared(&ctl->mask_off[s]) + 2 * wit;  // (before the stage can be handed back)
       const int pix = x0 + col;
       const T* tile = reinterpret_cast<const T*>(tile_smem + static_cast<size_t>(s) * stage_bytes);
       const T* cls_rows = LAZY ? tile : tile + kBoxCh * kTileW;  // first class row of the tile
@@ -629,13 +637,14 @@ __device__ __forceinline__ void tma_scan_cta(const TmaMaps& maps, const TmaGeom&
       }
       // anchors past the end of the level (zero-filled tail of the last tile) never pass; the test is
       // warp-uniform because every level holds a multiple of 16 anchors
-      const bool in_level = pix < lv_hw;
+      const bool in_level = col < left;
       const float m0 = in_level ? P::lo(mv) : -INFINITY, m1 = in_level ? P::hi(mv) : -INFINITY;
       float am = fmaxf(m0, m1);
       am = fmaxf(am, __shfl_xor_sync(kFull, am, 8));
       am = fmaxf(am, __shfl_xor_sync(kFull, am, 16));
 
       bool cand0 = false, cand1 = false, released = false;
+      uint32_t mask_bits = 0u;  // (lane 0)
       if (__any_sync(kFull, am > logit_gate)) {
         // ---- exact N1 for the anchors that can pass, then D1 for the survivors ----
         float best0 = -1.f, best1 = -1.f;
@@ -643,13 +652,16 @@ __device__ __forceinline__ void tma_scan_cta(const TmaMaps& maps, const TmaGeom&
         if (NC80) {
           // both anchors of the lane in one sweep: a packed load yields the two class values of a row
           if (m0 > logit_gate || m1 > logit_gate) {
-            unsigned bits0 = 0u, bits1 = 0u;
+            // which of the quarter's 20 classes can pass: a packed compare against the gate rounded DOWN to the element
+            // type (a superset of the classes above the gate; what it adds cannot reach the confidence threshold)
+            unsigned lo16 = 0u, hi4 = 0u;  // classes 0..15: anchor 0 in the low half, anchor 1 in the high half; 16..19 likewise
 #pragma unroll
-            for (int i = 0; i < 20; ++i) {
-              const typename P::V v = P::load(cls_col + 4 * i * kTileW);
-              bits0 |= (P::lo(v) > logit_gate ? 1u : 0u) << i;
-              bits1 |= (P::hi(v) > logit_gate ? 1u : 0u) << i;
-            }
+            for (int i = 0; i < 16; ++i)
+              lo16 |= P::gt_mask(P::load(cls_col + 4 * i * kTileW), gate_pair) & ((1u << i) | (1u << (i + 16)));
+#pragma unroll
+            for (int i = 16; i < 20; ++i)
+              hi4 |= P::gt_mask(P::load(cls_col + 4 * i * kTileW), gate_pair) & ((1u << (i - 16)) | (1u << i));
+            unsigned bits0 = (lo16 & 0xffffu) | ((hi4 & 0xfu) << 16), bits1 = (lo16 >> 16) | (((hi4 >> 16) & 0xfu) << 16);
             while (bits0) {  // ascending classes, strict >: the first maximum (torch's max(1) on the sigmoid tensor)
               const int i = __ffs(bits0) - 1;
               bits0 &= bits0 - 1;
@@ -688,9 +700,19 @@ __device__ __forceinline__ void tma_scan_cta(const TmaMaps& maps, const TmaGeom&
         }
         cand0 = best0 > prm.conf_thres && class_wanted(prm, bc0 & 255);
         cand1 = best1 > prm.conf_thres && class_wanted(prm, bc1 & 255);
+        const unsigned m0b = __ballot_sync(kFull, cand0 && q == 0) & 0xffu, m1b = __ballot_sync(kFull, cand1 && q == 0) & 0xffu;
+        if (lane == 0) {  // candidate bits of the warp's 16 anchors, even and odd anchors interleaved
+          uint32_t even = m0b, odd = m1b;
+          even = (even | (even << 4)) & 0x0f0fu;
+          even = (even | (even << 2)) & 0x3333u;
+          even = (even | (even << 1)) & 0x5555u;
+          odd = (odd | (odd << 4)) & 0x0f0fu;
+          odd = (odd | (odd << 2)) & 0x3333u;
+          odd = (odd | (odd << 1)) & 0x5555u;
+          mask_bits = even | (odd << 1);
+        }
         if (LAZY) {
           // hand the candidates to the decoder warps: the warp goes on with its next tile
-          const unsigned m0b = __ballot_sync(kFull, cand0 && q == 0), m1b = __ballot_sync(kFull, cand1 && q == 0);
           if (m0b | m1b) {
             int base = 0;
             if (lane == 0) base = atomicAdd(&cq->tail, __popc(m0b) + __popc(m1b));
@@ -719,18 +741,10 @@ __device__ __forceinline__ void tma_scan_cta(const TmaMaps& maps, const TmaGeom&
           decode_and_store(x0v, x1v, cand0, cand1, best0, best1, bc0, bc1, b, li, pix);
         }
       }
-      // candidate bits of this warp's 16 anchors: two bytes of the stream's mask
-      uint32_t even = __ballot_sync(kFull, cand0 && q == 0) & 0xffu, odd = __ballot_sync(kFull, cand1 && q == 0) & 0xffu;
-      if (lane == 0 && in_level) {
-        even = (even | (even << 4)) & 0x0f0fu;
-        even = (even | (even << 2)) & 0x3333u;
-        even = (even | (even << 1)) & 0x5555u;
-        odd = (odd | (odd << 4)) & 0x0f0fu;
-        odd = (odd | (odd << 2)) & 0x3333u;
-        odd = (odd | (odd << 1)) & 0x5555u;
-        *reinterpret_cast<uint16_t*>(mask_bytes + static_cast<size_t>(b) * ws.words * 4 + ((lv_anchor0 + pix) >> 3)) =
-            static_cast<uint16_t>(even | (odd << 1));
-      }
+      // candidate bits of this warp's 16 anchors: two bytes of the stream's mask (written whether or not any is set:
+      // nothing clears the mask between frames)
+      if (lane == 0 && in_level)
+        *reinterpret_cast<uint16_t*>(mask_bytes + static_cast<uint32_t>(mask_off)) = static_cast<uint16_t>(mask_bits);
       if (!released) {
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[s]);  // this warp is done with the stage
