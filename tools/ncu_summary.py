@@ -19,7 +19,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-OURS = ("track_step_kernel", "zone_step_kernel", "step_kernel", "letterbox_decimate3_kernel", "decode_tma_kernel", "decode_ldg_kernel", "post_kernel", "nms_kernel",
+OURS = ("track_step_kernel", "zone_step_kernel", "step_kernel", "letterbox_decimate3_wide_kernel", "letterbox_tile_kernel", "letterbox_decimate3_kernel", "decode_tma_kernel", "decode_ldg_kernel", "post_kernel", "nms_kernel",
         "letterbox_kernel", "pred_candidates_kernel", "decode_head_kernel", "kalman", "lapjv")
 
 METRICS = [
