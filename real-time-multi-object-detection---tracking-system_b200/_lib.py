@@ -238,9 +238,21 @@ def ptr(t) -> int:
     return None if t is None else t.data_ptr()
 
 
-def cuda_stream() -> int:
+_raw_stream = None
+
+
+def cuda_stream(device_index=None) -> int:
+    """Handle of torch's current CUDA stream on ``device_index`` (default: the current device).  The raw getter is a
+    tenth of the cost of building a ``torch.cuda.Stream`` object (0.3 vs 3.3 us - a quarter of a step's host side)."""
+    global _raw_stream
     import torch
-    return torch.cuda.current_stream().cuda_stream
+    if _raw_stream is None:
+        _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", False)
+    if _raw_stream:
+        return _raw_stream(torch.cuda.current_device() if device_index is None else device_index)
+    if device_index is None:
+        return torch.cuda.current_stream().cuda_stream
+    return torch.cuda.current_stream(device_index).cuda_stream
 
 
 def dtype_code(torch_dtype) -> int:

@@ -22,6 +22,8 @@
 //   2. post_kernel (this file)            one CTA per stream: NMS -> tracker step -> zone step
 #include <stdlib.h>
 
+#include <chrono>
+#include <stdio.h>
 #include "decode_body.cuh"
 #include "track_body.cuh"
 #include "zone_body.cuh"
@@ -365,13 +367,40 @@ void fill_post_args(PostArgs* a, const rtm_step_io* io, const rtm_nms_params* pa
   a->work_bytes = static_cast<int>(work);
 }
 
+// RTM_HOST_TIMING=1: where the host side of a step goes (std::chrono between the sections of step_fused, printed every
+// 1000 calls)
+struct HostTiming {
+  bool on = env_flag("RTM_HOST_TIMING", false);
+  std::chrono::steady_clock::time_point t;
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  long calls = 0;
+  void start() {
+    if (on) t = std::chrono::steady_clock::now();
+  }
+  void lap(int i) {
+    if (!on) return;
+    const auto n = std::chrono::steady_clock::now();
+    acc[i] += std::chrono::duration<double, std::micro>(n - t).count();
+    t = n;
+  }
+  void end() {
+    if (!on || ++calls % 1000) return;
+    fprintf(stderr, "rtm host timing, us per step: plan %.2f  workspace %.2f  args %.2f  caller mark %.2f  launch %.2f  done event %.2f\n",
+            acc[0] / 1000, acc[1] / 1000, acc[2] / 1000, acc[3] / 1000, acc[4] / 1000, acc[5] / 1000);
+    for (double& a : acc) a = 0;
+  }
+};
+
 // The one-launch step.  Returns 1 when it was enqueued, 0 when the caller should take the two-launch path.
 int step_fused(const rtm_step_io* io, const rtm_nms_params* params, cudaStream_t s, size_t work, size_t post_smem) {
   const int B = io->table_in->num_streams;
   const bool optimal = io->assignment == RTM_ASSIGN_OPTIMAL;
+  static HostTiming ht;
+  ht.start();
   rtm::TmaScanPlan plan;
   int rc = rtm::plan_tma_scan80(io->head_p3, io->head_p4, io->head_p5, io->head_dtype, B, io->img_h, io->img_w, params, &plan);
   if (rc <= 0) return rc;
+  ht.lap(0);
   if (!plan.nc80) return 0;
   // ring depth: as many stages as fit into a CTA's share of the SM (two CTAs per SM), the same number for every team
   static const int stages_env = env_int_or("RTM_STEP_STAGES", 0);
@@ -411,6 +440,7 @@ int step_fused(const rtm_step_io* io, const rtm_nms_params* params, cudaStream_t
   rc = rtm::take_scan_slot(ctx, io->workspace, io->workspace_bytes, B, plan.tg.g.num_anchors, &a.post.ws);
   if (rc) return rc;
   const int slot = a.post.ws.slot;
+  ht.lap(1);
   fill_post_args(&a.post, io, params, work);
   a.tg = plan.tg;
   a.logit_gate = plan.logit_gate;
@@ -450,6 +480,7 @@ int step_fused(const rtm_step_io* io, const rtm_nms_params* params, cudaStream_t
   const bool async = io->scan_async != 0;
   cudaStream_t ls = s;
   bool pdl = false;
+  ht.lap(2);
   if (async) {
     rc = rtm::workspace_streams(ctx);
     if (rc) return rc;
@@ -487,6 +518,7 @@ int step_fused(const rtm_step_io* io, const rtm_nms_params* params, cudaStream_t
     ctx->chain_streams = 0;
   }
   a.chain = pdl ? 1 : 0;
+  ht.lap(3);
 
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
@@ -513,10 +545,13 @@ int step_fused(const rtm_step_io* io, const rtm_nms_params* params, cudaStream_t
   }
   if (rc) return rc;
   RTM_LAUNCH_CHECK("step_kernel");
+  ht.lap(4);
   if (async) {
     RTM_CUDA(cudaEventRecord(ctx->done[slot], ls));
     RTM_CUDA(cudaStreamWaitEvent(s, ctx->done[slot], 0));
   }
+  ht.lap(5);
+  ht.end();
   return 1;
 }
 

@@ -410,10 +410,10 @@ class StreamBatch:
             io.scan_async, io.results_alternate = 1, 1           # the result buffers alternate with the tables
             io.heads_ready_event = None if heads_ready is True else heads_ready.cuda_event
         if torch.cuda.current_device() == self.device.index:
-            rc = self.lib.rtm_post_backbone_step(C.byref(io), C.byref(self.params), torch.cuda.current_stream().cuda_stream)
+            rc = self.lib.rtm_post_backbone_step(C.byref(io), C.byref(self.params), _lib.cuda_stream(self.device.index))
         else:
             with torch.cuda.device(self.device):
-                rc = self.lib.rtm_post_backbone_step(C.byref(io), C.byref(self.params), torch.cuda.current_stream().cuda_stream)
+                rc = self.lib.rtm_post_backbone_step(C.byref(io), C.byref(self.params), _lib.cuda_stream(self.device.index))
         if rc:
             _lib.check(rc)
         self._advance()
