@@ -447,7 +447,7 @@ int step_fused(const rtm_step_io* io, const rtm_nms_params* params, cudaStream_t
   a.num_streams = B;
   a.seq = ctx->seq++;
   // every CTA scans, the first `post_workers` of them then work through the post stages.  A launch that runs by
-  // itself (ordinary launch) takes all CTA slots but the ones its post workers will keep.  In a chain of programmatic
+  // itself (ordinary launch) takes all CTA slots (59.2 us per step with the workers' slots left free, 58.4 with all).  In a chain of programmatic
   // dependent launches the grid is 3/8 of the slots: every CTA of a launch must have started before the next launch
   // can, so with small grids two or three launches are resident at any time and their scans overlap continuously -
   // no ramp and tail per launch (measured, 64 streams: 232 CTAs 29.2 us per step, 148: 28.3, 111: 27.6, 64: 26.9;
@@ -455,7 +455,7 @@ int step_fused(const rtm_step_io* io, const rtm_nms_params* params, cudaStream_t
   static const int grid_env = env_int_or("RTM_STEP_GRID", 0), workers_env = env_int_or("RTM_STEP_POST_CTAS", 64);
   a.post_workers = max(1, min(B, workers_env));
   const int slots = rtm::sm_count() * kStepCtasPerSm;
-  const int want = grid_env > 0 ? grid_env : (io->scan_async ? max(slots * 3 / 8, a.post_workers) : slots - a.post_workers);
+  const int want = grid_env > 0 ? grid_env : (io->scan_async ? max(slots * 3 / 8, a.post_workers) : slots);
   const int grid = max(a.post_workers, min((plan.tg.total_tiles + kScanTeams - 1) / kScanTeams, want));
   int* slot_words = a.post.ws.tile_counter;  // the slot's 32 header words
   a.post.ws.tile_counter = nullptr;
