@@ -5,9 +5,13 @@
 // A tile = all 64 + nc channels x kTileW consecutive anchors of one (stream, level), fetched by one TMA
 // tensor copy into a ring of shared-memory stages (full / empty mbarriers).  A CTA holds GROUPS teams, each a
 // ring of its own, a producer warp (one elected lane) that keeps it full and kTileW / 16 consumer warps that work on its tiles
-// independently of each other, without a block barrier (one team per CTA in the stand-alone kernel, three in
-// the step kernel, which has an SM to itself).  Tiles are handed out by a ticket counter after a static first
+// independently of each other, without a block barrier (one team per CTA in the stand-alone kernel, two in
+// the step kernel, two of whose CTAs share an SM).  Tiles are handed out by a ticket counter after a static first
 // ring round, so whichever CTAs are resident share the work evenly.
+//
+// LAZY (the step kernel's default): a tile is the nc CLASS rows only.  Consumer warps do N1 and push their candidates
+// into a shared-memory queue (CandQueue); the block's other warps (cand_decoder_warp) read the 64 DFL values of every
+// candidate from global memory and do D1 beside the scan - the box rows of anchors that are no candidates are never read.
 #pragma once
 
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through the runtime)

@@ -7,7 +7,7 @@ TAG=${1:-r2b}
 mkdir -p gpurun_out
 SHORT="python bench.py --steps 6 --warmup 3 --no-e2e --no-cpu --no-extras --no-parity"
 timeout 300 python tools/diag_dist.py --tag final --reps 3 2>&1 | grep ^diag | cut -c1-400
-timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_${TAG}.log 2>&1
+timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_${TAG}.log 2>&1; timeout 300 python __graft_entry__.py --smoke > gpurun_out/smoke_${TAG}.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/smoke_${TAG}.log
 echo "pytest rc=$?"; tail -3 gpurun_out/pytest_${TAG}.log | cut -c1-300
 timeout 900 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/bench_ref_${TAG}.json 2> gpurun_out/bench_ref_${TAG}.err
 echo "bench reference rc=$?"
