@@ -98,6 +98,12 @@ __device__ __forceinline__ void store_candidate(const Workspace& ws, int b, int 
 // ---------------------------------------------------------------------------------------
 constexpr int kAnchorsPerWarp = 16;  // a lane owns 2 adjacent anchors x one class quarter
 constexpr int kMaxStages = 12;
+// anchors per tile of the one-launch step kernel (experiments: -DRTM_STEP_TILE_W=64 | 128; 80 divides every level of a
+// 640 x 640 input exactly, other widths leave zero-filled tails that are masked out)
+#ifndef RTM_STEP_TILE_W
+#define RTM_STEP_TILE_W 80
+#endif
+constexpr int kStepTileW = RTM_STEP_TILE_W;
 constexpr int tma_consumer_warps(int tile_w) { return tile_w / kAnchorsPerWarp; }
 // threads of a scan CTA: GROUPS teams, each its consumer warps + a producer warp
 constexpr int tma_threads(int tile_w, int groups = 1) { return groups * (tma_consumer_warps(tile_w) + 1) * 32; }
@@ -495,7 +501,7 @@ __device__ __forceinline__ void tma_scan_cta(const TmaMaps& maps, const TmaGeom&
         const int x = (r - (li == 2 ? tb2 : (li == 1 ? tb1 : 0))) * kTileW;
         asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(
                          reinterpret_cast<uint64_t>(li == 0 ? &map0 : (li == 1 ? &map1 : &map2))),
-                     "r"(x), "r"(0), "r"(b)
+                     "r"(x), "r"(LAZY ? kBoxCh : 0), "r"(b)
                      : "memory");
       };
       // first round of the ring: tiles vcta + k * vgrid, no ticket needed; the tickets of the

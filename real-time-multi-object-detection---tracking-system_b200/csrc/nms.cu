@@ -1034,17 +1034,18 @@ int rtm::plan_tma_scan80(const void* p3, const void* p4, const void* p5, int hea
   for (const void* p : {p3, p4, p5})
     RTM_REQUIRE((reinterpret_cast<uintptr_t>(p) & 15) == 0, "head tensors must be 16-byte aligned");
   if (decode_impl() != 1 || env_int("RTM_TMA_TILEW", 80) != 80) return 0;
-  for (int l = 0; l < 3; ++l)
-    if (g.lv[l].hw % 80 != 0) return 0;
+  if (rtm::kStepTileW == 80)
+    for (int l = 0; l < 3; ++l)
+      if (g.lv[l].hw % 80 != 0) return 0;
   plan->logit_gate = logit_gate_for(params->conf_thres);
   plan->nc80 = g.num_classes == 80;
   switch (head_dtype) {
     case RTM_F32:
-      return plan_tma_scan<float, 80>(p3, p4, p5, g, num_streams, &plan->maps, &plan->tg);
+      return plan_tma_scan<float, rtm::kStepTileW>(p3, p4, p5, g, num_streams, &plan->maps, &plan->tg);
     case RTM_F16:
-      return plan_tma_scan<__half, 80>(p3, p4, p5, g, num_streams, &plan->maps, &plan->tg);
+      return plan_tma_scan<__half, rtm::kStepTileW>(p3, p4, p5, g, num_streams, &plan->maps, &plan->tg);
     case RTM_BF16:
-      return plan_tma_scan<__nv_bfloat16, 80>(p3, p4, p5, g, num_streams, &plan->maps, &plan->tg);
+      return plan_tma_scan<__nv_bfloat16, rtm::kStepTileW>(p3, p4, p5, g, num_streams, &plan->maps, &plan->tg);
     default:
       RTM_REQUIRE(false, "unknown head_dtype %d", head_dtype);
   }

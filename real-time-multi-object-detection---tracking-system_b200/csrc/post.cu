@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(kPostThreads, RTM_POST_CTAS_PER_SM) post_kerne
 constexpr int kScanTeams = 2;
 constexpr int kStepThreads = kPostThreads;
 constexpr int kStepCtasPerSm = 2;
-constexpr int kScanRoleThreads = rtm::tma_threads(80, kScanTeams);
+constexpr int kScanRoleThreads = rtm::tma_threads(rtm::kStepTileW, kScanTeams);
 static_assert(kScanRoleThreads <= kStepThreads, "the scan role must fit the step kernel's block");
 
 struct StepArgs {
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(kStepThreads, kStepCtasPerSm) step_kernel(cons
   if (tid < kScanRoleThreads) {
     rtm::Workspace ws = a.post.ws;
     ws.tile_counter = a.tile_tickets;
-    rtm::tma_scan_cta<T, true, 80, kScanTeams, LAZY>(maps, a.tg, a.post.prm, a.logit_gate, ws, scan_sync,
+    rtm::tma_scan_cta<T, true, rtm::kStepTileW, kScanTeams, LAZY>(maps, a.tg, a.post.prm, a.logit_gate, ws, scan_sync,
                                                      static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x), smem_raw, &ctl, cq);
   } else if (LAZY) {
     // the block's other warps decode the candidates the scan finds (D1), until the scan is over and the queue empty
