@@ -615,8 +615,9 @@ def e2e_bench(pkg, wl, sb, f0, K, W, total_streams, world, dev, pinned_frames=4)
         for f in range(first, first + n):
             res = feeder.step_pinned(pinned[order[f % len(order)]], now=T0 + f / FPS, frame_id=f)
             results.append(res)
-            if len(results) > 2:
-                results.pop(0).wait()                     # consume the results of step k-2 on the host
+            if len(results) > 1:
+                results.pop(0).wait()                     # consume the results of step k-1 on the host (two slots: step
+                                                          # k-2's buffers already belong to step k)
         while results:
             results.pop(0).wait()
 

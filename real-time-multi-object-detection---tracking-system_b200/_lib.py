@@ -131,7 +131,8 @@ class StepHostIO(C.Structure):
                 ("host_det_xyxy", C.c_void_p), ("host_det_conf", C.c_void_p),
                 ("host_det_cls", C.c_void_p), ("host_det_track_id", C.c_void_p),
                 ("host_det_count", C.c_void_p), ("host_status", C.c_void_p),
-                ("wait_event", C.c_void_p), ("done_event", C.c_void_p), ("host_event_stride", C.c_int32)]
+                ("wait_event", C.c_void_p), ("done_event", C.c_void_p), ("host_event_stride", C.c_int32),
+                ("copy_wait_event", C.c_void_p), ("copy_done_event", C.c_void_p)]
 
 
 #: every symbol include/rtmodt_b200.h declares: name -> (restype, argtypes)

@@ -160,6 +160,7 @@ extern "C" int rtm_post_backbone_step_host(const rtm_step_io* io, const rtm_step
   const int strides[3] = {8, 16, 32};
   size_t bytes[3];
   for (int l = 0; l < 3; ++l) bytes[l] = B * ch * (static_cast<size_t>(io->img_h / strides[l]) * (io->img_w / strides[l])) * es;
+  if (h->copy_wait_event) RTM_CUDA(cudaStreamWaitEvent(s, static_cast<cudaEvent_t>(h->copy_wait_event), 0));
   const char *s0 = static_cast<const char*>(src[0]), *d0 = static_cast<const char*>(dst[0]);
   if (src[1] == s0 + bytes[0] && src[2] == s0 + bytes[0] + bytes[1] && dst[1] == d0 + bytes[0] && dst[2] == d0 + bytes[0] + bytes[1]) {
     // the three levels are back to back on both sides: one transfer (a few percent more PCIe throughput)
@@ -167,6 +168,7 @@ extern "C" int rtm_post_backbone_step_host(const rtm_step_io* io, const rtm_step
   } else {
     for (int l = 0; l < 3; ++l) RTM_CUDA(cudaMemcpyAsync(dst[l], src[l], bytes[l], cudaMemcpyHostToDevice, s));
   }
+  if (h->copy_done_event) RTM_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(h->copy_done_event), s));
   if (h->wait_event) RTM_CUDA(cudaStreamWaitEvent(s, static_cast<cudaEvent_t>(h->wait_event), 0));
   int rc = rtm_post_backbone_step(io, params, stream);
   if (rc) return rc;

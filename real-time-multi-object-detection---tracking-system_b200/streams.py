@@ -549,21 +549,35 @@ class StreamBatch:
 class StepResult:
     """Results of one host-fed step; ``wait()`` blocks until its device->host copies landed."""
 
-    def __init__(self, feeder: "HostFeeder", slot: dict) -> None:
-        self._feeder, self._slot = feeder, slot
+    def __init__(self, feeder: "HostFeeder", slot: dict, index: int) -> None:
+        self._feeder, self._slot, self._index = feeder, slot, index
+
+    @property
+    def stale(self) -> bool:
+        """The slot has been handed to a later step (``depth`` steps on): its host buffers hold that step's results."""
+        return self._feeder.k > self._index + self._feeder.depth
 
     def wait(self) -> "StepResult":
-        self._slot["done"].synchronize()
-        _lib.raise_on_status(self._slot["status"].numpy(), "HostFeeder")
+        # (a stale result is complete - the feeder synchronised on it before reusing the slot - and the slot's event now
+        # belongs to the later step: waiting on it would wait for THAT step and stall the caller's pipeline)
+        if not self.stale:
+            self._slot["done"].synchronize()
+            _lib.raise_on_status(self._slot["status"].numpy(), "HostFeeder")
         return self
+
+    def _fresh(self) -> None:
+        if self.stale:
+            raise _lib.RtmError(f"HostFeeder: the results of step {self._index} were overwritten by step "
+                                f"{self._index + self._feeder.depth}; read a step's results before {self._feeder.depth} more steps are enqueued")
+        self.wait()
 
     @property
     def det_count(self) -> np.ndarray:
-        self.wait()
+        self._fresh()
         return self._slot["det_count"].numpy().copy()
 
     def detections(self):
-        self.wait()
+        self._fresh()
         s = self._slot
         n = s["det_count"].numpy()
         return [dict(xyxy=s["det_xyxy"].numpy()[b, :n[b]].copy(), confidence=s["det_conf"].numpy()[b, :n[b]].copy(),
@@ -571,7 +585,7 @@ class StepResult:
                 for b in range(len(n))]
 
     def events(self, class_names=None):
-        self.wait()
+        self._fresh()
         z = self._feeder.batch.zones
         if z is None:
             return [[] for _ in range(self._feeder.batch.B)]
@@ -617,11 +631,12 @@ class HostFeeder:
         with torch.cuda.device(dev):
             for _ in range(self.depth):
                 stream = torch.cuda.Stream(device=dev)
-                done = torch.cuda.Event()
-                done.record(stream)                          # materialise the cudaEvent_t handle
+                done, copied = torch.cuda.Event(), torch.cuda.Event()
+                done.record(stream)                          # materialise the cudaEvent_t handles
+                copied.record(stream)
                 ev_stride = self.event_prefix
                 self.slots.append(dict(
-                    stream=stream, done=done,
+                    stream=stream, done=done, copied=copied,
                     host_heads=views(pin((total,), head_dtype)),
                     dev_heads=views(torch.empty(total, dtype=head_dtype, device=dev)),
                     events=pin((B, ev_stride, 64), torch.uint8), event_count=pin((B,), torch.int32).zero_(),
@@ -685,9 +700,13 @@ class HostFeeder:
         h.host_event_stride = self.event_prefix
         h.wait_event = prev["done"].cuda_event if self.k > 0 and self.depth > 1 else None
         h.done_event = slot["done"].cuda_event
+        # the copies of consecutive steps follow each other on the link (side by side they end side by side and the link
+        # idles while both streams run their kernels)
+        h.copy_wait_event = prev["copied"].cuda_event if self.k > 0 and self.depth > 1 else None
+        h.copy_done_event = slot["copied"].cuda_event
         with torch.cuda.device(b.device):
             _lib.check(self.lib.rtm_post_backbone_step_host(C.byref(io), C.byref(h), C.byref(b.params),
                                                             slot["stream"].cuda_stream))
         b._advance()
         self.k += 1
-        return StepResult(self, slot)
+        return StepResult(self, slot, self.k - 1)

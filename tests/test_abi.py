@@ -38,7 +38,7 @@ def test_struct_layouts_match_the_header(pkg):
     assert ctypes.sizeof(L.NmsParams) == 8 + 4 * 4 + 32
     assert ctypes.sizeof(L.TrackTable) == 8 + 8 * 8
     assert ctypes.sizeof(L.ZoneSet) == 8 + 6 * 8
-    assert ctypes.sizeof(L.StepHostIO) == 14 * 8
+    assert ctypes.sizeof(L.StepHostIO) == 16 * 8
 
 
 def test_compute_entry_points_refuse_to_run_without_a_gpu(pkg):

@@ -324,6 +324,29 @@ def test_host_feeder_copies_event_heads_only_and_says_so(pkg):
     assert [len(e) for e in res.events()] == [len(e) for e in sb.read_events()]
 
 
+def test_host_feeder_results_outlived_by_their_slot(pkg):
+    """A result whose slot has been handed to a later step (two slots: two steps on) is complete but gone: waiting on
+    it returns at once - it must not wait for the LATER step, which would stall a pipelined caller (that cost the
+    end-to-end bench 4 % once) - and reading it raises instead of returning the later step's data."""
+    import torch
+    B = 2
+    frames = moving_heads(pkg, B, 4, seed=4, n_obj=6)
+    sb = pkg.StreamBatch(B, None, src_hw=(1080, 1920), classes=WANTED, max_tracks=64)
+    feeder = pkg.HostFeeder(sb, torch.bfloat16)
+    res = [feeder.step([torch.from_numpy(h).to(torch.bfloat16) for h in heads], now=5.0 + f, frame_id=f)
+           for f, heads in enumerate(frames)]
+    assert [r.stale for r in res] == [True, True, False, False]
+    assert res[0].wait() is res[0]
+    with pytest.raises(pkg.RtmError, match="overwritten"):
+        res[1].detections()
+    got = res[3].detections()
+    dev = sb.read_detections()
+    for b in range(B):
+        np.testing.assert_array_equal(got[b]["track_id"], dev[b]["track_id"])
+        np.testing.assert_array_equal(got[b]["xyxy"], dev[b]["xyxy"])
+    assert len(res[2].detections()) == B
+
+
 @pytest.mark.parametrize("kalman", [False, True])
 def test_state_export_import_resumes_bit_exactly(pkg, kalman):
     """rtm_state_export / rtm_state_import (checkpoint / resume): a batch resumed from a blob in
