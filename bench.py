@@ -337,6 +337,27 @@ def workload_config(args, total_streams):
 
 # ---------------------------------------------------------------------------
 # the CUDA arm
+def bind_to_gpu_node(index, uuid):
+    """One process per GPU: run this process on the CPUs NVML names as closest to its GPU, before anything is
+    allocated, so that its pinned staging buffers land on the GPU's NUMA node (first touch).  Returns the number of
+    CPUs bound to, or None when NVML has no affinity to offer (RTM_BENCH_AFFINITY=0 turns it off)."""
+    if os.environ.get("RTM_BENCH_AFFINITY", "1") == "0":
+        return None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByUUID(f"GPU-{uuid}".encode()) if uuid else pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return None
+
+
 # ---------------------------------------------------------------------------
 def run_b200(args):
     import numpy as np
@@ -349,6 +370,7 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    affinity = bind_to_gpu_node(local, getattr(torch.cuda.get_device_properties(dev), "uuid", None)) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ge = importlib.import_module("__graft_entry__")
@@ -502,6 +524,8 @@ def run_b200(args):
         e2e = None
         if not args.no_e2e:
             e2e = e2e_bench(pkg, wl, sb, state["f"], K, W, total_streams, world, dev)
+            e2e["cpu_affinity"] = (f"rank bound to the {affinity} CPUs NVML names as closest to its GPU (pinned buffers on that node)"
+                                   if affinity else "not bound")
             state["f"] += K + W
         sb.check_status()
 
