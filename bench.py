@@ -337,27 +337,6 @@ def workload_config(args, total_streams):
 
 # ---------------------------------------------------------------------------
 # the CUDA arm
-def bind_to_gpu_node(index, uuid):
-    """One process per GPU: run this process on the CPUs NVML names as closest to its GPU, before anything is
-    allocated, so that its pinned staging buffers land on the GPU's NUMA node (first touch).  Returns the number of
-    CPUs bound to, or None when NVML has no affinity to offer (RTM_BENCH_AFFINITY=0 turns it off)."""
-    if os.environ.get("RTM_BENCH_AFFINITY", "1") == "0":
-        return None
-    try:
-        import pynvml
-        pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByUUID(f"GPU-{uuid}".encode()) if uuid else pynvml.nvmlDeviceGetHandleByIndex(index)
-        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
-        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1}
-        cpus &= os.sched_getaffinity(0)
-        if not cpus:
-            return None
-        os.sched_setaffinity(0, cpus)
-        return len(cpus)
-    except Exception:
-        return None
-
-
 # ---------------------------------------------------------------------------
 def run_b200(args):
     import numpy as np
@@ -370,7 +349,6 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    affinity = bind_to_gpu_node(local, getattr(torch.cuda.get_device_properties(dev), "uuid", None)) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ge = importlib.import_module("__graft_entry__")
@@ -381,6 +359,13 @@ def run_b200(args):
     pkg = importlib.import_module("rtmodt_b200")
     from rtmodt_b200.workload import PostBackboneWorkload
     from rtmodt_b200 import sharding, _lib
+    affinity = None
+    if world > 1 and os.environ.get("RTM_BENCH_AFFINITY", "1") != "0":
+        # one process per GPU: run on the CPUs closest to it before the buffers are allocated (pinned staging buffers then
+        # land on the GPU's NUMA node).  On this pool it changes nothing - NVML names the same 32 CPUs for every GPU and an
+        # A/B at N = 4 gave 53.4 vs 53.5 GB/s per GPU; what differs is the box: 28.7, 40.7 and 53.4 GB/s per GPU in three
+        # 4-GPU runs of the same code
+        affinity = sharding.bind_process_to_gpu(local, getattr(torch.cuda.get_device_properties(dev), "uuid", None))
 
     tdt = {"bf16": torch.bfloat16, "f16": torch.float16, "f32": torch.float32}[args.head_dtype]
     S, F, K, W = args.streams, args.frames, args.steps, max(args.warmup, 3)
