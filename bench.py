@@ -478,7 +478,8 @@ def run_b200(args):
             roofline["dram_achieved"] = moved / (in_region_us * 1e-6) / 1e9
             roofline["dram_frac"] = roofline["dram_achieved"] / hbm_peak
             roofline["note"] = ("lazy box rows: DFL channels are read for candidates only, so traffic < algorithmic bytes; "
-                                "frac = algorithmic bytes / time / peak (contract), dram_frac = bytes moved / time / peak")
+                                "frac = algorithmic bytes / time / peak (contract; it can pass 1.0 in long regions for that reason), "
+                                "dram_frac = bytes moved / time / peak")
 
         extras = {}
         if not args.no_extras:
