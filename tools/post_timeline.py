@@ -38,7 +38,8 @@ steps = int(sys.argv[1]) if len(sys.argv) > 1 else 48
 S, F = 64, 16
 dev = torch.device("cuda", 0)
 wl = PostBackboneWorkload(S, F, first_stream=0, device=dev, dtype=torch.bfloat16)
-sb = pkg.StreamBatch(S, wl.zones, src_hw=(1080, 1920), classes=[0, 1, 2, 3, 5, 7], max_tracks=512, device=dev)
+sb = pkg.StreamBatch(S, wl.zones, src_hw=(1080, 1920), classes=[0, 1, 2, 3, 5, 7], max_tracks=512, device=dev,
+                     assignment=os.environ.get("TL_ASSIGNMENT", "greedy"))   # TL_ASSIGNMENT=lapjv: the optimal-assignment mode
 lib = sb.lib
 lib.rtm_debug_timeline.restype, lib.rtm_debug_timeline.argtypes = C.c_int, [C.c_void_p]
 buf = torch.zeros((16384 + 16 * 512 * 8,), dtype=torch.int64, device=dev)   # stage rows first, the step kernel's CTA rows behind
