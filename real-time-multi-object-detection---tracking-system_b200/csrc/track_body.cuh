@@ -381,6 +381,8 @@ constexpr int kAssignMaxSide = 32;
 struct AssignScratch {
   int n_edges;
   int limit_hit;
+  int n_open;                                // pairs left after the pairs alone in their row and column are settled
+  unsigned short open[kAssignMaxEdges];      // their indices, ascending
   unsigned short edge_row[kAssignMaxEdges], edge_col[kAssignMaxEdges];
   float edge_cost[kAssignMaxEdges];  // 1 - IoU in float32 (what the reference hands to lap), < 0 = settled
   // working set of the component solver (thread 0 only)
@@ -782,32 +784,63 @@ __device__ __forceinline__ int associate_optimal(const TrackPrefetch* pf, const 
     }
   }
   __syncthreads();
-  // ---- 3. the rest, component by component (thread 0) ----
+  // ---- 3. the rest, component by component ----
+  // The open pairs are listed in index order (in parallel); thread 0 then floods one component after the other from the
+  // first open pair, in the order a scan over all pairs would: membership of a row / column is a stamp in deg_row /
+  // deg_col (component number and local index, degrees are not needed any more), and a finished component's pairs
+  // leave the list - the walk over "every unsettled pair from e0 on" shrinks with every component instead of
+  // re-reading the settled ones and comparing against the member lists.
+  {
+    int run = 0;
+    for (int e0 = 0; e0 < E; e0 += THREADS) {
+      const int e = e0 + tid;
+      const bool is_open = e < E && !(sc->edge_cost[e] < 0.f);
+      int tot;
+      const int p = run + block_exclusive_count<THREADS>(is_open, s_scan, &tot);
+      if (is_open) sc->open[p] = static_cast<unsigned short>(e);
+      run += tot;
+    }
+    if (tid == 0) sc->n_open = run;
+    __syncthreads();
+  }
   if (tid == 0) {
     if (sc->n_edges > kAssignMaxEdges) sc->limit_hit = 1;  // the list is incomplete: components cannot be told from it
-    for (int e0 = 0; e0 < E && !sc->limit_hit; ++e0) {
-      if (sc->edge_cost[e0] < 0.f) continue;
+    int U = sc->n_open;
+    for (int comp = 1; U > 0 && !sc->limit_hit; ++comp) {
       int *rows = sc->rows, *cols = sc->cols, r = 0, c = 0;
       float* cost = sc->cost;
       bool too_big = false;
-      rows[r++] = sc->edge_row[e0];
-      cols[c++] = sc->edge_col[e0];
-      // flood: pull in every unsettled pair that shares a row or a column with the component
+      const int base = -(comp * 64) - 1;  // member k of this component carries base - k (kAssignMaxSide <= 64)
+      auto local = [&](const int mark) { return (mark <= base && mark > base - 64) ? base - mark : -1; };
+      const int e_first = sc->open[0];
+      rows[r] = sc->edge_row[e_first];
+      deg_row[rows[r]] = base - r;
+      ++r;
+      cols[c] = sc->edge_col[e_first];
+      deg_col[cols[c]] = base - c;
+      ++c;
+      // flood: pull in every open pair that shares a row or a column with the component
       for (bool grown = true; grown && !too_big;) {
         grown = false;
-        for (int e = e0; e < E && !too_big; ++e) {
-          if (sc->edge_cost[e] < 0.f) continue;
+        for (int k = 0; k < U && !too_big; ++k) {
+          const int e = sc->open[k];
           const int t = sc->edge_row[e], j = sc->edge_col[e];
-          bool has_r = false, has_c = false;
-          for (int k = 0; k < r; ++k) has_r |= rows[k] == t;
-          for (int k = 0; k < c; ++k) has_c |= cols[k] == j;
+          const bool has_r = local(deg_row[t]) >= 0, has_c = local(deg_col[j]) >= 0;
           if (has_r == has_c) continue;  // neither (not ours) or both (already in)
           if (!has_r) {
             if (r == kAssignMaxSide) too_big = true;
-            else rows[r++] = t;
+            else {
+              rows[r] = t;
+              deg_row[t] = base - r;
+              ++r;
+            }
           } else {
             if (c == kAssignMaxSide) too_big = true;
-            else cols[c++] = j;
+            else {
+              cols[c] = j;
+              deg_col[j] = base - c;
+              ++c;
+            }
           }
           grown = true;
         }
@@ -817,18 +850,18 @@ __device__ __forceinline__ int associate_optimal(const TrackPrefetch* pf, const 
         break;
       }
       for (int k = 0; k < r * c; ++k) cost[k] = 3.4e38f;
-      for (int e = e0; e < E; ++e) {
-        if (sc->edge_cost[e] < 0.f) continue;
-        int li = -1, lj = -1;
-        for (int k = 0; k < r; ++k)
-          if (rows[k] == sc->edge_row[e]) li = k;
-        for (int k = 0; k < c; ++k)
-          if (cols[k] == sc->edge_col[e]) lj = k;
+      int kept = 0;
+      for (int k = 0; k < U; ++k) {
+        const int e = sc->open[k];
+        const int li = local(deg_row[sc->edge_row[e]]), lj = local(deg_col[sc->edge_col[e]]);
         if (li >= 0 && lj >= 0) {
           cost[li * c + lj] = sc->edge_cost[e];
           sc->edge_cost[e] = -1.f;  // settled with this component
+        } else {
+          sc->open[kept++] = static_cast<unsigned short>(e);
         }
       }
+      U = kept;
       hungarian_component(sc, r, c, cost_limit * 0.5);
       const int* match = sc->match;
       for (int k = 0; k < r; ++k) {
